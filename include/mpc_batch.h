@@ -1,0 +1,158 @@
+/*
+ * Batched convex-MPC engine for sm_100a -- C ABI (additive; the reference has
+ * no batched entry point).  The legacy single-robot interface in
+ * convexMPC_interface.h is a batch-of-one client of this API.
+ *
+ * One "problem" is one robot x horizon instance of the reference's
+ * solve_mpc(update_data_t*, problem_setup*)
+ *   (/root/reference/src/MPC_Ctrl/SolverMPC.cpp:296-639):
+ * the condensed single-rigid-body QP  min 1/2 u'Hu + g'u  over the 12*h contact
+ * forces, subject to the friction pyramid and 0 <= fz <= gait*f_max per
+ * (step, leg), with swing legs eliminated (SolverMPC.cpp:441-525) and the
+ * optimum returned as 12*h numbers, zeros for swing legs (SolverMPC.cpp:545-557).
+ *
+ * Plain pointers and sizes only; no torch / Eigen types cross this boundary.
+ * Functions return 0 on success and a negative MPC_E_* code otherwise; they
+ * never throw and never fall back to a CPU solver.
+ */
+#ifndef QUADRUPED_MPC_BATCH_H
+#define QUADRUPED_MPC_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * Problem record: one contiguous, 16-byte aligned block per problem (array of
+ * records), so that a warp stages its whole problem with a single bulk copy.
+ * All scalars are IEEE fp32, exactly the types update_data_t/problem_setup
+ * carry (convexMPC_interface.h:13-38); I_body and mass are the constants the
+ * reference hard-codes in RobotState (RobotState.cpp:38-40, RobotState.h:23),
+ * promoted to per-problem inputs.
+ *
+ *   float index   field
+ *   0..2          p[3]      world position                (update_data_t::p)
+ *   3..5          v[3]      world velocity                (::v)
+ *   6..9          q[4]      orientation (w,x,y,z)         (::q)
+ *   10..12        w[3]      world angular velocity        (::w)
+ *   13..24        r[12]     foot - COM, r[axis*4+leg]     (::r)
+ *   25            yaw                                     (::yaw)
+ *   26            x_drag                                  (::x_drag)
+ *   27            alpha                                   (::alpha)
+ *   28..39        weights[12]                             (::weights)
+ *   40..42        I_body diagonal                         (RobotState.cpp:38)
+ *   43            mass                                    (RobotState.h:23)
+ *   44            dt                                      (problem_setup::dt)
+ *   45            mu                                      (problem_setup::mu)
+ *   46            f_max                                   (problem_setup::f_max)
+ *   47            reserved (0)
+ *   48..48+12h-1  traj[12*h], row-major per step          (::traj)
+ *   then          gait[4*h] bytes, gait[step*4+leg] 0/1   (::gait)
+ *   zero padding up to mpc_record_stride(h)
+ * ---------------------------------------------------------------------- */
+enum {
+  MPC_REC_P = 0, MPC_REC_V = 3, MPC_REC_Q = 6, MPC_REC_W = 10, MPC_REC_R = 13,
+  MPC_REC_YAW = 25, MPC_REC_XDRAG = 26, MPC_REC_ALPHA = 27, MPC_REC_WEIGHTS = 28,
+  MPC_REC_IBODY = 40, MPC_REC_MASS = 43, MPC_REC_DT = 44, MPC_REC_MU = 45,
+  MPC_REC_FMAX = 46, MPC_REC_RESERVED = 47, MPC_REC_TRAJ = 48
+};
+#define MPC_MAX_HORIZON 36 /* traj[12*36] in update_data_t caps h (convexMPC_interface.h:3,30) */
+
+/* Bytes between consecutive records for horizon h: 4*(48+12h)+4h rounded up to 16. */
+size_t mpc_record_stride(int horizon);
+/* Byte offset of the gait table inside a record. */
+size_t mpc_record_gait_offset(int horizon);
+
+/* Per-problem status word written next to the forces:
+ *   bits 0..7   code (MPC_STATUS_*), bits 8..31 working-set iterations taken. */
+enum {
+  MPC_STATUS_OPTIMAL = 0,      /* KKT-exact optimum of the reduced QP                      */
+  MPC_STATUS_MAX_ITER = 1,     /* iteration cap hit; forces are the last dual-feasible iterate */
+  MPC_STATUS_BAD_INPUT = 2,    /* non-finite input or mu/mass/inertia/dt <= 0; forces = 0  */
+  MPC_STATUS_NOT_PD = 3,       /* Hessian not positive definite (alpha <= 0 with zero weights) */
+  MPC_STATUS_NO_STANCE = 4     /* every leg in swing over the whole horizon: all-zero optimum */
+};
+#define MPC_STATUS_CODE(s) ((s) & 0xff)
+#define MPC_STATUS_ITERS(s) (((unsigned)(s)) >> 8)
+
+/* error codes */
+enum {
+  MPC_OK = 0, MPC_E_ARG = -1, MPC_E_CUDA = -2, MPC_E_NOMEM = -3, MPC_E_NODEVICE = -4
+};
+
+typedef struct mpc_batch mpc_batch_t; /* opaque engine handle, one per (device, horizon) */
+
+/* Creates an engine on CUDA device `device` for horizon `horizon`
+ * (1..MPC_MAX_HORIZON) able to solve up to `max_batch` problems per call.
+ * Fails with MPC_E_NODEVICE when no sm_100 device is present. */
+int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch);
+void mpc_batch_destroy(mpc_batch_t* eng);
+
+/* Device-resident solve, asynchronous on `cuda_stream` (a cudaStream_t; NULL =
+ * legacy default stream).
+ *   records_dev  [batch * mpc_record_stride(h)] bytes, 16-byte aligned
+ *   forces_dev   [batch * 12] fp32: first-horizon-step forces, force[leg*3+axis],
+ *                world frame, exactly what get_solution(0..11) returns upstream
+ *   solution_dev optional [batch * 12*h] fp64: the whole q_soln vector
+ *                (SolverMPC.cpp:545-557); NULL to skip
+ *   status_dev   optional [batch] int32 status words; NULL to skip            */
+int mpc_batch_solve_device(mpc_batch_t* eng, const void* records_dev, int batch,
+                           float* forces_dev, double* solution_dev,
+                           int32_t* status_dev, void* cuda_stream);
+
+/* Host-resident solve: stages records through pinned memory, runs the device
+ * solve, copies forces/solution/status back and synchronises. */
+int mpc_batch_solve_host(mpc_batch_t* eng, const void* records_host, int batch,
+                         float* forces_host, double* solution_host,
+                         int32_t* status_host);
+
+/* Debug / parity entry: assembles the reduced QP only and writes it out.
+ *   nvar_dev [batch] int32: reduced variable count nv = 3 * (#stance (step,leg))
+ *   H_dev    [batch * (12h)*(12h)] fp64 row-major, leading dimension 12h; top-left nv x nv used
+ *   g_dev    [batch * 12h] fp64                                             */
+int mpc_batch_assemble_device(mpc_batch_t* eng, const void* records_dev, int batch,
+                              int32_t* nvar_dev, double* H_dev, double* g_dev,
+                              void* cuda_stream);
+
+/* Shard-and-gather epilogue for a batch split over several GPUs: when set, the
+ * solve kernel also stores each problem's 12 forces straight into every peer's
+ * gather buffer at row (rank_offset + i) through NVLink peer mappings, which
+ * replaces the separate all-gather.  peers[k] is the base of rank k's
+ * [world_batch * 12] fp32 gather buffer as mapped into THIS process (or NULL to
+ * skip rank k); pass n_peers = 0 to turn the epilogue off. */
+int mpc_batch_set_gather_peers(mpc_batch_t* eng, float* const* peers, int n_peers,
+                               int rank_offset);
+
+/* Iteration cap of the active-set loop (working-set additions); default 4000.
+ * The reference caps qpOASES at nWSR = 100 (SolverMPC.cpp:435) and returns stale
+ * memory beyond it; this engine reports MPC_STATUS_MAX_ITER instead. */
+int mpc_batch_set_max_iterations(mpc_batch_t* eng, int max_iter);
+
+/* Turns CUDA-event timing of the solve kernels on or off (off by default). */
+int mpc_batch_set_timing(mpc_batch_t* eng, int enabled);
+
+/* Size classes the engine sorts problems into (by reduced variable count).
+ * info[6] = { nv_cap, m_cap, threads per CTA, grid, shared-memory bytes per CTA,
+ *             1 if the QP tile lives in shared memory (0: per-CTA global slab) }. */
+int mpc_batch_num_classes(const mpc_batch_t* eng);
+int mpc_batch_class_info(const mpc_batch_t* eng, int idx, int* info);
+
+/* Number of kernels the engine has launched since creation (for accounting). */
+long mpc_batch_kernel_launches(const mpc_batch_t* eng);
+/* Device time in ms of the solve kernels of the most recent solve call, measured
+ * with CUDA events on the call's stream (synchronises that stream). */
+float mpc_batch_last_solve_kernel_ms(mpc_batch_t* eng);
+/* Human-readable description of the last error on this engine ("" if none). */
+const char* mpc_batch_last_error(const mpc_batch_t* eng);
+/* Library-level: text of the last error when no engine exists (create failed). */
+const char* mpc_last_error(void);
+/* Horizon the engine was built for / its record stride. */
+int mpc_batch_horizon(const mpc_batch_t* eng);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,772 @@
+// Per-problem convex-MPC algorithm: record -> reduced condensed QP -> exact optimum.
+//
+// This header is the body of the sm_100a solve kernel (mpc_kernels.cu includes it
+// with one CTA per problem).  It is written against a tiny execution context
+// (thread id, thread count, barrier, block reductions) so that the very same
+// source also compiles as single-thread host code for the logic tests in
+// tests/emu/ (TEST-ONLY build; never linked into libquadruped_mpc_b200.so --
+// the product has no CPU path).
+//
+// What it replaces, in the reference (/root/reference/src/MPC_Ctrl):
+//   RobotState::set                      RobotState.cpp:9-43
+//   quat_to_rpy, x_0, I_world            SolverMPC.cpp:257-267, 314-319
+//   ct_ss_mats, cross_mat                SolverMPC.cpp:226-254
+//   c2qp (expm + horizon stacking)       SolverMPC.cpp:87-125
+//   weights / X_d / U_b / fmat           SolverMPC.cpp:335-378
+//   qH, qg                               SolverMPC.cpp:395-399
+//   swing-leg elimination                SolverMPC.cpp:431-525
+//   qpOASES QProblem::init + scatter     SolverMPC.cpp:527-557
+//
+// How (B200-first, nothing of the reference's dense route is materialised):
+//   * A_c is nilpotent (A^3 = 0), so exp(k dt A) = I + k dt A + (k dt)^2/2 A^2 and
+//     Phi_k := A_d^k B_d = C0 + k C1 + k^2 C2 exactly.  B_qp (13h x 12h), the dense
+//     S (13h x 13h) and the 25x25 matrix exponential never exist.
+//   * H[(i,.),(j,.)] = 2 sum_{a,b} s_ab(i,j) C_a' Q C_b + 2 alpha I with integer
+//     sums s_ab(i,j) = sum_{r>=max(i,j)} (r-i)^a (r-j)^b: 9 FMAs per entry instead of
+//     a 13h-long dot product; only stance (step,leg) columns are ever formed.
+//   * The reduced H is inverted in place (symmetric sweep) and the QP is solved by
+//     the Goldfarb-Idnani dual active-set method on the explicit inverse: every
+//     constraint of the friction pyramid touches at most two variables, so the
+//     Schur complement entries are O(1) table look-ups and one working-set change
+//     costs O(nv*m) fully parallel work.
+//   * All arithmetic is fp64 (the reference assembles in fp32 and solves in fp64;
+//     fp64 assembly lands inside the reference's own fp32 rounding cloud).
+#ifndef QUADRUPED_MPC_CORE_H
+#define QUADRUPED_MPC_CORE_H
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/mpc_batch.h"
+
+#if defined(__CUDACC__)
+#define MPC_HD __device__ __forceinline__
+#define MPC_HDN __device__ __noinline__
+#else
+#define MPC_HD inline
+#define MPC_HDN inline
+#endif
+
+namespace mpc {
+
+// extra status codes (additive to include/mpc_batch.h) used between kernels
+enum { STATUS_RETRY_BIG = 0x40 };  // working set outgrew the fast-memory tile: re-queued to the big class
+
+// ---------------------------------------------------------------------------
+// Workspace layout.  `fast` is shared memory on the device; Hm and T live in fast
+// memory when they fit and in a per-CTA global (L2-resident) slab otherwise.
+// ---------------------------------------------------------------------------
+struct Layout {
+  int h;        // horizon
+  int nv_cap;   // largest reduced variable count this workspace can hold
+  int m_cap;    // largest working set (active constraints) it can hold
+  int ld;       // leading dimension of Hm (odd -> conflict-free column walks)
+  int ldT;      // leading dimension of T
+  int big_in_fast;  // 1: Hm and T are carved from `fast`; 0: from the global slab
+  // byte offsets into `fast`
+  int off_scal, off_g, off_x, off_ints, off_union, off_red, off_Hm, off_T;
+  int fast_bytes;
+  // byte offsets into the global slab (when !big_in_fast)
+  size_t slab_Hm, slab_T, slab_bytes;
+};
+
+struct Scalars {
+  int nv, ns, m, status, iters, p, kdrop, full, done;
+  double sp, t1, t2, t, up, vnp, znp, dreg;
+};
+
+constexpr int kAsmDoubles(int h) { return 3 * 156 + 9 * 144 + 39 + 12 * h; }
+constexpr int kRedDoubles = 40;
+
+inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// The same function sizes the launch (host) and carves the pointers (device).
+inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast) {
+  Layout L;
+  L.h = h;
+  L.nv_cap = nv_cap;
+  L.m_cap = m_cap;
+  L.ld = nv_cap | 1;
+  L.ldT = m_cap | 1;
+  L.big_in_fast = big_in_fast;
+  int o = 0;
+  L.off_scal = o;
+  o += (int)((sizeof(Scalars) + 15) / 16 * 16);
+  L.off_g = o;
+  o += 8 * nv_cap;
+  L.off_x = o;
+  o += 8 * nv_cap;
+  // ints: stance[4h] (k = step*4+leg of every stance pair), posk[4h], act[6*4h], W[m_cap+1]
+  L.off_ints = o;
+  o += 4 * (4 * h + 4 * h + 24 * h + m_cap + 1);
+  o = (o + 15) / 16 * 16;
+  L.off_union = o;
+  int gi = nv_cap * 3 + (m_cap + 1) * 4;  // z, cvec, ck, w, r, u, tcol
+  int un = kAsmDoubles(h);
+  int t_doubles = m_cap * L.ldT;
+  int hm_doubles = nv_cap * L.ld;
+  if (big_in_fast) gi += t_doubles;
+  if (gi > un) un = gi;
+  o += 8 * un;
+  L.off_red = o;
+  o += 8 * kRedDoubles;
+  L.off_Hm = o;
+  L.off_T = L.off_union;  // T sits at the start of the GI part of the union
+  if (big_in_fast) o += 8 * hm_doubles;
+  L.fast_bytes = (o + 15) / 16 * 16;
+  L.slab_Hm = 0;
+  L.slab_T = (size_t)hm_doubles * 8;
+  L.slab_bytes = big_in_fast ? 0 : ((size_t)(hm_doubles + t_doubles) * 8 + 255) / 256 * 256;
+  return L;
+}
+
+struct Work {
+  Scalars* sc;
+  double *g, *x, *Hm, *T;
+  int *stance, *posk, *act, *W;
+  // assembly view of the union
+  double *C, *M, *xs, *qe;
+  // active-set view of the union
+  double *z, *cvec, *ck, *w, *r, *u, *tcol;
+  double* red;
+  int ld, ldT, nv_cap, m_cap, h;
+};
+
+MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
+  Work k;
+  k.sc = (Scalars*)(fast + L.off_scal);
+  k.g = (double*)(fast + L.off_g);
+  k.x = (double*)(fast + L.off_x);
+  int* ip = (int*)(fast + L.off_ints);
+  k.stance = ip;
+  k.posk = ip + 4 * L.h;
+  k.act = ip + 8 * L.h;
+  k.W = ip + 32 * L.h;
+  double* un = (double*)(fast + L.off_union);
+  k.C = un;
+  k.M = un + 3 * 156;
+  k.xs = k.M + 9 * 144;
+  k.qe = k.xs + 39;
+  double* gi = un;
+  if (L.big_in_fast) {
+    k.T = gi;
+    gi += L.m_cap * L.ldT;
+    k.Hm = (double*)(fast + L.off_Hm);
+  } else {
+    k.Hm = (double*)(slab + L.slab_Hm);
+    k.T = (double*)(slab + L.slab_T);
+  }
+  k.z = gi;
+  k.cvec = k.z + L.nv_cap;
+  k.ck = k.cvec + L.nv_cap;
+  k.w = k.ck + L.nv_cap;
+  k.r = k.w + (L.m_cap + 1);
+  k.u = k.r + (L.m_cap + 1);
+  k.tcol = k.u + (L.m_cap + 1);
+  k.red = (double*)(fast + L.off_red);
+  k.ld = L.ld;
+  k.ldT = L.ldT;
+  k.nv_cap = L.nv_cap;
+  k.m_cap = L.m_cap;
+  k.h = L.h;
+  return k;
+}
+
+// ---------------------------------------------------------------------------
+// Execution context.  Device: one CTA.  Host emulation: one thread.
+// ---------------------------------------------------------------------------
+#if defined(__CUDACC__)
+struct Cta {
+  int tid, nt;
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+#endif
+struct OneThread {
+  int tid, nt;
+  inline void sync() const {}
+};
+
+#define MPC_FOR(i, n) for (int i = cx.tid; i < (n); i += cx.nt)
+#define MPC_ONE if (cx.tid == 0)
+
+// Block-wide argmin of (val, idx) pairs; every thread passes its local best and
+// gets the global best back.  Ties resolve to the smaller idx (deterministic).
+template <class Cx>
+MPC_HD void block_argmin(const Cx& cx, double* red, double& val, int& idx) {
+#if defined(__CUDA_ARCH__)
+  for (int o = 16; o > 0; o >>= 1) {
+    double v2 = __shfl_xor_sync(0xffffffffu, val, o);
+    int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (v2 < val || (v2 == val && i2 < idx)) { val = v2; idx = i2; }
+  }
+  const int nw = (cx.nt + 31) >> 5;
+  int* redi = (int*)(red + 16);
+  cx.sync();  // scratch may still be read from a previous reduction
+  if ((cx.tid & 31) == 0) { red[cx.tid >> 5] = val; redi[cx.tid >> 5] = idx; }
+  cx.sync();
+  val = red[0];
+  idx = redi[0];
+  for (int w = 1; w < nw; w++) {
+    double v2 = red[w];
+    int i2 = redi[w];
+    if (v2 < val || (v2 == val && i2 < idx)) { val = v2; idx = i2; }
+  }
+#else
+  (void)cx; (void)red; (void)val; (void)idx;
+#endif
+}
+
+template <class Cx>
+MPC_HD double block_sum(const Cx& cx, double* red, double val) {
+#if defined(__CUDA_ARCH__)
+  for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+  const int nw = (cx.nt + 31) >> 5;
+  cx.sync();
+  if ((cx.tid & 31) == 0) red[cx.tid >> 5] = val;
+  cx.sync();
+  double s = 0;
+  for (int w = 0; w < nw; w++) s += red[w];
+  return s;
+#else
+  (void)cx; (void)red;
+  return val;
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// Constraint catalogue.  Every stance pair j (reduced variables 3j..3j+2 =
+// fx,fy,fz) carries six one-sided rows  n.x >= b  (SolverMPC.cpp:361-378 f_block,
+// lower bound 0 :428-429, upper bounds U_b :349-358; the four 5e10 upper bounds
+// on the cone rows are not constraints):
+//   type 0:  fx/mu + fz >= 0     type 1: -fx/mu + fz >= 0
+//   type 2:  fy/mu + fz >= 0     type 3: -fy/mu + fz >= 0
+//   type 4:  fz >= 0             type 5: -fz >= -gait*f_max
+// A row is (ia, ca, iz=3j+2, cz): n = ca*e_ia + cz*e_iz (ia == iz, ca = 0 for 4,5).
+// ---------------------------------------------------------------------------
+struct Row {
+  int ia, iz;
+  double ca, cz;
+};
+MPC_HD Row make_row(int c, double mu_inv) {
+  const int j = c / 6, t = c - 6 * j;
+  Row r;
+  r.iz = 3 * j + 2;
+  r.cz = (t == 5) ? -1.0 : 1.0;
+  if (t < 2) { r.ia = 3 * j; r.ca = (t == 0) ? mu_inv : -mu_inv; }
+  else if (t < 4) { r.ia = 3 * j + 1; r.ca = (t == 2) ? mu_inv : -mu_inv; }
+  else { r.ia = r.iz; r.ca = 0.0; }
+  return r;
+}
+// n_a' Minv n_b for two catalogue rows: at most four look-ups
+MPC_HD double row_minv_row(const double* Hm, int ld, const Row& a, const Row& b) {
+  double s = a.cz * b.cz * Hm[a.iz * ld + b.iz];
+  if (a.ca != 0.0) s += a.ca * b.cz * Hm[a.ia * ld + b.iz];
+  if (b.ca != 0.0) s += a.cz * b.ca * Hm[a.iz * ld + b.ia];
+  if (a.ca != 0.0 && b.ca != 0.0) s += a.ca * b.ca * Hm[a.ia * ld + b.ia];
+  return s;
+}
+
+MPC_HD bool finite_f(float v) { return v == v && fabsf(v) <= 3.0e38f; }
+
+// ---------------------------------------------------------------------------
+// Stage 1: dynamics, discretisation polynomial, QP assembly (reduced, fp64).
+// Leaves nv, ns, stance[], posk[], Hm (= reduced qH), g (= reduced qg) behind.
+// ---------------------------------------------------------------------------
+template <class Cx>
+MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, const Work& k) {
+  const int h = k.h;
+  Scalars* sc = k.sc;
+  double* A = k.M;          // 13x13   (M region is free until the C_a are final)
+  double* B = A + 169;      // 13x12
+  double* t1 = B + 156;     // 13x12 scratch
+  double* t2 = t1 + 156;    // 13x12 scratch
+  double* C0 = k.C;
+  double* C1 = C0 + 156;
+  double* C2 = C1 + 156;
+  double* x0 = k.xs;        // 13
+  double* Ax0 = x0 + 13;
+  double* A2x0 = Ax0 + 13;
+
+  // ---- stance list / swing elimination (SolverMPC.cpp:441-469) and input check ----
+  MPC_ONE {
+    int status = MPC_STATUS_OPTIMAL;
+    for (int i = 0; i < MPC_REC_TRAJ + 12 * h; i++)
+      if (!finite_f(rec[i])) status = MPC_STATUS_BAD_INPUT;
+    const float fmax = rec[MPC_REC_FMAX];
+    if (!(rec[MPC_REC_MU] > 0.f) || !(rec[MPC_REC_MASS] > 0.f) || !(rec[MPC_REC_DT] > 0.f) ||
+        !(rec[MPC_REC_IBODY] > 0.f) || !(rec[MPC_REC_IBODY + 1] > 0.f) || !(rec[MPC_REC_IBODY + 2] > 0.f) ||
+        !(fmax >= 0.f))
+      status = MPC_STATUS_BAD_INPUT;
+    int ns = 0;
+    for (int kk = 0; kk < 4 * h; kk++) {
+      // U_b(5k+4) = gait[k]*f_max in float; the row is eliminated when it is "near zero"
+      const float ub = (float)gait[kk] * fmax;
+      const bool swing = ((double)ub < 0.01 && (double)ub > -0.01);
+      if (!swing) { k.stance[ns] = kk; k.posk[kk] = ns; ns++; }
+      else k.posk[kk] = -1;
+    }
+    if (status == MPC_STATUS_OPTIMAL && ns == 0) status = MPC_STATUS_NO_STANCE;
+    sc->ns = ns;
+    sc->nv = 3 * ns;
+    sc->status = status;
+    sc->m = 0;
+    sc->iters = 0;
+  }
+  // ---- A_c, B_c (SolverMPC.cpp:235-254) --------------------------------------
+  MPC_FOR(i, 169 + 156) k.M[i] = 0.0;
+  cx.sync();
+  if (sc->status != MPC_STATUS_OPTIMAL) return;
+  MPC_ONE {
+    const double yaw = (double)rec[MPC_REC_YAW];
+    const double yc = cos(yaw), ys = sin(yaw);
+    const double R[3][3] = {{yc, -ys, 0}, {ys, yc, 0}, {0, 0, 1}};  // RobotState.cpp:33-35
+    const double Ib[3] = {(double)rec[MPC_REC_IBODY], (double)rec[MPC_REC_IBODY + 1], (double)rec[MPC_REC_IBODY + 2]};
+    // quat_to_rpy (SolverMPC.cpp:257-267), q = (w,x,y,z)
+    const double qw = rec[MPC_REC_Q], qx = rec[MPC_REC_Q + 1], qy = rec[MPC_REC_Q + 2], qz = rec[MPC_REC_Q + 3];
+    double as = -2. * (qx * qz - qw * qy);
+    if (!(as < .99999)) as = .99999;
+    const double rpy0 = atan2(2. * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
+    const double rpy1 = asin(as);
+    const double rpy2 = atan2(2. * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
+    x0[0] = rpy2; x0[1] = rpy1; x0[2] = rpy0;
+    for (int i = 0; i < 3; i++) {
+      x0[3 + i] = rec[MPC_REC_P + i];
+      x0[6 + i] = rec[MPC_REC_W + i];
+      x0[9 + i] = rec[MPC_REC_V + i];
+    }
+    x0[12] = (double)-9.8f;
+    // I_world = R I_body R' and its inverse (SolverMPC.cpp:319, 247)
+    double Iw[3][3];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double acc = 0;
+        for (int q = 0; q < 3; q++) acc += (R[i][q] * Ib[q]) * R[j][q];
+        Iw[i][j] = acc;
+      }
+    const double det = Iw[0][0] * (Iw[1][1] * Iw[2][2] - Iw[1][2] * Iw[2][1]) -
+                       Iw[0][1] * (Iw[1][0] * Iw[2][2] - Iw[1][2] * Iw[2][0]) +
+                       Iw[0][2] * (Iw[1][0] * Iw[2][1] - Iw[1][1] * Iw[2][0]);
+    double Ii[3][3];
+    Ii[0][0] = (Iw[1][1] * Iw[2][2] - Iw[1][2] * Iw[2][1]) / det;
+    Ii[0][1] = (Iw[0][2] * Iw[2][1] - Iw[0][1] * Iw[2][2]) / det;
+    Ii[0][2] = (Iw[0][1] * Iw[1][2] - Iw[0][2] * Iw[1][1]) / det;
+    Ii[1][0] = (Iw[1][2] * Iw[2][0] - Iw[1][0] * Iw[2][2]) / det;
+    Ii[1][1] = (Iw[0][0] * Iw[2][2] - Iw[0][2] * Iw[2][0]) / det;
+    Ii[1][2] = (Iw[0][2] * Iw[1][0] - Iw[0][0] * Iw[1][2]) / det;
+    Ii[2][0] = (Iw[1][0] * Iw[2][1] - Iw[1][1] * Iw[2][0]) / det;
+    Ii[2][1] = (Iw[0][1] * Iw[2][0] - Iw[0][0] * Iw[2][1]) / det;
+    Ii[2][2] = (Iw[0][0] * Iw[1][1] - Iw[0][1] * Iw[1][0]) / det;
+    A[3 * 13 + 9] = 1.0;
+    A[11 * 13 + 9] = (double)rec[MPC_REC_XDRAG];
+    A[4 * 13 + 10] = 1.0;
+    A[5 * 13 + 11] = 1.0;
+    A[11 * 13 + 12] = 1.0;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) A[i * 13 + 6 + j] = R[j][i];
+    const double minv = 1.0 / (double)rec[MPC_REC_MASS];
+    for (int b = 0; b < 4; b++) {
+      const double rx = rec[MPC_REC_R + b], ry = rec[MPC_REC_R + 4 + b], rz = rec[MPC_REC_R + 8 + b];
+      const double cm[3][3] = {{0, -rz, ry}, {rz, 0, -rx}, {-ry, rx, 0}};
+      for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) {
+          double acc = 0;
+          for (int q = 0; q < 3; q++) acc += Ii[i][q] * cm[q][j];
+          B[(6 + i) * 12 + b * 3 + j] = acc;
+        }
+        B[(9 + i) * 12 + b * 3 + i] = minv;
+      }
+    }
+  }
+  cx.sync();
+  const double dt = (double)rec[MPC_REC_DT];
+  // ---- exact discretisation: B_d = dt B + dt^2/2 AB + dt^3/6 A^2 B (c2qp, SolverMPC.cpp:87-101) ----
+  MPC_FOR(e, 156) {  // t1 = A B
+    const int i = e / 12, j = e - 12 * i;
+    double acc = 0;
+    for (int q = 0; q < 13; q++) acc += A[i * 13 + q] * B[q * 12 + j];
+    t1[e] = acc;
+  }
+  MPC_FOR(e, 13) {  // A x0
+    double acc = 0;
+    for (int q = 0; q < 13; q++) acc += A[e * 13 + q] * x0[q];
+    Ax0[e] = acc;
+  }
+  cx.sync();
+  MPC_FOR(e, 156) {  // t2 = A (A B)
+    const int i = e / 12, j = e - 12 * i;
+    double acc = 0;
+    for (int q = 0; q < 13; q++) acc += A[i * 13 + q] * t1[q * 12 + j];
+    t2[e] = acc;
+  }
+  MPC_FOR(e, 13) {  // A^2 x0
+    double acc = 0;
+    for (int q = 0; q < 13; q++) acc += A[e * 13 + q] * Ax0[q];
+    A2x0[e] = acc;
+  }
+  cx.sync();
+  MPC_FOR(e, 156) C0[e] = dt * B[e] + (dt * dt / 2.0) * t1[e] + (dt * dt * dt / 6.0) * t2[e];
+  cx.sync();
+  // ---- Phi_k = A_d^k B_d = C0 + k C1 + k^2 C2 with C1 = dt A B_d, C2 = dt^2/2 A^2 B_d ----
+  MPC_FOR(e, 156) {
+    const int i = e / 12, j = e - 12 * i;
+    double acc = 0;
+    for (int q = 0; q < 13; q++) acc += A[i * 13 + q] * C0[q * 12 + j];
+    t1[e] = acc;
+  }
+  cx.sync();
+  MPC_FOR(e, 156) {
+    const int i = e / 12, j = e - 12 * i;
+    double acc = 0;
+    for (int q = 0; q < 13; q++) acc += A[i * 13 + q] * t1[q * 12 + j];
+    C1[e] = dt * t1[e];
+    C2[e] = (dt * dt / 2.0) * acc;
+  }
+  // ---- weighted tracking error q_e[r] = Q (A_d^{r+1} x0 - x_d[r]) (SolverMPC.cpp:335-347,399) ----
+  MPC_FOR(e, 12 * h) {
+    const int r = e / 12, i = e - 12 * r;
+    const double tt = (double)(r + 1) * dt;
+    const double xr = x0[i] + tt * Ax0[i] + (tt * tt / 2.0) * A2x0[i];
+    k.qe[e] = (double)rec[MPC_REC_WEIGHTS + i] * (xr - (double)rec[MPC_REC_TRAJ + e]);
+  }
+  cx.sync();
+  // ---- M_ab = C_a' Q C_b (12x12 each).  M overlays A,B,t1,t2, which are dead: the
+  // barrier above is the last point anything reads them. ----
+  MPC_FOR(e, 9 * 144) {
+    const int ab = e / 144, ij = e - 144 * ab;
+    const int a = ab / 3, b = ab - 3 * a, i = ij / 12, j = ij - 12 * i;
+    const double* Ca = C0 + 156 * a;
+    const double* Cb = C0 + 156 * b;
+    double s = 0;
+    for (int q = 0; q < 12; q++) s += Ca[q * 12 + i] * ((double)rec[MPC_REC_WEIGHTS + q] * Cb[q * 12 + j]);
+    k.M[e] = s;
+  }
+  cx.sync();
+  // ---- reduced gradient: g_v = 2 sum_{r>=j} Phi_{r-j}[:,c]' q_e[r] (SolverMPC.cpp:399) ----
+  const int nv = sc->nv, ns = sc->ns;
+  MPC_FOR(v, nv) {
+    const int sidx = v / 3, ax = v - 3 * sidx;
+    const int kk = k.stance[sidx], j = kk >> 2, c = (kk & 3) * 3 + ax;
+    double acc = 0;
+    for (int r = j; r < h; r++) {
+      const double kd = (double)(r - j), kd2 = kd * kd;
+      const double* q = k.qe + 12 * r;
+      double s = 0;
+      for (int row = 0; row < 12; row++)
+        s += (C0[row * 12 + c] + kd * C1[row * 12 + c] + kd2 * C2[row * 12 + c]) * q[row];
+      acc += s;
+    }
+    k.g[v] = 2.0 * acc;
+  }
+  // ---- reduced Hessian, one 3x3 block per stance pair (a >= b) (SolverMPC.cpp:395) ----
+  const double alpha = (double)rec[MPC_REC_ALPHA];
+  const int nblk = ns * (ns + 1) / 2;
+  MPC_FOR(e, nblk) {
+    // e -> (a, b) with a >= b:  a = floor((sqrt(8e+1)-1)/2)
+    int a = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+    while ((a + 1) * (a + 2) / 2 <= e) a++;
+    while (a * (a + 1) / 2 > e) a--;
+    const int b = e - a * (a + 1) / 2;
+    const int ka = k.stance[a], kb = k.stance[b];
+    const int i = ka >> 2, la = ka & 3, j = kb >> 2, lb = kb & 3;  // i >= j (stance[] is ascending)
+    const int d = i - j, n = h - 1 - i;
+    double s[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int q = 0; q <= n; q++) {  // exact small-integer sums
+      const double p1 = (double)q, p2 = p1 * p1, r1 = (double)(q + d), r2 = r1 * r1;
+      s[0][0] += 1.0; s[0][1] += r1; s[0][2] += r2;
+      s[1][0] += p1; s[1][1] += p1 * r1; s[1][2] += p1 * r2;
+      s[2][0] += p2; s[2][1] += p2 * r1; s[2][2] += p2 * r2;
+    }
+    for (int ax = 0; ax < 3; ax++)
+      for (int bx = 0; bx < 3; bx++) {
+        const int ci = la * 3 + ax, cj = lb * 3 + bx;
+        double acc = 0;
+        for (int pa = 0; pa < 3; pa++)
+          for (int pb = 0; pb < 3; pb++) acc += s[pa][pb] * k.M[(pa * 3 + pb) * 144 + ci * 12 + cj];
+        double val = 2.0 * acc;
+        if (a == b && ax == bx) val += 2.0 * alpha;
+        k.Hm[(3 * a + ax) * k.ld + 3 * b + bx] = val;
+        k.Hm[(3 * b + bx) * k.ld + 3 * a + ax] = val;
+      }
+  }
+  cx.sync();
+}
+
+// ---------------------------------------------------------------------------
+// Stage 2: Hm <- Hm^{-1} in place by symmetric sweeps (no pivoting: Hm is SPD).
+// After sweeping every index the array holds -H^{-1}; the sign is flipped at the
+// end.  A non-positive pivot means H is not positive definite.
+// ---------------------------------------------------------------------------
+template <class Cx>
+MPC_HD void invert_spd(const Cx& cx, const Work& k) {
+  Scalars* sc = k.sc;
+  const int nv = sc->nv, ld = k.ld;
+  double* Hm = k.Hm;
+  double* ck = k.ck;
+  // thread -> (row group, column): columns fastest so that a warp shares one row
+  int cols = 1;
+  while (cols < nv && cols < cx.nt) cols <<= 1;
+  const int rgroups = cx.nt / cols > 0 ? cx.nt / cols : 1;
+  const int jc = cx.tid % cols, ig = cx.tid / cols;
+  for (int p = 0; p < nv; p++) {
+    const double d = Hm[p * ld + p];
+    if (!(d > 0.0)) {  // uniform: every thread reads the same pivot
+      cx.sync();
+      MPC_ONE sc->status = MPC_STATUS_NOT_PD;
+      cx.sync();
+      return;
+    }
+    MPC_FOR(i, nv) ck[i] = Hm[p * ld + i];
+    cx.sync();
+    const double dinv = 1.0 / d;
+    if (ig < rgroups) {
+      for (int j = jc; j < nv; j += cols) {
+        const double cj = ck[j] * dinv;
+        for (int i = ig; i < nv; i += rgroups) {
+          double val;
+          if (i == p) val = (j == p) ? -dinv : cj;
+          else if (j == p) val = ck[i] * dinv;
+          else val = Hm[i * ld + j] - ck[i] * cj;
+          Hm[i * ld + j] = val;
+        }
+      }
+    }
+    cx.sync();
+  }
+  if (ig < rgroups)
+    for (int j = jc; j < nv; j += cols)
+      for (int i = ig; i < nv; i += rgroups) Hm[i * ld + j] = -Hm[i * ld + j];
+  cx.sync();
+}
+
+// ---------------------------------------------------------------------------
+// Stage 3: Goldfarb-Idnani dual active-set iterations on the explicit inverse.
+//   x  = -Minv g (unconstrained optimum), working set W empty, duals u = 0;
+//   repeat: pick the most violated row p; move along z = Minv(n_p - N r),
+//   r = T N' Minv n_p with T = (N' Minv N)^{-1} kept explicitly (bordered on an
+//   add, Schur-downdated on a drop), until p is satisfied or blocked duals leave.
+// Returns through sc->status.  Exactness: the loop ends only when no row is
+// violated by more than `vtol`, every dual is >= 0 by construction and x is the
+// stationary point of its working set, i.e. the KKT point of the strictly convex QP.
+// ---------------------------------------------------------------------------
+template <class Cx>
+MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait, const Work& k, int max_iter) {
+  Scalars* sc = k.sc;
+  const int nv = sc->nv, ns = sc->ns, ld = k.ld, ldT = k.ldT;
+  const int ncons = 6 * ns;
+  const double mu_inv = 1.0 / (double)rec[MPC_REC_MU];
+  const double fmax = (double)rec[MPC_REC_FMAX];
+  const double* Hm = k.Hm;
+  double* T = k.T;
+  const double vtol = 1e-9;
+
+  MPC_FOR(i, nv) {
+    double acc = 0;
+    for (int j = 0; j < nv; j++) acc += Hm[j * ld + i] * k.g[j];
+    k.x[i] = -acc;
+  }
+  MPC_FOR(c, ncons) k.act[c] = -1;
+  cx.sync();
+
+  for (;;) {
+    // ---- most violated row -------------------------------------------------
+    double best = -vtol;
+    int bidx = 0x7fffffff;
+    MPC_FOR(c, ncons) {
+      if (k.act[c] >= 0) continue;
+      const Row rw = make_row(c, mu_inv);
+      const int t = c % 6;
+      const double b = (t == 5) ? -(double)((float)gait[k.stance[c / 6]] * (float)fmax) : 0.0;
+      const double sl = rw.ca * k.x[rw.ia] + rw.cz * k.x[rw.iz] - b;
+      if (sl < best) { best = sl; bidx = c; }
+    }
+    block_argmin(cx, k.red, best, bidx);
+    if (bidx == 0x7fffffff) break;  // uniform
+    if (sc->iters >= max_iter) {
+      cx.sync();
+      MPC_ONE sc->status = MPC_STATUS_MAX_ITER;
+      cx.sync();
+      break;
+    }
+    const int p = bidx;
+    const Row rp = make_row(p, mu_inv);
+    const double bp = (p % 6 == 5) ? -(double)((float)gait[k.stance[p / 6]] * (float)fmax) : 0.0;
+    cx.sync();
+    MPC_ONE { sc->iters++; sc->up = 0.0; }
+    cx.sync();
+    // ---- inner loop: partial steps drop blocking rows until p can be added ----
+    bool fail = false;
+    for (;;) {
+      const int m = sc->m;
+      // w_a = n_a' Minv n_p,  vnp = n_p' Minv n_p
+      MPC_FOR(a, m) {
+        const Row ra = make_row(k.W[a], mu_inv);
+        k.w[a] = row_minv_row(Hm, ld, ra, rp);
+      }
+      const double vnp = row_minv_row(Hm, ld, rp, rp);
+      cx.sync();
+      // r = T w   (T symmetric: walk columns for contiguous reads)
+      MPC_FOR(a, m) {
+        double acc = 0;
+        for (int b = 0; b < m; b++) acc += T[b * ldT + a] * k.w[b];
+        k.r[a] = acc;
+      }
+      cx.sync();
+      // znp = vnp - w.r ; t1 = min_{r_a > 0} u_a / r_a
+      double part = 0, tbest = 1e300;
+      int tidx = 0x7fffffff;
+      MPC_FOR(a, m) {
+        part += k.w[a] * k.r[a];
+        if (k.r[a] > 0.0) {
+          const double q = k.u[a] / k.r[a];
+          if (q < tbest) { tbest = q; tidx = a; }
+        }
+      }
+      const double wr = block_sum(cx, k.red, part);
+      block_argmin(cx, k.red, tbest, tidx);
+      const double znp = vnp - wr;
+      const bool dependent = !(znp > 1e-11 * vnp);
+      const double spc = rp.ca * k.x[rp.ia] + rp.cz * k.x[rp.iz] - bp;  // current slack of p (< 0)
+      const double t2 = dependent ? 1e300 : -spc / znp;
+      const double t1 = (tidx == 0x7fffffff) ? 1e300 : tbest;
+      const double t = t1 < t2 ? t1 : t2;
+      if (t >= 1e300) { fail = true; break; }  // infeasible (cannot happen: f = 0 is feasible)
+      // coefficient vector c = n_p - N r, gathered per variable through act[]
+      MPC_FOR(v, nv) {
+        const int j = v / 3, ax = v - 3 * j;
+        double cv = 0.0;
+        if (rp.iz == v) cv += rp.cz;
+        if (rp.ca != 0.0 && rp.ia == v) cv += rp.ca;
+        const int* aj = k.act + 6 * j;
+        if (ax == 0) {
+          if (aj[0] >= 0) cv -= k.r[aj[0]] * mu_inv;
+          if (aj[1] >= 0) cv += k.r[aj[1]] * mu_inv;
+        } else if (ax == 1) {
+          if (aj[2] >= 0) cv -= k.r[aj[2]] * mu_inv;
+          if (aj[3] >= 0) cv += k.r[aj[3]] * mu_inv;
+        } else {
+          for (int q = 0; q < 5; q++)
+            if (aj[q] >= 0) cv -= k.r[aj[q]];
+          if (aj[5] >= 0) cv += k.r[aj[5]];
+        }
+        k.cvec[v] = cv;
+      }
+      cx.sync();
+      // x += t * Minv c  (skipped when p is linearly dependent on W: pure dual step)
+      if (!dependent) {
+        MPC_FOR(i, nv) {
+          double acc = 0;
+          for (int j = 0; j < nv; j++) {
+            const double cj = k.cvec[j];
+            if (cj != 0.0) acc += cj * Hm[j * ld + i];
+          }
+          k.x[i] += t * acc;
+        }
+      }
+      MPC_FOR(a, m) k.u[a] -= t * k.r[a];
+      cx.sync();
+      if (t2 <= t1) {
+        // ---- full step: p joins the working set; border T ----
+        if (m >= k.m_cap) {
+          MPC_ONE sc->status = STATUS_RETRY_BIG;
+          cx.sync();
+          return;
+        }
+        const double dinv = 1.0 / znp;
+        for (int e = cx.tid; e < m * m; e += cx.nt) {
+          const int a = e / m, b = e - a * m;
+          T[a * ldT + b] += k.r[a] * k.r[b] * dinv;
+        }
+        MPC_FOR(a, m) {
+          T[a * ldT + m] = -k.r[a] * dinv;
+          T[m * ldT + a] = -k.r[a] * dinv;
+        }
+        MPC_ONE {
+          T[m * ldT + m] = dinv;
+          k.W[m] = p;
+          k.u[m] = sc->up + t;
+          k.act[p] = m;
+          sc->m = m + 1;
+        }
+        cx.sync();
+        break;
+      }
+      // ---- partial step: row W[tidx] leaves; Schur-downdate T, move the last row into the hole ----
+      const int a0 = tidx, last = m - 1;
+      MPC_FOR(a, m) k.tcol[a] = T[a0 * ldT + a];
+      cx.sync();
+      const double taa_inv = 1.0 / k.tcol[a0];
+      for (int e = cx.tid; e < m * m; e += cx.nt) {
+        const int a = e / m, b = e - a * m;
+        if (a != a0 && b != a0) T[a * ldT + b] -= k.tcol[a] * k.tcol[b] * taa_inv;
+      }
+      cx.sync();
+      if (a0 != last) {
+        MPC_FOR(b, last) {
+          if (b == a0) continue;
+          const double v = T[last * ldT + b];
+          T[a0 * ldT + b] = v;
+          T[b * ldT + a0] = v;
+        }
+        MPC_ONE T[a0 * ldT + a0] = T[last * ldT + last];
+      }
+      cx.sync();
+      MPC_ONE {
+        sc->up += t;
+        k.act[k.W[a0]] = -1;
+        if (a0 != last) {
+          k.W[a0] = k.W[last];
+          k.u[a0] = k.u[last];
+          k.act[k.W[a0]] = a0;
+        }
+        sc->m = last;
+      }
+      cx.sync();
+    }
+    if (fail) {
+      cx.sync();
+      MPC_ONE sc->status = MPC_STATUS_MAX_ITER;
+      cx.sync();
+      break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Stage 4: scatter (SolverMPC.cpp:545-557): eliminated variables are exactly 0.
+//   forces   [12] fp32  = q_soln[0..11] (what get_solution(0..11) hands the caller)
+//   solution [12h] fp64 = q_soln (optional)
+// On any failure status the forces are zero (the reference would return stale memory).
+// ---------------------------------------------------------------------------
+template <class Cx>
+MPC_HD void scatter(const Cx& cx, const Work& k, float* forces, double* solution, int32_t* status) {
+  const Scalars* sc = k.sc;
+  const int code = sc->status;
+  const bool ok = (code == MPC_STATUS_OPTIMAL || code == MPC_STATUS_MAX_ITER);
+  MPC_FOR(i, 12) {
+    const int pos = k.posk[i / 3];
+    forces[i] = (ok && pos >= 0) ? (float)k.x[3 * pos + (i % 3)] : 0.f;
+  }
+  if (solution) {
+    MPC_FOR(i, 12 * k.h) {
+      const int pos = (code == MPC_STATUS_BAD_INPUT) ? -1 : k.posk[i / 3];
+      solution[i] = (ok && pos >= 0) ? k.x[3 * pos + (i % 3)] : 0.0;
+    }
+  }
+  MPC_ONE {
+    if (status) *status = (code & 0xff) | (sc->iters << 8);
+  }
+}
+
+// One problem, start to finish.  Returns the status code (uniform across the CTA).
+template <class Cx>
+MPC_HD int solve_problem(const Cx& cx, const float* rec, const unsigned char* gait, const Work& k, int max_iter) {
+  assemble(cx, rec, gait, k);
+  if (k.sc->status != MPC_STATUS_OPTIMAL) return k.sc->status;
+  invert_spd(cx, k);
+  if (k.sc->status != MPC_STATUS_OPTIMAL) return k.sc->status;
+  active_set(cx, rec, gait, k, max_iter);
+  return k.sc->status;
+}
+
+}  // namespace mpc
+#endif

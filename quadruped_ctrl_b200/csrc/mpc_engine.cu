@@ -1,0 +1,540 @@
+// Batched convex-MPC engine for sm_100a: kernels + the C ABI of include/mpc_batch.h.
+//
+// Kernels
+//   mpc_classify_kernel  one thread per problem: counts stance (step,leg) pairs in the
+//                        gait table and appends the problem to the size class whose
+//                        shared-memory tile fits its reduced QP (nv = 3 * stance).
+//   mpc_solve_kernel<NT> persistent CTAs, one problem per CTA at a time.  Records are
+//                        staged global -> shared by TMA bulk copies (cp.async.bulk +
+//                        mbarrier, double buffered: the next record lands while the
+//                        current one is solved).  Assembly, inversion and the active-set
+//                        iterations (csrc/mpc_core.h) run entirely in shared memory; H
+//                        and g never touch HBM.  Only the record (4*(48+12h)+4h bytes)
+//                        is read and 12 fp32 forces (+ optional 12h fp64, status) written.
+// There is no CPU solver in this library: every entry point either runs these kernels or
+// fails with an error code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "mpc_core.h"
+
+namespace {
+
+constexpr int kMaxPeers = 8;
+constexpr int kMaxClasses = 6;
+
+struct SolveParams {
+  const char* records;
+  unsigned long long stride;
+  int h, batch;
+  const int* list;    // problem ids of this class (nullptr: identity)
+  const int* count;   // number of ids (nullptr: batch)
+  float* forces;
+  double* solution;
+  int32_t* status;
+  int* retry_list;    // where to queue a problem whose working set outgrew this class
+  int* retry_count;
+  char* slab;
+  mpc::Layout L;
+  int max_iter;
+  float* peers[kMaxPeers];
+  int n_peers, rank_offset;
+  int32_t* nvar_out;  // assemble-only mode when H_out != nullptr
+  double* H_out;
+  double* g_out;
+};
+
+// ---- TMA bulk copy + mbarrier (PTX) -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__global__ void mpc_classify_kernel(const char* records, unsigned long long stride, int h, int batch, int n_classes,
+                                    const int* __restrict__ class_cap, int* lists, int* counts, int max_batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const float* rec = (const float*)(records + stride * b);
+  const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * h);
+  const float fmax = rec[MPC_REC_FMAX];
+  int ns = 0;
+  for (int k = 0; k < 4 * h; k++) {
+    const float ub = (float)gait[k] * fmax;
+    ns += !((double)ub < 0.01 && (double)ub > -0.01);
+  }
+  const int nv = 3 * ns;
+  int c = 0;
+  while (c < n_classes - 1 && nv > class_cap[c]) c++;
+  const int slot = atomicAdd(&counts[c], 1);
+  lists[c * max_batch + slot] = b;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) mpc_solve_kernel(const __grid_constant__ SolveParams P) {
+  extern __shared__ __align__(128) char smem[];
+  const int count = P.count ? *P.count : P.batch;
+  if ((int)blockIdx.x >= count) return;
+  uint64_t* bar = (uint64_t*)smem;
+  char* recbuf = smem + 16;
+  char* fast = recbuf + 2 * P.stride;
+  const mpc::Cta cx{(int)threadIdx.x, NT};
+  const mpc::Work k = mpc::carve(P.L, fast, P.slab ? P.slab + (size_t)blockIdx.x * P.L.slab_bytes : nullptr);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t rec_bytes = (uint32_t)P.stride;
+  int item = blockIdx.x;
+  if (threadIdx.x == 0) {
+    const int b0 = P.list ? P.list[item] : item;
+    mbar_expect_tx(&bar[0], rec_bytes);
+    tma_bulk_g2s(recbuf, P.records + P.stride * b0, rec_bytes, &bar[0]);
+  }
+  for (int it = 0; item < count; item += gridDim.x, it++) {
+    const int cur = it & 1;
+    const int next = item + gridDim.x;
+    if (threadIdx.x == 0 && next < count) {  // buffer cur^1 was released by the barrier that ended the last pass
+      const int bn = P.list ? P.list[next] : next;
+      mbar_expect_tx(&bar[cur ^ 1], rec_bytes);
+      tma_bulk_g2s(recbuf + (size_t)(cur ^ 1) * P.stride, P.records + P.stride * bn, rec_bytes, &bar[cur ^ 1]);
+    }
+    mbar_wait(&bar[cur], (uint32_t)((it >> 1) & 1));
+    const int b = P.list ? P.list[item] : item;
+    const float* rec = (const float*)(recbuf + (size_t)cur * P.stride);
+    const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
+
+    if (P.H_out) {  // debug / parity entry: reduced QP only
+      mpc::assemble(cx, rec, gait, k);
+      const int nv = (k.sc->status == MPC_STATUS_OPTIMAL) ? k.sc->nv : 0;
+      const int NU = 12 * P.h;
+      if (threadIdx.x == 0 && P.nvar_out) P.nvar_out[b] = nv;
+      double* Ho = P.H_out + (size_t)b * NU * NU;
+      for (int e = threadIdx.x; e < nv * nv; e += NT) {
+        const int i = e / nv, j = e - i * nv;
+        Ho[(size_t)i * NU + j] = k.Hm[i * k.ld + j];
+      }
+      if (P.g_out)
+        for (int i = threadIdx.x; i < nv; i += NT) P.g_out[(size_t)b * NU + i] = k.g[i];
+      __syncthreads();
+      continue;
+    }
+
+    const int code = mpc::solve_problem(cx, rec, gait, k, P.max_iter);
+    if (code == mpc::STATUS_RETRY_BIG && P.retry_list) {
+      if (threadIdx.x == 0) {
+        const int slot = atomicAdd(P.retry_count, 1);
+        P.retry_list[slot] = b;
+      }
+    } else {
+      if (code == mpc::STATUS_RETRY_BIG && threadIdx.x == 0) k.sc->status = MPC_STATUS_MAX_ITER;
+      __syncthreads();
+      mpc::scatter(cx, k, P.forces + (size_t)12 * b, P.solution ? P.solution + (size_t)12 * P.h * b : nullptr,
+                   P.status ? P.status + b : nullptr);
+      if (P.n_peers > 0 && threadIdx.x < 12) {
+        // shard-and-gather epilogue: the forces go straight into every rank's gather buffer over NVLink
+        const float f = P.forces[(size_t)12 * b + threadIdx.x];
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; q++)
+          if (q < P.n_peers && P.peers[q]) P.peers[q][(size_t)12 * (P.rank_offset + b) + threadIdx.x] = f;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct ClassCfg {
+  int nv_cap, m_cap, in_fast, threads, grid;
+  size_t smem;
+  mpc::Layout L;
+};
+
+thread_local std::string g_err;
+
+}  // namespace
+
+struct mpc_batch {
+  int device = 0, h = 0, max_batch = 0, sms = 0;
+  size_t stride = 0;
+  cudaStream_t stream = nullptr;  // owned, used by the host-resident entry
+  char* rec_dev = nullptr;
+  float* forces_dev = nullptr;
+  double* sol_dev = nullptr;
+  int32_t* status_dev = nullptr;
+  char* rec_pin = nullptr;
+  float* forces_pin = nullptr;
+  double* sol_pin = nullptr;
+  int32_t* status_pin = nullptr;
+  int* lists = nullptr;
+  int* counts = nullptr;
+  int* caps_dev = nullptr;
+  char* slab = nullptr;
+  std::vector<ClassCfg> classes;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  long launches = 0;
+  int max_iter = 4000;
+  float* peers[kMaxPeers] = {nullptr};
+  int n_peers = 0, rank_offset = 0;
+  float* gather_buf = nullptr;
+  void* peer_open[kMaxPeers] = {nullptr};
+  std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      eng->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+      return MPC_E_CUDA;                                                                \
+    }                                                                                   \
+  } while (0)
+
+template <int NT>
+int configure_kernel(mpc_batch* eng, ClassCfg& c) {
+  // the attribute is per template instantiation, shared by every class that uses it: raise it to the device limit
+  int max_smem = 0;
+  CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, eng->device));
+  CK(cudaFuncSetAttribute(mpc_solve_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_solve_kernel<NT>, NT, c.smem));
+  if (occ < 1) {
+    eng->err = "solve kernel does not fit on an SM";
+    return MPC_E_CUDA;
+  }
+  c.grid = occ * eng->sms;
+  return MPC_OK;
+}
+
+// largest working-set capacity whose T tile hides under the assembly temporaries
+int free_m_cap(int h, int nv_cap) {
+  int m = 8;
+  while (m < nv_cap) {
+    const int mm = m + 1;
+    const int gi = mm * (mm | 1) + 3 * nv_cap + 4 * (mm + 1);
+    if (gi > mpc::kAsmDoubles(h)) break;
+    m = mm;
+  }
+  return m;
+}
+
+int build_classes(mpc_batch* eng) {
+  const int h = eng->h, nv_max = 12 * h;
+  std::vector<int> caps;
+  for (int c : {60, 96, 120, 156})
+    if (c < nv_max) caps.push_back(c);
+  caps.push_back(std::min(nv_max, 156));
+  int max_smem = 0;
+  CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, eng->device));
+  for (int cap : caps) {
+    ClassCfg c;
+    c.nv_cap = cap;
+    c.m_cap = free_m_cap(h, cap);
+    c.in_fast = 1;
+    c.L = mpc::make_layout(h, c.nv_cap, c.m_cap, 1);
+    c.smem = 16 + 2 * eng->stride + c.L.fast_bytes;
+    c.threads = cap <= 96 ? 128 : 256;
+    if ((int)c.smem > max_smem) continue;
+    int rc = c.threads == 128 ? configure_kernel<128>(eng, c) : configure_kernel<256>(eng, c);
+    if (rc) return rc;
+    eng->classes.push_back(c);
+  }
+  // catch-all: full-size problem and working set in a per-CTA global slab (L2 resident)
+  ClassCfg big;
+  big.nv_cap = nv_max;
+  big.m_cap = nv_max;
+  big.in_fast = 0;
+  big.L = mpc::make_layout(h, big.nv_cap, big.m_cap, 0);
+  big.smem = 16 + 2 * eng->stride + big.L.fast_bytes;
+  big.threads = 256;
+  int rc = configure_kernel<256>(eng, big);
+  if (rc) return rc;
+  big.grid = std::min(big.grid, eng->sms);  // one slab per SM keeps the slabs inside L2
+  eng->classes.push_back(big);
+  if ((int)eng->classes.size() > kMaxClasses) {
+    eng->err = "too many classes";
+    return MPC_E_ARG;
+  }
+  return MPC_OK;
+}
+
+void fill_params(const mpc_batch* eng, SolveParams& P, const void* records, int batch, float* forces, double* solution,
+                 int32_t* status) {
+  memset(&P, 0, sizeof(P));
+  P.records = (const char*)records;
+  P.stride = eng->stride;
+  P.h = eng->h;
+  P.batch = batch;
+  P.forces = forces;
+  P.solution = solution;
+  P.status = status;
+  P.max_iter = eng->max_iter;
+  P.n_peers = eng->n_peers;
+  P.rank_offset = eng->rank_offset;
+  for (int q = 0; q < kMaxPeers; q++) P.peers[q] = eng->peers[q];
+}
+
+int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int grid, cudaStream_t st) {
+  if (c.threads == 128) mpc_solve_kernel<128><<<grid, 128, c.smem, st>>>(P);
+  else mpc_solve_kernel<256><<<grid, 256, c.smem, st>>>(P);
+  eng->launches++;
+  CK(cudaGetLastError());
+  return MPC_OK;
+}
+
+int solve_on_stream(mpc_batch* eng, const void* records, int batch, float* forces, double* solution, int32_t* status,
+                    cudaStream_t st, int32_t* nvar_out, double* H_out, double* g_out) {
+  if (batch == 0) return MPC_OK;
+  const int nc = (int)eng->classes.size();
+  CK(cudaMemsetAsync(eng->counts, 0, sizeof(int) * kMaxClasses, st));
+  mpc_classify_kernel<<<(batch + 127) / 128, 128, 0, st>>>((const char*)records, eng->stride, eng->h, batch, nc,
+                                                           eng->caps_dev, eng->lists, eng->counts, eng->max_batch);
+  eng->launches++;
+  CK(cudaGetLastError());
+  if (eng->timed) CK(cudaEventRecord(eng->ev0, st));
+  for (int ci = 0; ci < nc; ci++) {
+    const ClassCfg& c = eng->classes[ci];
+    SolveParams P;
+    fill_params(eng, P, records, batch, forces, solution, status);
+    P.list = eng->lists + (size_t)ci * eng->max_batch;
+    P.count = eng->counts + ci;
+    P.L = c.L;
+    P.slab = c.in_fast ? nullptr : eng->slab;
+    if (ci != nc - 1) {
+      P.retry_list = eng->lists + (size_t)(nc - 1) * eng->max_batch;
+      P.retry_count = eng->counts + (nc - 1);
+    }
+    P.nvar_out = nvar_out;
+    P.H_out = H_out;
+    P.g_out = g_out;
+    int rc = launch_solve(eng, c, P, std::min(c.grid, batch), st);
+    if (rc) return rc;
+  }
+  if (eng->timed) CK(cudaEventRecord(eng->ev1, st));
+  return MPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t mpc_record_stride(int h) { return ((size_t)(4 * (MPC_REC_TRAJ + 12 * h) + 4 * h) + 15) / 16 * 16; }
+size_t mpc_record_gait_offset(int h) { return (size_t)4 * (MPC_REC_TRAJ + 12 * h); }
+
+const char* mpc_last_error(void) { return g_err.c_str(); }
+
+int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) {
+  if (!out || horizon < 1 || horizon > MPC_MAX_HORIZON || max_batch < 1) {
+    g_err = "mpc_batch_create: bad argument";
+    return MPC_E_ARG;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    g_err = "mpc_batch_create: no such CUDA device (this library has no CPU path)";
+    return MPC_E_NODEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    g_err = "mpc_batch_create: device is not sm_100 (the kernels are built for sm_100a only)";
+    return MPC_E_NODEVICE;
+  }
+  mpc_batch* eng = new mpc_batch();
+  auto fail = [&](int rc) {
+    g_err = eng->err;
+    mpc_batch_destroy(eng);
+    return rc;
+  };
+#define CKC(call)                                                       \
+  do {                                                                  \
+    cudaError_t e_ = (call);                                            \
+    if (e_ != cudaSuccess) {                                            \
+      eng->err = std::string(#call) + ": " + cudaGetErrorString(e_);    \
+      return fail(e_ == cudaErrorMemoryAllocation ? MPC_E_NOMEM : MPC_E_CUDA); \
+    }                                                                   \
+  } while (0)
+  eng->device = device;
+  eng->h = horizon;
+  eng->max_batch = max_batch;
+  eng->sms = prop.multiProcessorCount;
+  eng->stride = mpc_record_stride(horizon);
+  CKC(cudaSetDevice(device));
+  CKC(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreate(&eng->ev0));
+  CKC(cudaEventCreate(&eng->ev1));
+  int rc = build_classes(eng);
+  if (rc) return fail(rc);
+  const size_t B = (size_t)max_batch, NU = 12 * (size_t)horizon;
+  CKC(cudaMalloc(&eng->rec_dev, B * eng->stride));
+  CKC(cudaMalloc(&eng->forces_dev, B * 12 * sizeof(float)));
+  CKC(cudaMalloc(&eng->sol_dev, B * NU * sizeof(double)));
+  CKC(cudaMalloc(&eng->status_dev, B * sizeof(int32_t)));
+  CKC(cudaMallocHost(&eng->rec_pin, B * eng->stride));
+  CKC(cudaMallocHost(&eng->forces_pin, B * 12 * sizeof(float)));
+  CKC(cudaMallocHost(&eng->sol_pin, B * NU * sizeof(double)));
+  CKC(cudaMallocHost(&eng->status_pin, B * sizeof(int32_t)));
+  CKC(cudaMalloc(&eng->lists, sizeof(int) * kMaxClasses * B));
+  CKC(cudaMalloc(&eng->counts, sizeof(int) * kMaxClasses));
+  CKC(cudaMalloc(&eng->caps_dev, sizeof(int) * kMaxClasses));
+  int caps[kMaxClasses] = {0};
+  for (size_t i = 0; i < eng->classes.size(); i++) caps[i] = eng->classes[i].nv_cap;
+  CKC(cudaMemcpy(eng->caps_dev, caps, sizeof(caps), cudaMemcpyHostToDevice));
+  const ClassCfg& big = eng->classes.back();
+  CKC(cudaMalloc(&eng->slab, big.L.slab_bytes * (size_t)big.grid));
+#undef CKC
+  *out = eng;
+  return MPC_OK;
+}
+
+void mpc_batch_destroy(mpc_batch_t* eng) {
+  if (!eng) return;
+  cudaSetDevice(eng->device);
+  for (int q = 0; q < kMaxPeers; q++)
+    if (eng->peer_open[q]) cudaIpcCloseMemHandle(eng->peer_open[q]);
+  cudaFree(eng->gather_buf);
+  cudaFree(eng->rec_dev);
+  cudaFree(eng->forces_dev);
+  cudaFree(eng->sol_dev);
+  cudaFree(eng->status_dev);
+  cudaFreeHost(eng->rec_pin);
+  cudaFreeHost(eng->forces_pin);
+  cudaFreeHost(eng->sol_pin);
+  cudaFreeHost(eng->status_pin);
+  cudaFree(eng->lists);
+  cudaFree(eng->counts);
+  cudaFree(eng->caps_dev);
+  cudaFree(eng->slab);
+  if (eng->ev0) cudaEventDestroy(eng->ev0);
+  if (eng->ev1) cudaEventDestroy(eng->ev1);
+  if (eng->stream) cudaStreamDestroy(eng->stream);
+  delete eng;
+}
+
+int mpc_batch_solve_device(mpc_batch_t* eng, const void* records_dev, int batch, float* forces_dev,
+                           double* solution_dev, int32_t* status_dev, void* cuda_stream) {
+  if (!eng) return MPC_E_ARG;
+  if (!records_dev || !forces_dev || batch < 0 || batch > eng->max_batch || ((uintptr_t)records_dev & 15)) {
+    eng->err = "mpc_batch_solve_device: bad argument (null pointer, batch out of range or records not 16-byte aligned)";
+    return MPC_E_ARG;
+  }
+  CK(cudaSetDevice(eng->device));
+  return solve_on_stream(eng, records_dev, batch, forces_dev, solution_dev, status_dev, (cudaStream_t)cuda_stream,
+                         nullptr, nullptr, nullptr);
+}
+
+int mpc_batch_solve_host(mpc_batch_t* eng, const void* records_host, int batch, float* forces_host,
+                         double* solution_host, int32_t* status_host) {
+  if (!eng) return MPC_E_ARG;
+  if (!records_host || !forces_host || batch < 0 || batch > eng->max_batch) {
+    eng->err = "mpc_batch_solve_host: bad argument";
+    return MPC_E_ARG;
+  }
+  if (batch == 0) return MPC_OK;
+  CK(cudaSetDevice(eng->device));
+  const size_t NU = 12 * (size_t)eng->h;
+  cudaStream_t st = eng->stream;
+  // pageable -> pinned staging on the host, then one async H2D; callers that already hold
+  // pinned memory pay one memcpy (the record block is < 1 KB per problem)
+  memcpy(eng->rec_pin, records_host, (size_t)batch * eng->stride);
+  CK(cudaMemcpyAsync(eng->rec_dev, eng->rec_pin, (size_t)batch * eng->stride, cudaMemcpyHostToDevice, st));
+  int rc = solve_on_stream(eng, eng->rec_dev, batch, eng->forces_dev, solution_host ? eng->sol_dev : nullptr,
+                           eng->status_dev, st, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(eng->forces_pin, eng->forces_dev, (size_t)batch * 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (solution_host)
+    CK(cudaMemcpyAsync(eng->sol_pin, eng->sol_dev, (size_t)batch * NU * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (status_host)
+    CK(cudaMemcpyAsync(eng->status_pin, eng->status_dev, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(forces_host, eng->forces_pin, (size_t)batch * 12 * sizeof(float));
+  if (solution_host) memcpy(solution_host, eng->sol_pin, (size_t)batch * NU * sizeof(double));
+  if (status_host) memcpy(status_host, eng->status_pin, (size_t)batch * sizeof(int32_t));
+  return MPC_OK;
+}
+
+int mpc_batch_assemble_device(mpc_batch_t* eng, const void* records_dev, int batch, int32_t* nvar_dev, double* H_dev,
+                              double* g_dev, void* cuda_stream) {
+  if (!eng) return MPC_E_ARG;
+  if (!records_dev || !H_dev || batch < 0 || batch > eng->max_batch) {
+    eng->err = "mpc_batch_assemble_device: bad argument";
+    return MPC_E_ARG;
+  }
+  CK(cudaSetDevice(eng->device));
+  return solve_on_stream(eng, records_dev, batch, eng->forces_dev, nullptr, nullptr, (cudaStream_t)cuda_stream,
+                         nvar_dev, H_dev, g_dev);
+}
+
+int mpc_batch_set_gather_peers(mpc_batch_t* eng, float* const* peers, int n_peers, int rank_offset) {
+  if (!eng || n_peers < 0 || n_peers > kMaxPeers || (n_peers > 0 && !peers)) return MPC_E_ARG;
+  for (int q = 0; q < kMaxPeers; q++) eng->peers[q] = q < n_peers ? peers[q] : nullptr;
+  eng->n_peers = n_peers;
+  eng->rank_offset = rank_offset;
+  return MPC_OK;
+}
+
+int mpc_batch_set_max_iterations(mpc_batch_t* eng, int max_iter) {
+  if (!eng || max_iter < 1) return MPC_E_ARG;
+  eng->max_iter = max_iter;
+  return MPC_OK;
+}
+
+int mpc_batch_set_timing(mpc_batch_t* eng, int enabled) {
+  if (!eng) return MPC_E_ARG;
+  eng->timed = enabled != 0;
+  return MPC_OK;
+}
+
+long mpc_batch_kernel_launches(const mpc_batch_t* eng) { return eng ? eng->launches : 0; }
+
+float mpc_batch_last_solve_kernel_ms(mpc_batch_t* eng) {
+  if (!eng || !eng->timed) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(eng->ev1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+const char* mpc_batch_last_error(const mpc_batch_t* eng) { return eng ? eng->err.c_str() : ""; }
+int mpc_batch_horizon(const mpc_batch_t* eng) { return eng ? eng->h : 0; }
+
+int mpc_batch_num_classes(const mpc_batch_t* eng) { return eng ? (int)eng->classes.size() : 0; }
+// info[6]: nv_cap, m_cap, threads, grid, shared bytes, 1 if the tile lives in shared memory
+int mpc_batch_class_info(const mpc_batch_t* eng, int idx, int* info) {
+  if (!eng || idx < 0 || idx >= (int)eng->classes.size() || !info) return MPC_E_ARG;
+  const ClassCfg& c = eng->classes[idx];
+  info[0] = c.nv_cap; info[1] = c.m_cap; info[2] = c.threads; info[3] = c.grid; info[4] = (int)c.smem; info[5] = c.in_fast;
+  return MPC_OK;
+}
+
+}  // extern "C"

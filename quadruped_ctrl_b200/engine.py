@@ -1,0 +1,222 @@
+"""ctypes binding of libquadruped_mpc_b200.so (include/mpc_batch.h) -- the batched sm_100a MPC engine.
+
+PyTorch is used for device memory and streams only; every solve runs the hand-written CUDA
+kernels in csrc/.  There is no CPU implementation behind this module: importing works
+anywhere (so host logic can be tested), but creating an engine without the built library or
+without an sm_100 device raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from . import records as R
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libquadruped_mpc_b200.so")
+_LIB = None
+
+MPC_OK, MPC_E_ARG, MPC_E_CUDA, MPC_E_NOMEM, MPC_E_NODEVICE = 0, -1, -2, -3, -4
+STATUS_OPTIMAL, STATUS_MAX_ITER, STATUS_BAD_INPUT, STATUS_NOT_PD, STATUS_NO_STANCE = 0, 1, 2, 3, 4
+
+# every symbol include/mpc_batch.h and include/convexMPC_interface.h declare
+BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_create", "mpc_batch_destroy",
+                 "mpc_batch_solve_device", "mpc_batch_solve_host", "mpc_batch_assemble_device",
+                 "mpc_batch_set_gather_peers", "mpc_batch_set_max_iterations", "mpc_batch_set_timing",
+                 "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
+                 "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_error", "mpc_last_error", "mpc_batch_horizon"]
+LEGACY_SYMBOLS = ["setup_problem", "update_problem_data", "update_problem_data_floats", "get_solution",
+                  "update_solver_settings", "_Z13update_x_dragf", "mpc_last_status", "mpc_last_iterations",
+                  "mpc_set_robot", "mpc_shutdown"]
+
+
+class MpcError(RuntimeError):
+    pass
+
+
+def build(force=False):
+    """Compiles csrc/ for sm_100a into libquadruped_mpc_b200.so (nvcc cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc")
+    deps = [os.path.join(src, f) for f in ("mpc_engine.cu", "mpc_core.h", "convexMPC_interface.cpp", "Makefile")]
+    deps += [os.path.join(_HERE, "..", "include", f) for f in ("mpc_batch.h", "convexMPC_interface.h")]
+    stale = force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(map(os.path.getmtime, deps))
+    if stale:
+        subprocess.check_call(["make", "-C", src, "-s"] + (["-B"] if force else []))
+    return LIB_PATH
+
+
+def lib():
+    """Loads the shared library and declares the C signatures.  Raises when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise MpcError("libquadruped_mpc_b200.so is not built (run __graft_entry__.build() or make -C "
+                       "quadruped_ctrl_b200/csrc); this package has no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, f32, f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
+    L.mpc_record_stride.argtypes = [i32]
+    L.mpc_record_stride.restype = ctypes.c_size_t
+    L.mpc_record_gait_offset.argtypes = [i32]
+    L.mpc_record_gait_offset.restype = ctypes.c_size_t
+    L.mpc_batch_create.argtypes = [ctypes.POINTER(vp), i32, i32, i32]
+    L.mpc_batch_destroy.argtypes = [vp]
+    L.mpc_batch_destroy.restype = None
+    L.mpc_batch_solve_device.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.mpc_batch_solve_host.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.mpc_batch_assemble_device.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.mpc_batch_set_gather_peers.argtypes = [vp, ctypes.POINTER(vp), i32, i32]
+    L.mpc_batch_set_max_iterations.argtypes = [vp, i32]
+    L.mpc_batch_set_timing.argtypes = [vp, i32]
+    L.mpc_batch_num_classes.argtypes = [vp]
+    L.mpc_batch_class_info.argtypes = [vp, i32, ctypes.POINTER(i32)]
+    L.mpc_batch_kernel_launches.argtypes = [vp]
+    L.mpc_batch_kernel_launches.restype = ctypes.c_long
+    L.mpc_batch_last_solve_kernel_ms.argtypes = [vp]
+    L.mpc_batch_last_solve_kernel_ms.restype = f32
+    L.mpc_batch_last_error.argtypes = [vp]
+    L.mpc_batch_last_error.restype = ctypes.c_char_p
+    L.mpc_last_error.restype = ctypes.c_char_p
+    L.mpc_batch_horizon.argtypes = [vp]
+    # legacy interface (include/convexMPC_interface.h)
+    fp, dp, ip = ctypes.POINTER(f32), ctypes.POINTER(f64), ctypes.POINTER(i32)
+    L.setup_problem.argtypes = [f64, i32, f64, f64]
+    L.setup_problem.restype = None
+    L.update_problem_data_floats.argtypes = [fp, fp, fp, fp, fp, f32, fp, fp, f32, ip]
+    L.update_problem_data_floats.restype = None
+    L.update_problem_data.argtypes = [dp, dp, dp, dp, dp, f64, dp, dp, f64, ip]
+    L.update_problem_data.restype = None
+    L.update_solver_settings.argtypes = [i32, f64, f64, f64, f64, f64]
+    L.update_solver_settings.restype = None
+    L.get_solution.argtypes = [i32]
+    L.get_solution.restype = f64
+    L._Z13update_x_dragf.argtypes = [f32]
+    L._Z13update_x_dragf.restype = None
+    L.mpc_set_robot.argtypes = [fp, f32]
+    L.mpc_set_robot.restype = None
+    L.mpc_shutdown.restype = None
+    _LIB = L
+    return L
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class MpcBatch:
+    """One engine per (device, horizon).  Problems are packed records (records.pack_records)."""
+
+    def __init__(self, horizon, max_batch, device=0):
+        L = lib()
+        self._L = L
+        self.horizon = int(horizon)
+        self.max_batch = int(max_batch)
+        self.device = int(device)
+        self.stride = R.record_stride(self.horizon)
+        assert self.stride == L.mpc_record_stride(self.horizon)
+        h = ctypes.c_void_p()
+        rc = L.mpc_batch_create(ctypes.byref(h), self.device, self.horizon, self.max_batch)
+        if rc != MPC_OK:
+            raise MpcError("mpc_batch_create failed (rc=%d): %s" % (rc, L.mpc_last_error().decode()))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mpc_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc != MPC_OK:
+            raise MpcError("%s failed (rc=%d): %s" % (what, rc, self._L.mpc_batch_last_error(self._h).decode()))
+
+    # ---- configuration ------------------------------------------------------------------
+    def set_max_iterations(self, n):
+        self._check(self._L.mpc_batch_set_max_iterations(self._h, int(n)), "set_max_iterations")
+
+    def set_timing(self, on):
+        self._check(self._L.mpc_batch_set_timing(self._h, int(bool(on))), "set_timing")
+
+    def last_solve_kernel_ms(self):
+        return float(self._L.mpc_batch_last_solve_kernel_ms(self._h))
+
+    def kernel_launches(self):
+        return int(self._L.mpc_batch_kernel_launches(self._h))
+
+    def classes(self):
+        out = []
+        info = (ctypes.c_int * 6)()
+        for i in range(self._L.mpc_batch_num_classes(self._h)):
+            self._L.mpc_batch_class_info(self._h, i, info)
+            out.append(dict(nv_cap=info[0], m_cap=info[1], threads=info[2], grid=info[3], smem=info[4],
+                            in_smem=bool(info[5])))
+        return out
+
+    def set_gather_peers(self, peer_ptrs, rank_offset):
+        n = len(peer_ptrs)
+        arr = (ctypes.c_void_p * max(n, 1))(*[ctypes.c_void_p(int(p)) for p in peer_ptrs])
+        self._check(self._L.mpc_batch_set_gather_peers(self._h, arr, n, int(rank_offset)), "set_gather_peers")
+
+    # ---- solves ---------------------------------------------------------------------------
+    def solve_device(self, records, forces=None, solution=None, status=None, want_solution=False,
+                     want_status=True, stream=None):
+        """records: cuda uint8 tensor [B, stride] on this engine's device.  Asynchronous on `stream`
+        (default: torch's current stream).  Returns (forces [B,12] f32, solution [B,12h] f64 | None,
+        status [B] int32 | None), all cuda tensors."""
+        torch = _torch()
+        assert records.is_cuda and records.dtype == torch.uint8 and records.is_contiguous()
+        B = records.shape[0]
+        assert records.shape[1] == self.stride, (records.shape, self.stride)
+        dev = records.device
+        if forces is None:
+            forces = torch.empty((B, 12), dtype=torch.float32, device=dev)
+        if solution is None and want_solution:
+            solution = torch.empty((B, 12 * self.horizon), dtype=torch.float64, device=dev)
+        if status is None and want_status:
+            status = torch.empty((B,), dtype=torch.int32, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = self._L.mpc_batch_solve_device(self._h, records.data_ptr(), B, forces.data_ptr(),
+                                            solution.data_ptr() if solution is not None else None,
+                                            status.data_ptr() if status is not None else None, st.cuda_stream)
+        self._check(rc, "mpc_batch_solve_device")
+        return forces, solution, status
+
+    def solve_host(self, records, want_solution=False, out_forces=None):
+        """records: numpy uint8 [B, stride] in host memory.  Synchronous: H2D, kernels, D2H.
+        Returns (forces [B,12] f32, solution [B,12h] f64 | None, status [B] int32)."""
+        records = np.ascontiguousarray(records, np.uint8)
+        B = records.shape[0]
+        assert records.shape[1] == self.stride
+        forces = out_forces if out_forces is not None else np.empty((B, 12), np.float32)
+        sol = np.empty((B, 12 * self.horizon), np.float64) if want_solution else None
+        status = np.empty((B,), np.int32)
+        rc = self._L.mpc_batch_solve_host(self._h, records.ctypes.data, B, forces.ctypes.data,
+                                          sol.ctypes.data if want_solution else None, status.ctypes.data)
+        self._check(rc, "mpc_batch_solve_host")
+        return forces, sol, status
+
+    def assemble_device(self, records, stream=None):
+        """Parity entry: the reduced QP only.  Returns (nv [B] int32, H [B,12h,12h] f64, g [B,12h] f64)."""
+        torch = _torch()
+        B = records.shape[0]
+        NU = 12 * self.horizon
+        dev = records.device
+        nv = torch.zeros((B,), dtype=torch.int32, device=dev)
+        H = torch.zeros((B, NU, NU), dtype=torch.float64, device=dev)
+        g = torch.zeros((B, NU), dtype=torch.float64, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = self._L.mpc_batch_assemble_device(self._h, records.data_ptr(), B, nv.data_ptr(), H.data_ptr(),
+                                               g.data_ptr(), st.cuda_stream)
+        self._check(rc, "mpc_batch_assemble_device")
+        return nv, H, g
+
+
+def status_code(status):
+    return np.asarray(status) & 0xff
+
+
+def status_iterations(status):
+    return (np.asarray(status).astype(np.uint32)) >> 8

@@ -1,0 +1,58 @@
+// TEST-ONLY: single-thread host build of the kernel source (csrc/mpc_core.h).
+//
+// It exists so that the algorithm the CUDA kernel runs (closed-form assembly,
+// sweep inversion, dual active-set iterations) can be logic-checked against the
+// oracle in the CPU test tier, where there is no GPU.  It is never linked into
+// libquadruped_mpc_b200.so and nothing in quadruped_ctrl_b200/ loads it: the
+// product has no CPU path.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../quadruped_ctrl_b200/csrc/mpc_core.h"
+
+extern "C" {
+
+// Runs `batch` records through the kernel body with one emulated thread.
+//   nv_cap / m_cap <= 0 -> worst case (12h).  H_out/g_out (optional): the reduced QP
+//   before inversion, [batch*(12h)^2] / [batch*12h] with leading dimension 12h.
+//   info [batch*4]: nv, active-set size at exit, iterations, status code.
+int emu_solve_batch(const void* records, int batch, int h, int nv_cap, int m_cap, int max_iter, float* forces,
+                    double* solution, int* info, double* H_out, double* g_out) {
+  using namespace mpc;
+  if (nv_cap <= 0) nv_cap = 12 * h;
+  if (m_cap <= 0) m_cap = nv_cap;
+  const Layout L = make_layout(h, nv_cap, m_cap, 1);
+  std::vector<char> fast(L.fast_bytes + 64);
+  const size_t stride = ((size_t)(4 * (MPC_REC_TRAJ + 12 * h) + 4 * h) + 15) / 16 * 16;
+  OneThread cx{0, 1};
+  const int NU = 12 * h;
+  for (int b = 0; b < batch; b++) {
+    memset(fast.data(), 0xCD, fast.size());  // poison: nothing may rely on zeroed workspace
+    const Work k = carve(L, fast.data(), nullptr);
+    const float* rec = (const float*)((const char*)records + stride * b);
+    const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * h);
+    assemble(cx, rec, gait, k);
+    if (k.sc->status == MPC_STATUS_OPTIMAL && k.sc->nv > nv_cap) return -1;
+    if (k.sc->status == MPC_STATUS_OPTIMAL) {
+      if (H_out)
+        for (int i = 0; i < k.sc->nv; i++)
+          for (int j = 0; j < k.sc->nv; j++) H_out[(size_t)b * NU * NU + (size_t)i * NU + j] = k.Hm[i * k.ld + j];
+      if (g_out)
+        for (int i = 0; i < k.sc->nv; i++) g_out[(size_t)b * NU + i] = k.g[i];
+      invert_spd(cx, k);
+      if (k.sc->status == MPC_STATUS_OPTIMAL) active_set(cx, rec, gait, k, max_iter);
+    }
+    int32_t st = 0;
+    scatter(cx, k, forces + 12 * b, solution ? solution + (size_t)NU * b : nullptr, &st);
+    if (info) {
+      info[4 * b + 0] = k.sc->nv;
+      info[4 * b + 1] = k.sc->m;
+      info[4 * b + 2] = k.sc->iters;
+      info[4 * b + 3] = k.sc->status;
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"
