@@ -88,6 +88,9 @@ EXTERNC int mpc_last_iterations(void);
 /* Additive: body inertia diagonal [3] and mass, which the reference hard-codes
  * (RobotState.cpp:38-40, RobotState.h:23); defaults are those constants. */
 EXTERNC void mpc_set_robot(const float* I_body_diag, float mass);
+/* Additive: the inputs last given to setup_problem / update_x_drag / update_problem_data* as one batch
+ * record of include/mpc_batch.h (out holds mpc_record_stride(horizon) bytes); returns the horizon. */
+EXTERNC int mpc_legacy_record(void* out);
 /* Additive: destroys the cached GPU engines. */
 EXTERNC void mpc_shutdown(void);
 #endif

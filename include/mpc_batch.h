@@ -145,6 +145,18 @@ long mpc_batch_kernel_launches(const mpc_batch_t* eng);
 /* Device time in ms of the solve kernels of the most recent solve call, measured
  * with CUDA events on the call's stream (synchronises that stream). */
 float mpc_batch_last_solve_kernel_ms(mpc_batch_t* eng);
+/* Same, for the solve kernel of size class `idx` alone. */
+float mpc_batch_last_class_kernel_ms(mpc_batch_t* eng, int idx);
+/* Timing over a region without synchronising inside it: mark, run up to 256 solves,
+ * then collect the mean duration of size class `idx`'s solve kernel over the solves
+ * since the mark (CUDA events recorded on each call's own stream). */
+void mpc_batch_timing_mark(mpc_batch_t* eng);
+int mpc_batch_timing_collect(mpc_batch_t* eng, int idx, float* mean_ms, int* n_solves);
+/* The engine's pinned host staging buffers ([max_batch] records / forces / solution /
+ * status).  A caller that fills *records and passes these same pointers to
+ * mpc_batch_solve_host skips the pageable->pinned copies. */
+int mpc_batch_host_buffers(mpc_batch_t* eng, void** records, float** forces, double** solution,
+                           int32_t** status);
 /* Human-readable description of the last error on this engine ("" if none). */
 const char* mpc_batch_last_error(const mpc_batch_t* eng);
 /* Library-level: text of the last error when no engine exists (create failed). */

@@ -27,6 +27,7 @@
 // of index 4 (rows 12..24 are zero and A^3 = 0); I_world.inverse()
 // (SolverMPC.cpp:247) is the 3x3 adjugate formula.
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -189,11 +190,15 @@ void solve_one(const Inputs& in, int backend, double* sol, Result* res,
   for (int i = 1; i < h + 1; i++) power.push_back(matmul(Adt, power[i - 1]));
 
   Mat<T> A_qp(NX, 13), B_qp(NX, NU);
+  // powerMats[r-c]*Bdt depends on r-c only: form each product once and copy it into every block
+  // of its diagonal (bit-identical to recomputing it per block as the reference does).
+  std::vector<Mat<T>> phi;
+  for (int d = 0; d < h; d++) phi.push_back(matmul(power[d], Bdt));
   for (int r = 0; r < h; r++) {
     for (int i = 0; i < 13; i++)
       for (int j = 0; j < 13; j++) A_qp(13 * r + i, j) = power[r + 1](i, j);
     for (int c = 0; c <= r; c++) {
-      Mat<T> blk = matmul(power[r - c], Bdt);
+      const Mat<T>& blk = phi[r - c];
       for (int i = 0; i < 13; i++)
         for (int j = 0; j < 12; j++) B_qp(13 * r + i, 12 * c + j) = blk(i, j);
     }
@@ -224,16 +229,24 @@ void solve_one(const Inputs& in, int backend, double* sol, Result* res,
   Mat<T> qH(NU, NU);
   std::vector<T> qg(NU);
   {
+    // qH = 2*(B'(S B) + alpha I) as a rank-1-update sweep over the rows of B_qp (unit-stride inner
+    // loop, vectorisable; Eigen's own summation order is unknown, any order restates it).  S is
+    // diagonal; the reference stores it dense and pays a 13h x 13h x 12h product for S*B_qp on top.
     Mat<T> SB(NX, NU);
     for (int k = 0; k < NX; k++)
       for (int j = 0; j < NU; j++) SB(k, j) = Sdiag[k] * B_qp(k, j);
-    for (int i = 0; i < NU; i++) {
-      for (int j = 0; j < NU; j++) {
-        T acc = 0;
-        // only block rows r >= max(i,j)/12 are non-zero, but sum all like the dense product
-        for (int k = 0; k < NX; k++) acc += B_qp(k, i) * SB(k, j);
-        qH(i, j) = (T)2 * (acc + (i == j ? (T)in.alpha : (T)0));
+    for (int k = 0; k < NX; k++) {
+      const T* sb = &SB.a[(size_t)k * NU];
+      const int jmax = 12 * (k / 13 + 1);  // B_qp row k is zero beyond its own block column
+      for (int i = 0; i < jmax; i++) {
+        const T b = B_qp(k, i);
+        if (b == (T)0) continue;
+        T* row = &qH.a[(size_t)i * NU];
+        for (int j = 0; j < jmax; j++) row[j] += b * sb[j];
       }
+    }
+    for (int i = 0; i < NU; i++) {
+      for (int j = 0; j < NU; j++) qH(i, j) = (T)2 * (qH(i, j) + (i == j ? (T)in.alpha : (T)0));
       T acc = 0;
       for (int k = 0; k < NX; k++) acc += ((T)2 * B_qp(k, i)) * Sdiag[k] * e[k];
       qg[i] = acc;
@@ -417,7 +430,8 @@ void oracle_update_problem_data_floats(float* p, float* v, float* q, float* w, f
   const int h = o_setup.horizon;
   o_update.alpha = alpha;
   o_update.yaw = yaw;
-  for (int i = 0; i < 4 * h; i++) o_update.gait[i] = (unsigned char)gait[i];  // spills into hack_pad like upstream
+  unsigned char* gait_bytes = reinterpret_cast<unsigned char*>(&o_update) + offsetof(update_data_t, gait);
+  for (int i = 0; i < 4 * h; i++) gait_bytes[i] = (unsigned char)gait[i];  // spills into hack_pad like upstream
   memcpy(o_update.p, p, 12);
   memcpy(o_update.v, v, 12);
   memcpy(o_update.q, q, 16);
@@ -442,7 +456,7 @@ void oracle_update_problem_data_floats(float* p, float* v, float* q, float* w, f
   in.f_max = o_setup.f_max;
   in.horizon = h;
   in.traj = o_update.traj;
-  in.gait = o_update.gait;
+  in.gait = gait_bytes;
   if (o_precision == 64) solve_one<double>(in, o_backend, o_soln.data(), &o_last, nullptr, nullptr);
   else solve_one<float>(in, o_backend, o_soln.data(), &o_last, nullptr, nullptr);
   o_has_solved = 1;

@@ -8,6 +8,7 @@
 // get_solution() at 0 and mpc_last_status() negative.
 #include "../../include/convexMPC_interface.h"
 
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -47,19 +48,9 @@ mpc_batch_t* engine_for(int h) {
 // reference: mint_to_u8, convexMPC_interface.cpp:75-79
 inline unsigned char mint_to_u8(int i) { return (unsigned char)i; }
 
-void solve_now() {
-  const int h = problem_configuration.horizon;
-  has_solved = 0;
-  if (h < 1 || h > MPC_MAX_HORIZON) {
-    fprintf(stderr, "[quadruped_mpc_b200] horizon %d outside 1..%d\n", h, MPC_MAX_HORIZON);
-    last_status = MPC_E_ARG;
-    return;
-  }
-  mpc_batch_t* eng = engine_for(h);
-  if (!eng) return;
-  const size_t stride = mpc_record_stride(h);
-  record.assign(stride, 0);
-  float* f = (float*)record.data();
+// the contents of problem_configuration / update that solve_mpc reads, as one batch record (mpc_batch.h)
+void pack_record(char* out, int h) {
+  float* f = (float*)out;
   memcpy(f + MPC_REC_P, update.p, 12);
   memcpy(f + MPC_REC_V, update.v, 12);
   memcpy(f + MPC_REC_Q, update.q, 16);
@@ -75,7 +66,23 @@ void solve_now() {
   f[MPC_REC_MU] = problem_configuration.mu;
   f[MPC_REC_FMAX] = problem_configuration.f_max;
   memcpy(f + MPC_REC_TRAJ, update.traj, sizeof(float) * 12 * h);
-  memcpy(record.data() + mpc_record_gait_offset(h), update.gait, 4 * h);  // gait[] runs on into hack_pad[] as upstream
+  memcpy(out + mpc_record_gait_offset(h), reinterpret_cast<const unsigned char*>(&update) + offsetof(update_data_t, gait),
+         4 * h);  // gait[] runs on into hack_pad[] as upstream
+}
+
+void solve_now() {
+  const int h = problem_configuration.horizon;
+  has_solved = 0;
+  if (h < 1 || h > MPC_MAX_HORIZON) {
+    fprintf(stderr, "[quadruped_mpc_b200] horizon %d outside 1..%d\n", h, MPC_MAX_HORIZON);
+    last_status = MPC_E_ARG;
+    return;
+  }
+  mpc_batch_t* eng = engine_for(h);
+  if (!eng) return;
+  const size_t stride = mpc_record_stride(h);
+  record.assign(stride, 0);
+  pack_record(record.data(), h);
   q_soln.assign(12 * h, 0.0);
   float forces[12];
   int32_t status = 0;
@@ -128,7 +135,10 @@ void update_problem_data_floats(float* p, float* v, float* q, float* w, float* r
   }
   update.alpha = alpha;
   update.yaw = yaw;
-  for (int i = 0; i < 4 * h; i++) update.gait[i] = mint_to_u8(gait[i]);  // spills into hack_pad for h > 9
+  // 4h bytes starting at update.gait: for h > 9 this runs on into hack_pad, exactly where upstream's
+  // out-of-bounds loop puts them.  Addressed from the struct base so the compiler cannot assume i < 36.
+  unsigned char* gait_bytes = reinterpret_cast<unsigned char*>(&update) + offsetof(update_data_t, gait);
+  for (int i = 0; i < 4 * h; i++) gait_bytes[i] = mint_to_u8(gait[i]);
   memcpy((void*)update.p, (void*)p, sizeof(float) * 3);
   memcpy((void*)update.v, (void*)v, sizeof(float) * 3);
   memcpy((void*)update.q, (void*)q, sizeof(float) * 4);
@@ -175,6 +185,17 @@ int mpc_last_iterations(void) { return last_iters; }
 extern "C" void mpc_set_robot(const float* I_body_diag, float mass) {
   if (I_body_diag) memcpy(robot_I_body, I_body_diag, 12);
   robot_mass = mass;
+}
+
+// Additive: writes the batch record (include/mpc_batch.h) of the inputs last handed to setup_problem /
+// update_x_drag / update_problem_data*, i.e. the bridge from the legacy calls to the batched API.
+// `out` must hold mpc_record_stride(horizon) bytes.  Returns the horizon, or MPC_E_ARG.
+extern "C" int mpc_legacy_record(void* out) {
+  const int h = problem_configuration.horizon;
+  if (!out || h < 1 || h > MPC_MAX_HORIZON) return MPC_E_ARG;
+  memset(out, 0, mpc_record_stride(h));
+  pack_record((char*)out, h);
+  return h;
 }
 
 // Additive: releases the cached engines (e.g. before the process unloads the library).

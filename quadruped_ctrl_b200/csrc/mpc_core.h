@@ -59,6 +59,7 @@ enum { STATUS_RETRY_BIG = 0x40 };  // working set outgrew the fast-memory tile: 
 struct Layout {
   int h;        // horizon
   int nv_cap;   // largest reduced variable count this workspace can hold
+  int ck_len;   // doubles reserved for the pivot-column broadcast buffer(s)
   int m_cap;    // largest working set (active constraints) it can hold
   int ld;       // leading dimension of Hm (odd -> conflict-free column walks)
   int ldT;      // leading dimension of T
@@ -81,10 +82,12 @@ constexpr int kRedDoubles = 40;
 inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
 // The same function sizes the launch (host) and carves the pointers (device).
-inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast) {
+inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npad = 0) {
   Layout L;
   L.h = h;
   L.nv_cap = nv_cap;
+  // register-tiled inversion: two (npad + 2)-long buffers (double-buffered pivot column + 1/pivot)
+  L.ck_len = npad > 0 ? 2 * (npad + 2) : nv_cap;
   L.m_cap = m_cap;
   L.ld = nv_cap | 1;
   L.ldT = m_cap | 1;
@@ -101,7 +104,7 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast) {
   o += 4 * (4 * h + 4 * h + 24 * h + m_cap + 1);
   o = (o + 15) / 16 * 16;
   L.off_union = o;
-  int gi = nv_cap * 3 + (m_cap + 1) * 4;  // z, cvec, ck, w, r, u, tcol
+  int gi = nv_cap * 2 + L.ck_len + (m_cap + 1) * 4;  // z, cvec, ck, w, r, u, tcol
   int un = kAsmDoubles(h);
   int t_doubles = m_cap * L.ldT;
   int hm_doubles = nv_cap * L.ld;
@@ -159,7 +162,7 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
   k.z = gi;
   k.cvec = k.z + L.nv_cap;
   k.ck = k.cvec + L.nv_cap;
-  k.w = k.ck + L.nv_cap;
+  k.w = k.ck + L.ck_len;
   k.r = k.w + (L.m_cap + 1);
   k.u = k.r + (L.m_cap + 1);
   k.tcol = k.u + (L.m_cap + 1);
@@ -537,6 +540,96 @@ MPC_HD void invert_spd(const Cx& cx, const Work& k) {
       for (int i = ig; i < nv; i += rgroups) Hm[i * ld + j] = -Hm[i * ld + j];
   cx.sync();
 }
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------
+// Stage 2, register-tiled (device only): the same symmetric sweep with the matrix held in
+// registers.  NT = GR*GC threads form a GR x GC grid; thread (tr, tc) owns the R x C elements
+// (tr + GR*i, tc + GC*j) of the NVP x NVP matrix (NVP = GR*R = GC*C >= nv, padded with the
+// identity).  Per pivot p the owners of column p publish it once through shared memory
+// (double-buffered: one barrier per pivot) with slot p holding d-1 instead of d = a_pp, and
+// every thread applies ONE uniform rank-1 update  a_ij -= u_i * (u_j / d):
+//     i,j != p :  a_ij - c_i c_j / d                      (the Schur complement)
+//     j == p   :  c_i - c_i (d-1)/d = c_i / d             (the swept column)
+//     i == j == p: d - (d-1)^2/d = 2 - 1/d  -> patched to -1/d by its owner
+// so the inner loop is R*C DFMAs with no per-element predicates; shared memory carries only
+// R + C broadcast loads per thread per pivot instead of the whole matrix.
+// ---------------------------------------------------------------------------
+template <int NT, int GR, int GC, int R, int C>
+__device__ __forceinline__ void invert_spd_tiled(const Work& k, int tid) {
+  constexpr int NVP = GR * R;
+  static_assert(GR * GC == NT && GC * C == NVP, "tile grid must cover the padded matrix");
+  Scalars* sc = k.sc;
+  const int nv = sc->nv, ld = k.ld;
+  double* Hm = k.Hm;
+  const int tr = tid / GC, tc = tid % GC;
+  double a[R][C];
+#pragma unroll
+  for (int i = 0; i < R; i++)
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+      const int r = tr + GR * i, c = tc + GC * j;
+      a[i][j] = (r < nv && c < nv) ? Hm[r * ld + c] : (r == c ? 1.0 : 0.0);
+    }
+  bool bad = false;
+  for (int p = 0; p < nv; p++) {
+    double* ck = k.ck + (p & 1) * (NVP + 2);
+    const int jp = p / GC, ip = p / GR;
+    if (tc == p % GC) {  // this thread holds R elements of column p (at j == jp)
+#pragma unroll
+      for (int j = 0; j < C; j++)
+        if (j == jp) {
+#pragma unroll
+          for (int i = 0; i < R; i++) ck[tr + GR * i] = a[i][j];
+          if (tr == p % GR) {
+#pragma unroll
+            for (int i = 0; i < R; i++)
+              if (i == ip) {
+                const double d = a[i][j];
+                ck[p] = d - 1.0;
+                ck[NVP] = 1.0 / d;
+              }
+          }
+        }
+    }
+    __syncthreads();
+    const double dinv = ck[NVP];
+    if (!(dinv > 0.0 && dinv < 1e300)) { bad = true; break; }  // uniform: everyone reads the same value
+    double u[R], v[C];
+#pragma unroll
+    for (int i = 0; i < R; i++) u[i] = ck[tr + GR * i];
+#pragma unroll
+    for (int j = 0; j < C; j++) v[j] = ck[tc + GC * j] * dinv;
+#pragma unroll
+    for (int i = 0; i < R; i++)
+#pragma unroll
+      for (int j = 0; j < C; j++) a[i][j] = fma(-u[i], v[j], a[i][j]);
+    if (tc == p % GC && tr == p % GR) {
+#pragma unroll
+      for (int j = 0; j < C; j++)
+        if (j == jp) {
+#pragma unroll
+          for (int i = 0; i < R; i++)
+            if (i == ip) a[i][j] = -dinv;
+        }
+    }
+  }
+  if (bad) {
+    __syncthreads();
+    if (tid == 0) sc->status = MPC_STATUS_NOT_PD;
+    __syncthreads();
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < R; i++)
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+      const int r = tr + GR * i, c = tc + GC * j;
+      if (r < nv && c < nv) Hm[r * ld + c] = -a[i][j];
+    }
+  __syncthreads();
+}
+#endif
 
 // ---------------------------------------------------------------------------
 // Stage 3: Goldfarb-Idnani dual active-set iterations on the explicit inverse.

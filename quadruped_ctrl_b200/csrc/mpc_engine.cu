@@ -28,6 +28,7 @@ namespace {
 
 constexpr int kMaxPeers = 8;
 constexpr int kMaxClasses = 6;
+constexpr int kRing = 256;
 
 struct SolveParams {
   const char* records;
@@ -97,8 +98,10 @@ __global__ void mpc_classify_kernel(const char* records, unsigned long long stri
   lists[c * max_batch + slot] = b;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) mpc_solve_kernel(const __grid_constant__ SolveParams P) {
+// NT threads per CTA; GR x GC thread grid with R x C register tiles for the inversion (R == 0: the generic
+// shared/global-memory sweep, used by the catch-all class whose matrix does not fit in registers).
+template <int NT, int GR, int GC, int R, int C, int MINB>
+__global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) char smem[];
   const int count = P.count ? *P.count : P.batch;
   if ((int)blockIdx.x >= count) return;
@@ -149,7 +152,13 @@ __global__ void __launch_bounds__(NT) mpc_solve_kernel(const __grid_constant__ S
       continue;
     }
 
-    const int code = mpc::solve_problem(cx, rec, gait, k, P.max_iter);
+    mpc::assemble(cx, rec, gait, k);
+    if (k.sc->status == MPC_STATUS_OPTIMAL) {
+      if constexpr (R > 0) mpc::invert_spd_tiled<NT, GR, GC, R, C>(k, (int)threadIdx.x);
+      else mpc::invert_spd(cx, k);
+    }
+    if (k.sc->status == MPC_STATUS_OPTIMAL) mpc::active_set(cx, rec, gait, k, P.max_iter);
+    const int code = k.sc->status;
     if (code == mpc::STATUS_RETRY_BIG && P.retry_list) {
       if (threadIdx.x == 0) {
         const int slot = atomicAdd(P.retry_count, 1);
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(NT) mpc_solve_kernel(const __grid_constant__ S
 }
 
 struct ClassCfg {
-  int nv_cap, m_cap, in_fast, threads, grid;
+  int nv_cap, m_cap, in_fast, threads, grid, variant;
   size_t smem;
   mpc::Layout L;
 };
@@ -200,6 +209,9 @@ struct mpc_batch {
   char* slab = nullptr;
   std::vector<ClassCfg> classes;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // timing ring: event pairs around every class kernel of the last kRing solves (no sync while recording)
+  std::vector<cudaEvent_t> ring0, ring1;
+  long ring_pos = 0, ring_mark = 0;
   bool timed = false;
   long launches = 0;
   int max_iter = 4000;
@@ -221,14 +233,28 @@ namespace {
     }                                                                                   \
   } while (0)
 
-template <int NT>
+// kernel variants: padded size -> (threads, thread grid, register tile)
+enum { V_64 = 0, V_96, V_128, V_160, V_GENERIC, V_COUNT };
+#define MPC_VARIANT_CALL(v, EXPR)                                        \
+  switch (v) {                                                           \
+    case V_64: { auto kern = mpc_solve_kernel<128, 16, 8, 4, 8, 4>; EXPR; } break;      \
+    case V_96: { auto kern = mpc_solve_kernel<256, 16, 16, 6, 6, 2>; EXPR; } break;     \
+    case V_128: { auto kern = mpc_solve_kernel<256, 16, 16, 8, 8, 1>; EXPR; } break;    \
+    case V_160: { auto kern = mpc_solve_kernel<256, 16, 16, 10, 10, 1>; EXPR; } break;   \
+    default: { auto kern = mpc_solve_kernel<256, 0, 0, 0, 0, 1>; EXPR; } break;         \
+  }
+const int kVariantThreads[V_COUNT] = {128, 256, 256, 256, 256};
+const int kVariantPad[V_COUNT] = {64, 96, 128, 160, 0};
+
 int configure_kernel(mpc_batch* eng, ClassCfg& c) {
-  // the attribute is per template instantiation, shared by every class that uses it: raise it to the device limit
+  // the attribute is per kernel instantiation: raise it to the device limit
   int max_smem = 0;
   CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, eng->device));
-  CK(cudaFuncSetAttribute(mpc_solve_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_solve_kernel<NT>, NT, c.smem));
+  MPC_VARIANT_CALL(c.variant, {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c.threads, c.smem));
+  });
   if (occ < 1) {
     eng->err = "solve kernel does not fit on an SM";
     return MPC_E_CUDA;
@@ -238,11 +264,11 @@ int configure_kernel(mpc_batch* eng, ClassCfg& c) {
 }
 
 // largest working-set capacity whose T tile hides under the assembly temporaries
-int free_m_cap(int h, int nv_cap) {
+int free_m_cap(int h, int nv_cap, int npad) {
   int m = 8;
   while (m < nv_cap) {
     const int mm = m + 1;
-    const int gi = mm * (mm | 1) + 3 * nv_cap + 4 * (mm + 1);
+    const int gi = mm * (mm | 1) + 2 * nv_cap + 2 * (npad + 2) + 4 * (mm + 1);
     if (gi > mpc::kAsmDoubles(h)) break;
     m = mm;
   }
@@ -260,13 +286,14 @@ int build_classes(mpc_batch* eng) {
   for (int cap : caps) {
     ClassCfg c;
     c.nv_cap = cap;
-    c.m_cap = free_m_cap(h, cap);
+    c.variant = cap <= 64 ? V_64 : cap <= 96 ? V_96 : cap <= 128 ? V_128 : V_160;
+    c.threads = kVariantThreads[c.variant];
+    c.m_cap = free_m_cap(h, cap, kVariantPad[c.variant]);
     c.in_fast = 1;
-    c.L = mpc::make_layout(h, c.nv_cap, c.m_cap, 1);
+    c.L = mpc::make_layout(h, c.nv_cap, c.m_cap, 1, kVariantPad[c.variant]);
     c.smem = 16 + 2 * eng->stride + c.L.fast_bytes;
-    c.threads = cap <= 96 ? 128 : 256;
     if ((int)c.smem > max_smem) continue;
-    int rc = c.threads == 128 ? configure_kernel<128>(eng, c) : configure_kernel<256>(eng, c);
+    int rc = configure_kernel(eng, c);
     if (rc) return rc;
     eng->classes.push_back(c);
   }
@@ -277,8 +304,9 @@ int build_classes(mpc_batch* eng) {
   big.in_fast = 0;
   big.L = mpc::make_layout(h, big.nv_cap, big.m_cap, 0);
   big.smem = 16 + 2 * eng->stride + big.L.fast_bytes;
-  big.threads = 256;
-  int rc = configure_kernel<256>(eng, big);
+  big.variant = V_GENERIC;
+  big.threads = kVariantThreads[V_GENERIC];
+  int rc = configure_kernel(eng, big);
   if (rc) return rc;
   big.grid = std::min(big.grid, eng->sms);  // one slab per SM keeps the slabs inside L2
   eng->classes.push_back(big);
@@ -306,8 +334,7 @@ void fill_params(const mpc_batch* eng, SolveParams& P, const void* records, int 
 }
 
 int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int grid, cudaStream_t st) {
-  if (c.threads == 128) mpc_solve_kernel<128><<<grid, 128, c.smem, st>>>(P);
-  else mpc_solve_kernel<256><<<grid, 256, c.smem, st>>>(P);
+  MPC_VARIANT_CALL(c.variant, (kern<<<grid, c.threads, c.smem, st>>>(P)));
   eng->launches++;
   CK(cudaGetLastError());
   return MPC_OK;
@@ -338,10 +365,16 @@ int solve_on_stream(mpc_batch* eng, const void* records, int batch, float* force
     P.nvar_out = nvar_out;
     P.H_out = H_out;
     P.g_out = g_out;
+    const size_t slot = (size_t)(eng->ring_pos % kRing) * kMaxClasses + ci;
+    if (eng->timed) CK(cudaEventRecord(eng->ring0[slot], st));
     int rc = launch_solve(eng, c, P, std::min(c.grid, batch), st);
     if (rc) return rc;
+    if (eng->timed) CK(cudaEventRecord(eng->ring1[slot], st));
   }
-  if (eng->timed) CK(cudaEventRecord(eng->ev1, st));
+  if (eng->timed) {
+    CK(cudaEventRecord(eng->ev1, st));
+    eng->ring_pos++;
+  }
   return MPC_OK;
 }
 
@@ -393,6 +426,12 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
   CKC(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&eng->ev0));
   CKC(cudaEventCreate(&eng->ev1));
+  eng->ring0.assign((size_t)kRing * kMaxClasses, nullptr);
+  eng->ring1.assign((size_t)kRing * kMaxClasses, nullptr);
+  for (size_t i = 0; i < eng->ring0.size(); i++) {
+    CKC(cudaEventCreate(&eng->ring0[i]));
+    CKC(cudaEventCreate(&eng->ring1[i]));
+  }
   int rc = build_classes(eng);
   if (rc) return fail(rc);
   const size_t B = (size_t)max_batch, NU = 12 * (size_t)horizon;
@@ -437,6 +476,10 @@ void mpc_batch_destroy(mpc_batch_t* eng) {
   cudaFree(eng->slab);
   if (eng->ev0) cudaEventDestroy(eng->ev0);
   if (eng->ev1) cudaEventDestroy(eng->ev1);
+  for (cudaEvent_t e : eng->ring0)
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : eng->ring1)
+    if (e) cudaEventDestroy(e);
   if (eng->stream) cudaStreamDestroy(eng->stream);
   delete eng;
 }
@@ -466,7 +509,7 @@ int mpc_batch_solve_host(mpc_batch_t* eng, const void* records_host, int batch, 
   cudaStream_t st = eng->stream;
   // pageable -> pinned staging on the host, then one async H2D; callers that already hold
   // pinned memory pay one memcpy (the record block is < 1 KB per problem)
-  memcpy(eng->rec_pin, records_host, (size_t)batch * eng->stride);
+  if (records_host != (const void*)eng->rec_pin) memcpy(eng->rec_pin, records_host, (size_t)batch * eng->stride);
   CK(cudaMemcpyAsync(eng->rec_dev, eng->rec_pin, (size_t)batch * eng->stride, cudaMemcpyHostToDevice, st));
   int rc = solve_on_stream(eng, eng->rec_dev, batch, eng->forces_dev, solution_host ? eng->sol_dev : nullptr,
                            eng->status_dev, st, nullptr, nullptr, nullptr);
@@ -477,9 +520,11 @@ int mpc_batch_solve_host(mpc_batch_t* eng, const void* records_host, int batch, 
   if (status_host)
     CK(cudaMemcpyAsync(eng->status_pin, eng->status_dev, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  memcpy(forces_host, eng->forces_pin, (size_t)batch * 12 * sizeof(float));
-  if (solution_host) memcpy(solution_host, eng->sol_pin, (size_t)batch * NU * sizeof(double));
-  if (status_host) memcpy(status_host, eng->status_pin, (size_t)batch * sizeof(int32_t));
+  if (forces_host != eng->forces_pin) memcpy(forces_host, eng->forces_pin, (size_t)batch * 12 * sizeof(float));
+  if (solution_host && solution_host != eng->sol_pin)
+    memcpy(solution_host, eng->sol_pin, (size_t)batch * NU * sizeof(double));
+  if (status_host && status_host != eng->status_pin)
+    memcpy(status_host, eng->status_pin, (size_t)batch * sizeof(int32_t));
   return MPC_OK;
 }
 
@@ -523,6 +568,46 @@ float mpc_batch_last_solve_kernel_ms(mpc_batch_t* eng) {
   if (cudaEventSynchronize(eng->ev1) != cudaSuccess) return -1.f;
   if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) != cudaSuccess) return -1.f;
   return ms;
+}
+
+float mpc_batch_last_class_kernel_ms(mpc_batch_t* eng, int idx) {
+  if (!eng || !eng->timed || idx < 0 || idx >= (int)eng->classes.size() || eng->ring_pos == 0) return -1.f;
+  const size_t slot = (size_t)((eng->ring_pos - 1) % kRing) * kMaxClasses + idx;
+  float ms = -1.f;
+  if (cudaEventSynchronize(eng->ring1[slot]) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, eng->ring0[slot], eng->ring1[slot]) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+void mpc_batch_timing_mark(mpc_batch_t* eng) {
+  if (eng) eng->ring_mark = eng->ring_pos;
+}
+
+int mpc_batch_timing_collect(mpc_batch_t* eng, int idx, float* mean_ms, int* n_solves) {
+  if (!eng || !eng->timed || idx < 0 || idx >= (int)eng->classes.size() || !mean_ms) return MPC_E_ARG;
+  long first = std::max(eng->ring_mark, eng->ring_pos - kRing);
+  double sum = 0;
+  int n = 0;
+  for (long s = first; s < eng->ring_pos; s++) {
+    const size_t slot = (size_t)(s % kRing) * kMaxClasses + idx;
+    float ms = 0;
+    CK(cudaEventSynchronize(eng->ring1[slot]));
+    CK(cudaEventElapsedTime(&ms, eng->ring0[slot], eng->ring1[slot]));
+    sum += ms;
+    n++;
+  }
+  *mean_ms = n ? (float)(sum / n) : -1.f;
+  if (n_solves) *n_solves = n;
+  return MPC_OK;
+}
+
+int mpc_batch_host_buffers(mpc_batch_t* eng, void** records, float** forces, double** solution, int32_t** status) {
+  if (!eng) return MPC_E_ARG;
+  if (records) *records = eng->rec_pin;
+  if (forces) *forces = eng->forces_pin;
+  if (solution) *solution = eng->sol_pin;
+  if (status) *status = eng->status_pin;
+  return MPC_OK;
 }
 
 const char* mpc_batch_last_error(const mpc_batch_t* eng) { return eng ? eng->err.c_str() : ""; }

@@ -25,10 +25,12 @@ BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_creat
                  "mpc_batch_solve_device", "mpc_batch_solve_host", "mpc_batch_assemble_device",
                  "mpc_batch_set_gather_peers", "mpc_batch_set_max_iterations", "mpc_batch_set_timing",
                  "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
-                 "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_error", "mpc_last_error", "mpc_batch_horizon"]
+                 "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_class_kernel_ms", "mpc_batch_timing_mark",
+                 "mpc_batch_timing_collect", "mpc_batch_host_buffers",
+                 "mpc_batch_last_error", "mpc_last_error", "mpc_batch_horizon"]
 LEGACY_SYMBOLS = ["setup_problem", "update_problem_data", "update_problem_data_floats", "get_solution",
                   "update_solver_settings", "_Z13update_x_dragf", "mpc_last_status", "mpc_last_iterations",
-                  "mpc_set_robot", "mpc_shutdown"]
+                  "mpc_set_robot", "mpc_shutdown", "mpc_legacy_record"]
 
 
 class MpcError(RuntimeError):
@@ -75,6 +77,13 @@ def lib():
     L.mpc_batch_kernel_launches.restype = ctypes.c_long
     L.mpc_batch_last_solve_kernel_ms.argtypes = [vp]
     L.mpc_batch_last_solve_kernel_ms.restype = f32
+    L.mpc_batch_last_class_kernel_ms.argtypes = [vp, i32]
+    L.mpc_batch_last_class_kernel_ms.restype = f32
+    L.mpc_batch_timing_mark.argtypes = [vp]
+    L.mpc_batch_timing_mark.restype = None
+    L.mpc_batch_timing_collect.argtypes = [vp, i32, ctypes.POINTER(f32), ctypes.POINTER(i32)]
+    L.mpc_batch_host_buffers.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                         ctypes.POINTER(vp)]
     L.mpc_batch_last_error.argtypes = [vp]
     L.mpc_batch_last_error.restype = ctypes.c_char_p
     L.mpc_last_error.restype = ctypes.c_char_p
@@ -96,6 +105,7 @@ def lib():
     L.mpc_set_robot.argtypes = [fp, f32]
     L.mpc_set_robot.restype = None
     L.mpc_shutdown.restype = None
+    L.mpc_legacy_record.argtypes = [vp]
     _LIB = L
     return L
 
@@ -143,6 +153,36 @@ class MpcBatch:
     def last_solve_kernel_ms(self):
         return float(self._L.mpc_batch_last_solve_kernel_ms(self._h))
 
+    def last_class_kernel_ms(self, idx):
+        return float(self._L.mpc_batch_last_class_kernel_ms(self._h, int(idx)))
+
+    def timing_mark(self):
+        self._L.mpc_batch_timing_mark(self._h)
+
+    def timing_collect(self, idx):
+        """(mean ms, n) of size class idx's solve kernel over the solves since timing_mark() (last 256 at most)."""
+        ms, n = ctypes.c_float(), ctypes.c_int()
+        self._check(self._L.mpc_batch_timing_collect(self._h, int(idx), ctypes.byref(ms), ctypes.byref(n)),
+                    "timing_collect")
+        return float(ms.value), int(n.value)
+
+    def host_buffers(self):
+        """numpy views of the engine's pinned staging buffers: (records [max_batch, stride] u8,
+        forces [max_batch, 12] f32, solution [max_batch, 12h] f64, status [max_batch] i32).  Passing these to
+        solve_host skips the pageable->pinned copies."""
+        ptrs = [ctypes.c_void_p() for _ in range(4)]
+        self._check(self._L.mpc_batch_host_buffers(self._h, *[ctypes.byref(p) for p in ptrs]), "host_buffers")
+        B, NU = self.max_batch, 12 * self.horizon
+
+        def view(p, nbytes, dtype, shape):
+            buf = (ctypes.c_char * nbytes).from_address(p.value)
+            return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+        return (view(ptrs[0], B * self.stride, np.uint8, (B, self.stride)),
+                view(ptrs[1], B * 48, np.float32, (B, 12)),
+                view(ptrs[2], B * NU * 8, np.float64, (B, NU)),
+                view(ptrs[3], B * 4, np.int32, (B,)))
+
     def kernel_launches(self):
         return int(self._L.mpc_batch_kernel_launches(self._h))
 
@@ -184,15 +224,17 @@ class MpcBatch:
         self._check(rc, "mpc_batch_solve_device")
         return forces, solution, status
 
-    def solve_host(self, records, want_solution=False, out_forces=None):
+    def solve_host(self, records, want_solution=False, out_forces=None, out_status=None, out_solution=None):
         """records: numpy uint8 [B, stride] in host memory.  Synchronous: H2D, kernels, D2H.
         Returns (forces [B,12] f32, solution [B,12h] f64 | None, status [B] int32)."""
         records = np.ascontiguousarray(records, np.uint8)
         B = records.shape[0]
         assert records.shape[1] == self.stride
         forces = out_forces if out_forces is not None else np.empty((B, 12), np.float32)
-        sol = np.empty((B, 12 * self.horizon), np.float64) if want_solution else None
-        status = np.empty((B,), np.int32)
+        want_solution = want_solution or out_solution is not None
+        sol = out_solution if out_solution is not None else (
+            np.empty((B, 12 * self.horizon), np.float64) if want_solution else None)
+        status = out_status if out_status is not None else np.empty((B,), np.int32)
         rc = self._L.mpc_batch_solve_host(self._h, records.ctypes.data, B, forces.ctypes.data,
                                           sol.ctypes.data if want_solution else None, status.ctypes.data)
         self._check(rc, "mpc_batch_solve_host")

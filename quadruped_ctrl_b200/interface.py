@@ -65,3 +65,13 @@ def set_robot(I_body_diag, mass):
 
 def shutdown():
     _E.lib().mpc_shutdown()
+
+
+def legacy_record(horizon):
+    """The inputs last handed to the legacy calls, as one packed batch record (uint8 [stride])."""
+    from . import records as R
+    out = np.zeros(R.record_stride(horizon), np.uint8)
+    h = _E.lib().mpc_legacy_record(out.ctypes.data)
+    if h != horizon:
+        raise _E.MpcError("mpc_legacy_record: horizon is %d, expected %d" % (h, horizon))
+    return out

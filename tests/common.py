@@ -1,0 +1,56 @@
+"""Shared helpers for the test suite."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden", "mpc_golden.npz")
+GOLDEN_CASES = ["config1", "config2", "config3", "config4", "config5", "four_stance", "edge"]
+
+
+def rel(a, b, floor=1.0):
+    """Per-problem relative L2 error with an absolute floor of `floor` newtons on the norm (problems whose
+    optimum is ~0 N -- every stance leg at the apex of its cone -- have no meaningful relative error)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), floor)
+
+
+def load_golden():
+    return np.load(GOLDEN)
+
+
+_EMU = None
+
+
+def emu_lib():
+    """TEST-ONLY single-thread host build of the kernel source (tests/emu/emu.cpp)."""
+    global _EMU
+    if _EMU is None:
+        src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
+        so = os.path.join(ROOT, "tests", "emu", "libmpc_emu.so")
+        core = os.path.join(ROOT, "quadruped_ctrl_b200", "csrc", "mpc_core.h")
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", src, "-o", so])
+        _EMU = ctypes.CDLL(so)
+    return _EMU
+
+
+def emu_solve(rec, h, nv_cap=0, m_cap=0, want_qp=False, max_iter=100000):
+    L = emu_lib()
+    rec = np.ascontiguousarray(rec, np.uint8)
+    B = rec.shape[0]
+    NU = 12 * h
+    f = np.zeros((B, 12), np.float32)
+    sol = np.zeros((B, NU))
+    info = np.zeros((B, 4), np.int32)
+    H = np.zeros((B, NU, NU)) if want_qp else None
+    g = np.zeros((B, NU)) if want_qp else None
+    vp = ctypes.c_void_p
+    rc = L.emu_solve_batch(vp(rec.ctypes.data), B, h, nv_cap, m_cap, max_iter, vp(f.ctypes.data), vp(sol.ctypes.data),
+                           vp(info.ctypes.data), vp(H.ctypes.data) if want_qp else None,
+                           vp(g.ctypes.data) if want_qp else None)
+    assert rc == 0, rc
+    return dict(forces=f, sol=sol, nv=info[:, 0], m=info[:, 1], iters=info[:, 2], status=info[:, 3], H=H, g=g)

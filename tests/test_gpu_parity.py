@@ -8,9 +8,14 @@ in fp64, so it is compared
   * with oracle32 (the reference-faithful path) at 1e-4 on the first-step forces for every problem
     whose oracle32 answer is itself within 2e-5 of oracle64 (the well-conditioned set).
 """
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from quadruped_ctrl_b200 import engine as E
 from quadruped_ctrl_b200 import workloads as W
@@ -18,8 +23,7 @@ from quadruped_ctrl_b200 import workloads as W
 pytestmark = pytest.mark.gpu
 
 
-def rel(a, b):
-    return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-9)
+from common import GOLDEN_CASES, load_golden, rel  # noqa: E402
 
 
 CASES = [("config1", None), ("config2", 512), ("config4", 512), ("four_stance", 128), ("config5", 192),
@@ -83,3 +87,123 @@ def test_device_entry_matches_host_entry(cuda_engine_factory):
     assert (f_dev.cpu().numpy() == f_host).all()
     assert (s_dev.cpu().numpy() == s_host).all()
     assert (st_dev.cpu().numpy() == st_host).all()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_fixture(name, cuda_engine_factory):
+    """Committed fixture (reference qpOASES outputs generated in the build container): no oracle needed."""
+    G = load_golden()
+    rec, h = G[name + "_records"], int(G[name + "_h"])
+    eng = cuda_engine_factory(h, rec.shape[0])
+    forces, sol, status = eng.solve_host(rec, want_solution=True)
+    assert (E.status_code(status) == E.STATUS_OPTIMAL).all()
+    ok = G[name + "_o64_rc"] == 0
+    assert rel(sol, G[name + "_o64_sol"])[ok].max() < 1e-6
+    cloud = rel(G[name + "_o32_sol"][:, :12], G[name + "_o64_sol"][:, :12])
+    e32 = rel(forces, G[name + "_o32_sol"][:, :12])
+    ok32 = ok & (G[name + "_o32_rc"] == 0)
+    assert (e32[ok32] <= cloud[ok32] + 1e-5).all()
+    well = ok32 & (cloud <= 2e-5)
+    if well.any():
+        assert e32[well].max() <= 1e-4
+
+
+def test_legacy_interface_matches_oracle(oracle):
+    """setup_problem -> update_x_drag -> update_solver_settings -> update_problem_data_floats -> get_solution,
+    the call sequence of ConvexMPCLocomotion.cpp:630-674, for every gait phase of config 1 and a horizon switch."""
+    from quadruped_ctrl_b200 import interface as I
+    from quadruped_ctrl_b200 import records as R
+    for rec, h in ((W.config1(), 10), (W.config5(4), 16), (W.config1(), 10)):
+        f = R.unpack_records(rec, h)
+        ref = oracle.solve_batch(rec, h, 64)
+        for b in range(rec.shape[0]):
+            I.setup_problem(float(f["dt"][b]), h, float(f["mu"][b]), float(f["f_max"][b]))
+            I.update_x_drag(float(f["x_drag"][b]))
+            I.update_solver_settings(10000, 1e-7, 1e-8, 1.5, 0.1, 0.0)
+            I.update_problem_data_floats(f["p"][b], f["v"][b], f["q"][b], f["w"][b], f["r"][b], float(f["yaw"][b]),
+                                         f["weights"][b], f["traj"][b], float(f["alpha"][b]), f["gait"][b].astype(np.int32))
+            assert I.last_status() == 0
+            got = np.array([I.get_solution(i) for i in range(12 * h)])
+            assert rel(got[None], ref["sol"][b][None])[0] < 1e-6
+    # the double-precision entry narrows to float and takes the same path
+    b = 3
+    rec, h = W.config1(), 10
+    f = R.unpack_records(rec, h)
+    I.setup_problem(float(f["dt"][b]), h, float(f["mu"][b]), float(f["f_max"][b]))
+    I.update_problem_data(f["p"][b].astype(np.float64), f["v"][b].astype(np.float64), f["q"][b].astype(np.float64),
+                          f["w"][b].astype(np.float64), f["r"][b].astype(np.float64), float(f["yaw"][b]),
+                          f["weights"][b].astype(np.float64), f["traj"][b].astype(np.float64), float(f["alpha"][b]),
+                          f["gait"][b].astype(np.int32))
+    ref = oracle.solve_batch(rec, h, 64)
+    got = np.array([I.get_solution(i) for i in range(12)])
+    assert rel(got[None], ref["forces"][b][None])[0] < 1e-6
+    I.shutdown()
+
+
+def test_status_codes_and_failure_outputs(cuda_engine_factory):
+    from quadruped_ctrl_b200 import records as R
+    h = 10
+    rec = W.config2(6, h, 5)
+    f = rec.view(np.float32)
+    go = R.gait_offset(h)
+    rec[0, go:go + 4 * h] = 0
+    f[1, R.REC_P] = np.nan
+    f[2, R.REC_MU] = 0.0
+    f[3, R.REC_MASS] = -1.0
+    f[4, R.REC_FMAX] = 0.001
+    eng = cuda_engine_factory(h, 6)
+    forces, sol, status = eng.solve_host(rec, want_solution=True)
+    assert E.status_code(status).tolist() == [E.STATUS_NO_STANCE, E.STATUS_BAD_INPUT, E.STATUS_BAD_INPUT,
+                                              E.STATUS_BAD_INPUT, E.STATUS_NO_STANCE, E.STATUS_OPTIMAL]
+    assert (forces[:5] == 0).all() and (sol[:5] == 0).all() and np.abs(forces[5]).max() > 1.0
+    eng.set_max_iterations(1)
+    rec = W.four_stance(16, h, 3)
+    eng2 = cuda_engine_factory(h, 16)
+    eng2.set_max_iterations(1)
+    _, _, st = eng2.solve_host(rec)
+    assert (E.status_code(st) == E.STATUS_MAX_ITER).any()
+
+
+def test_full_size_properties(cuda_engine_factory):
+    """BASELINE sizes (B=4096 config 2; B=65536 config 4 shard-free) through size-independent properties:
+    every problem optimal, swing legs exactly zero, friction pyramid and force limits hold, a permuted batch
+    gives the permuted answer bit for bit, and repeated solves are bitwise reproducible."""
+    for name, B in (("config2", 4096), ("config4", 65536)):
+        h = 10
+        rec = W.CONFIGS[name](B)
+        eng = cuda_engine_factory(h, B)
+        d = torch.from_numpy(rec).cuda()
+        forces, sol, status = eng.solve_device(d, want_solution=True)
+        torch.cuda.synchronize()
+        F, S, st = forces.cpu().numpy(), sol.cpu().numpy(), status.cpu().numpy()
+        assert (E.status_code(st) == E.STATUS_OPTIMAL).all()
+        gait = rec[:, 4 * (48 + 12 * h):4 * (48 + 12 * h) + 4 * h].reshape(B, h * 4)
+        X = S.reshape(B, 4 * h, 3)
+        assert (X[gait == 0] == 0).all()
+        fz = X[..., 2]
+        assert (fz >= -1e-7).all() and (fz <= 120 + 1e-7).all()
+        assert (np.abs(X[..., 0]) <= 0.4 * fz + 1e-6).all() and (np.abs(X[..., 1]) <= 0.4 * fz + 1e-6).all()
+        assert np.array_equal(F, S[:, :12].astype(np.float32))
+        perm = np.random.default_rng(0).permutation(B)
+        f2, s2, _ = eng.solve_device(torch.from_numpy(rec[perm]).cuda(), want_solution=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(s2.cpu().numpy(), S[perm])
+        f3, _, _ = eng.solve_device(d)
+        torch.cuda.synchronize()
+        assert np.array_equal(f3.cpu().numpy(), F)
+
+
+def test_working_set_overflow_is_requeued_not_dropped(oracle, cuda_engine_factory):
+    """Problems whose active set outgrows the shared-memory tile of their size class are re-solved by the
+    catch-all class inside the same call.  Forced here with f_max so low that most fz rows saturate."""
+    from quadruped_ctrl_b200 import records as R
+    h = 10
+    rec = W.four_stance(64, h, 9)
+    rec.view(np.float32)[:, R.REC_FMAX] = 6.0
+    eng = cuda_engine_factory(h, 64)
+    m_cap = eng.classes()[-2]["m_cap"]
+    forces, sol, status = eng.solve_host(rec, want_solution=True)
+    assert (E.status_code(status) == E.STATUS_OPTIMAL).all()
+    o = oracle.solve_batch(rec, h, 64, "port")
+    assert rel(sol, o["sol"]).max() < 1e-6
+    assert E.status_iterations(status).max() > m_cap   # at least one problem really did overflow the tile
