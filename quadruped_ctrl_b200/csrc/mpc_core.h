@@ -275,69 +275,104 @@ MPC_HD bool finite_f(float v) { return v == v && fabsf(v) <= 3.0e38f; }
 // Stage 1: dynamics, discretisation polynomial, QP assembly (reduced, fp64).
 // Leaves nv, ns, stance[], posk[], Hm (= reduced qH), g (= reduced qg) behind.
 // ---------------------------------------------------------------------------
+// (A X)[i][j] and (A^2 X)[i][j] for the continuous-time A of ct_ss_mats (SolverMPC.cpp:237-244):
+// A[0:3,6:9] = R_yaw', A[3,9] = A[4,10] = A[5,11] = 1, A[11,9] = x_drag, A[11,12] = 1, zero elsewhere,
+// hence A^2 = (x_drag e9' + e12') on row 5 only and A^3 = 0.  X has leading dimension ldx.
+MPC_HD double apply_A(const double* X, int ldx, int i, int j, double yc, double ys, double xd) {
+  switch (i) {
+    case 0: return yc * X[6 * ldx + j] + ys * X[7 * ldx + j];
+    case 1: return -ys * X[6 * ldx + j] + yc * X[7 * ldx + j];
+    case 2: return X[8 * ldx + j];
+    case 3: return X[9 * ldx + j];
+    case 4: return X[10 * ldx + j];
+    case 5: return X[11 * ldx + j];
+    case 11: return xd * X[9 * ldx + j] + X[12 * ldx + j];
+    default: return 0.0;
+  }
+}
+MPC_HD double apply_A2(const double* X, int ldx, int i, int j, double xd) {
+  return i == 5 ? xd * X[9 * ldx + j] + X[12 * ldx + j] : 0.0;
+}
+
 template <class Cx>
 MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, const Work& k) {
   const int h = k.h;
   Scalars* sc = k.sc;
-  double* A = k.M;          // 13x13   (M region is free until the C_a are final)
-  double* B = A + 169;      // 13x12
-  double* t1 = B + 156;     // 13x12 scratch
-  double* t2 = t1 + 156;    // 13x12 scratch
+  double* B = k.M;          // 13x12   (the M region is free until the C_a are final)
+  double* t1 = B + 156;     // A B
+  double* t2 = t1 + 156;    // A^2 B
+  double* scr = t2 + 156;   // cos(yaw), sin(yaw)
   double* C0 = k.C;
   double* C1 = C0 + 156;
   double* C2 = C1 + 156;
   double* x0 = k.xs;        // 13
   double* Ax0 = x0 + 13;
   double* A2x0 = Ax0 + 13;
+  double* mom = k.Hm;       // [3][h][12] moments of the tracking error; Hm is free until the H blocks are written
+  int* flag = k.act;        // 0/1 stance flags while the stance list is built (act[] proper is set up later)
+  const float fmax = rec[MPC_REC_FMAX];
 
-  // ---- stance list / swing elimination (SolverMPC.cpp:441-469) and input check ----
+  // ---- P0: reset, stance flags (SolverMPC.cpp:441-469: U_b(5k+4) = gait[k]*f_max "near zero" => eliminated) ----
   MPC_ONE {
-    int status = MPC_STATUS_OPTIMAL;
-    for (int i = 0; i < MPC_REC_TRAJ + 12 * h; i++)
-      if (!finite_f(rec[i])) status = MPC_STATUS_BAD_INPUT;
-    const float fmax = rec[MPC_REC_FMAX];
-    if (!(rec[MPC_REC_MU] > 0.f) || !(rec[MPC_REC_MASS] > 0.f) || !(rec[MPC_REC_DT] > 0.f) ||
-        !(rec[MPC_REC_IBODY] > 0.f) || !(rec[MPC_REC_IBODY + 1] > 0.f) || !(rec[MPC_REC_IBODY + 2] > 0.f) ||
-        !(fmax >= 0.f))
-      status = MPC_STATUS_BAD_INPUT;
-    int ns = 0;
-    for (int kk = 0; kk < 4 * h; kk++) {
-      // U_b(5k+4) = gait[k]*f_max in float; the row is eliminated when it is "near zero"
-      const float ub = (float)gait[kk] * fmax;
-      const bool swing = ((double)ub < 0.01 && (double)ub > -0.01);
-      if (!swing) { k.stance[ns] = kk; k.posk[kk] = ns; ns++; }
-      else k.posk[kk] = -1;
-    }
-    if (status == MPC_STATUS_OPTIMAL && ns == 0) status = MPC_STATUS_NO_STANCE;
-    sc->ns = ns;
-    sc->nv = 3 * ns;
-    sc->status = status;
+    sc->status = MPC_STATUS_OPTIMAL;
     sc->m = 0;
     sc->iters = 0;
   }
-  // ---- A_c, B_c (SolverMPC.cpp:235-254) --------------------------------------
-  MPC_FOR(i, 169 + 156) k.M[i] = 0.0;
+  MPC_FOR(kk, 4 * h) {
+    const float ub = (float)gait[kk] * fmax;
+    flag[kk] = ((double)ub < 0.01 && (double)ub > -0.01) ? 0 : 1;
+  }
+  MPC_FOR(i, 156) B[i] = 0.0;
   cx.sync();
-  if (sc->status != MPC_STATUS_OPTIMAL) return;
+  // ---- P1: input check, stance list, the four transcendental groups on four different warps ----
+  MPC_FOR(i, MPC_REC_TRAJ + 12 * h)
+    if (!finite_f(rec[i])) sc->status = MPC_STATUS_BAD_INPUT;  // same value from every writer
   MPC_ONE {
-    const double yaw = (double)rec[MPC_REC_YAW];
-    const double yc = cos(yaw), ys = sin(yaw);
-    const double R[3][3] = {{yc, -ys, 0}, {ys, yc, 0}, {0, 0, 1}};  // RobotState.cpp:33-35
-    const double Ib[3] = {(double)rec[MPC_REC_IBODY], (double)rec[MPC_REC_IBODY + 1], (double)rec[MPC_REC_IBODY + 2]};
-    // quat_to_rpy (SolverMPC.cpp:257-267), q = (w,x,y,z)
+    if (!(rec[MPC_REC_MU] > 0.f) || !(rec[MPC_REC_MASS] > 0.f) || !(rec[MPC_REC_DT] > 0.f) ||
+        !(rec[MPC_REC_IBODY] > 0.f) || !(rec[MPC_REC_IBODY + 1] > 0.f) || !(rec[MPC_REC_IBODY + 2] > 0.f) ||
+        !(fmax >= 0.f))
+      sc->status = MPC_STATUS_BAD_INPUT;
+  }
+  MPC_FOR(kk, 4 * h) {
+    int pos = 0;
+    for (int q = 0; q < kk; q++) pos += flag[q];
+    if (flag[kk]) { k.stance[pos] = kk; k.posk[kk] = pos; }
+    else k.posk[kk] = -1;
+    if (kk == 4 * h - 1) { sc->ns = pos + flag[kk]; sc->nv = 3 * (pos + flag[kk]); }
+  }
+  {
+    // quat_to_rpy (SolverMPC.cpp:257-267), q = (w,x,y,z); x_0 = [rpy(2), rpy(1), rpy(0), ...] (:318)
     const double qw = rec[MPC_REC_Q], qx = rec[MPC_REC_Q + 1], qy = rec[MPC_REC_Q + 2], qz = rec[MPC_REC_Q + 3];
-    double as = -2. * (qx * qz - qw * qy);
-    if (!(as < .99999)) as = .99999;
-    const double rpy0 = atan2(2. * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
-    const double rpy1 = asin(as);
-    const double rpy2 = atan2(2. * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
-    x0[0] = rpy2; x0[1] = rpy1; x0[2] = rpy0;
+    const int lanes = cx.nt >= 128 ? 32 : 0;  // task t runs on thread 32*t (one per warp); single thread: all on 0
+    if (cx.tid == 0 * lanes) {
+      const double yaw = (double)rec[MPC_REC_YAW];
+      scr[0] = cos(yaw);
+      scr[1] = sin(yaw);
+    }
+    if (cx.tid == 1 * lanes) x0[2] = atan2(2. * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
+    if (cx.tid == 2 * lanes) {
+      double as = -2. * (qx * qz - qw * qy);
+      if (!(as < .99999)) as = .99999;
+      x0[1] = asin(as);
+    }
+    if (cx.tid == 3 * lanes) x0[0] = atan2(2. * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
+  }
+  cx.sync();
+  // ---- P2: x_0 tail, B_c per leg (ct_ss_mats, SolverMPC.cpp:235-254; cross_mat :226-233) ----
+  MPC_ONE {
+    if (sc->status == MPC_STATUS_OPTIMAL && sc->ns == 0) sc->status = MPC_STATUS_NO_STANCE;
     for (int i = 0; i < 3; i++) {
       x0[3 + i] = rec[MPC_REC_P + i];
       x0[6 + i] = rec[MPC_REC_W + i];
       x0[9 + i] = rec[MPC_REC_V + i];
     }
     x0[12] = (double)-9.8f;
+  }
+  const double yc = scr[0], ys = scr[1];
+  const double xd = (double)rec[MPC_REC_XDRAG];
+  MPC_FOR(b, 4) {
+    const double R[3][3] = {{yc, -ys, 0}, {ys, yc, 0}, {0, 0, 1}};  // RobotState.cpp:33-35
+    const double Ib[3] = {(double)rec[MPC_REC_IBODY], (double)rec[MPC_REC_IBODY + 1], (double)rec[MPC_REC_IBODY + 2]};
     // I_world = R I_body R' and its inverse (SolverMPC.cpp:319, 247)
     double Iw[3][3];
     for (int i = 0; i < 3; i++)
@@ -359,72 +394,42 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
     Ii[2][0] = (Iw[1][0] * Iw[2][1] - Iw[1][1] * Iw[2][0]) / det;
     Ii[2][1] = (Iw[0][1] * Iw[2][0] - Iw[0][0] * Iw[2][1]) / det;
     Ii[2][2] = (Iw[0][0] * Iw[1][1] - Iw[0][1] * Iw[1][0]) / det;
-    A[3 * 13 + 9] = 1.0;
-    A[11 * 13 + 9] = (double)rec[MPC_REC_XDRAG];
-    A[4 * 13 + 10] = 1.0;
-    A[5 * 13 + 11] = 1.0;
-    A[11 * 13 + 12] = 1.0;
-    for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) A[i * 13 + 6 + j] = R[j][i];
     const double minv = 1.0 / (double)rec[MPC_REC_MASS];
-    for (int b = 0; b < 4; b++) {
-      const double rx = rec[MPC_REC_R + b], ry = rec[MPC_REC_R + 4 + b], rz = rec[MPC_REC_R + 8 + b];
-      const double cm[3][3] = {{0, -rz, ry}, {rz, 0, -rx}, {-ry, rx, 0}};
-      for (int i = 0; i < 3; i++) {
-        for (int j = 0; j < 3; j++) {
-          double acc = 0;
-          for (int q = 0; q < 3; q++) acc += Ii[i][q] * cm[q][j];
-          B[(6 + i) * 12 + b * 3 + j] = acc;
-        }
-        B[(9 + i) * 12 + b * 3 + i] = minv;
+    const double rx = rec[MPC_REC_R + b], ry = rec[MPC_REC_R + 4 + b], rz = rec[MPC_REC_R + 8 + b];
+    const double cm[3][3] = {{0, -rz, ry}, {rz, 0, -rx}, {-ry, rx, 0}};
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) {
+        double acc = 0;
+        for (int q = 0; q < 3; q++) acc += Ii[i][q] * cm[q][j];
+        B[(6 + i) * 12 + b * 3 + j] = acc;
       }
+      B[(9 + i) * 12 + b * 3 + i] = minv;
     }
   }
   cx.sync();
+  if (sc->status != MPC_STATUS_OPTIMAL) return;
   const double dt = (double)rec[MPC_REC_DT];
-  // ---- exact discretisation: B_d = dt B + dt^2/2 AB + dt^3/6 A^2 B (c2qp, SolverMPC.cpp:87-101) ----
-  MPC_FOR(e, 156) {  // t1 = A B
+  // ---- P3: A B, A^2 B, A x0, A^2 x0 ----
+  MPC_FOR(e, 156) {
     const int i = e / 12, j = e - 12 * i;
-    double acc = 0;
-    for (int q = 0; q < 13; q++) acc += A[i * 13 + q] * B[q * 12 + j];
-    t1[e] = acc;
+    t1[e] = apply_A(B, 12, i, j, yc, ys, xd);
+    t2[e] = apply_A2(B, 12, i, j, xd);
   }
-  MPC_FOR(e, 13) {  // A x0
-    double acc = 0;
-    for (int q = 0; q < 13; q++) acc += A[e * 13 + q] * x0[q];
-    Ax0[e] = acc;
+  MPC_FOR(e, 13) {
+    Ax0[e] = apply_A(x0, 1, e, 0, yc, ys, xd);
+    A2x0[e] = apply_A2(x0, 1, e, 0, xd);
   }
   cx.sync();
-  MPC_FOR(e, 156) {  // t2 = A (A B)
-    const int i = e / 12, j = e - 12 * i;
-    double acc = 0;
-    for (int q = 0; q < 13; q++) acc += A[i * 13 + q] * t1[q * 12 + j];
-    t2[e] = acc;
-  }
-  MPC_FOR(e, 13) {  // A^2 x0
-    double acc = 0;
-    for (int q = 0; q < 13; q++) acc += A[e * 13 + q] * Ax0[q];
-    A2x0[e] = acc;
-  }
-  cx.sync();
+  // ---- P5: exact discretisation B_d = dt B + dt^2/2 AB + dt^3/6 A^2 B (c2qp, SolverMPC.cpp:87-101) ----
   MPC_FOR(e, 156) C0[e] = dt * B[e] + (dt * dt / 2.0) * t1[e] + (dt * dt * dt / 6.0) * t2[e];
   cx.sync();
-  // ---- Phi_k = A_d^k B_d = C0 + k C1 + k^2 C2 with C1 = dt A B_d, C2 = dt^2/2 A^2 B_d ----
+  // ---- P7: Phi_k = A_d^k B_d = C0 + k C1 + k^2 C2 with C1 = dt A B_d, C2 = dt^2/2 A^2 B_d;
+  //          weighted tracking error q_e[r] = Q (A_d^{r+1} x0 - x_d[r]) (SolverMPC.cpp:335-347,399) ----
   MPC_FOR(e, 156) {
     const int i = e / 12, j = e - 12 * i;
-    double acc = 0;
-    for (int q = 0; q < 13; q++) acc += A[i * 13 + q] * C0[q * 12 + j];
-    t1[e] = acc;
+    C1[e] = dt * apply_A(C0, 12, i, j, yc, ys, xd);
+    C2[e] = (dt * dt / 2.0) * apply_A2(C0, 12, i, j, xd);
   }
-  cx.sync();
-  MPC_FOR(e, 156) {
-    const int i = e / 12, j = e - 12 * i;
-    double acc = 0;
-    for (int q = 0; q < 13; q++) acc += A[i * 13 + q] * t1[q * 12 + j];
-    C1[e] = dt * t1[e];
-    C2[e] = (dt * dt / 2.0) * acc;
-  }
-  // ---- weighted tracking error q_e[r] = Q (A_d^{r+1} x0 - x_d[r]) (SolverMPC.cpp:335-347,399) ----
   MPC_FOR(e, 12 * h) {
     const int r = e / 12, i = e - 12 * r;
     const double tt = (double)(r + 1) * dt;
@@ -432,35 +437,54 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
     k.qe[e] = (double)rec[MPC_REC_WEIGHTS + i] * (xr - (double)rec[MPC_REC_TRAJ + e]);
   }
   cx.sync();
-  // ---- M_ab = C_a' Q C_b (12x12 each).  M overlays A,B,t1,t2, which are dead: the
-  // barrier above is the last point anything reads them. ----
-  MPC_FOR(e, 9 * 144) {
-    const int ab = e / 144, ij = e - 144 * ab;
-    const int a = ab / 3, b = ab - 3 * a, i = ij / 12, j = ij - 12 * i;
-    const double* Ca = C0 + 156 * a;
-    const double* Cb = C0 + 156 * b;
-    double s = 0;
-    for (int q = 0; q < 12; q++) s += Ca[q * 12 + i] * ((double)rec[MPC_REC_WEIGHTS + q] * Cb[q * 12 + j]);
-    k.M[e] = s;
+  // ---- P8: moments mom[a][j][row] = sum_{r>=j} (r-j)^a q_e[r][row] ----
+  const int na = (xd != 0.0) ? 3 : 2;  // without drag C2 == 0 and every k^2 term drops out
+  MPC_FOR(e, na * 12 * h) {
+    const int a = e / (12 * h), jr = e - a * 12 * h, j = jr / 12, row = jr - 12 * j;
+    double acc = 0;
+    for (int r = j; r < h; r++) {
+      const double kd = (double)(r - j);
+      const double w = a == 0 ? 1.0 : (a == 1 ? kd : kd * kd);
+      acc += w * k.qe[12 * r + row];
+    }
+    mom[e] = acc;
   }
   cx.sync();
-  // ---- reduced gradient: g_v = 2 sum_{r>=j} Phi_{r-j}[:,c]' q_e[r] (SolverMPC.cpp:399) ----
+  // ---- P9: reduced gradient g_v = 2 sum_a C_a[:,c]' mom[a][j] (SolverMPC.cpp:399), and the nine tables
+  //          M_ab = C_a' Q C_b (12x12).  Row supports: C0 rows 0..11, C1 rows {0..5,11}, C2 row {5}.
+  //          M overlays B,t1,t2,scr, which are dead: the barrier above is the last point anything reads them. ----
   const int nv = sc->nv, ns = sc->ns;
+  const unsigned rowmask[3] = {0xFFFu, 0x83Fu, 0x020u};
   MPC_FOR(v, nv) {
     const int sidx = v / 3, ax = v - 3 * sidx;
     const int kk = k.stance[sidx], j = kk >> 2, c = (kk & 3) * 3 + ax;
     double acc = 0;
-    for (int r = j; r < h; r++) {
-      const double kd = (double)(r - j), kd2 = kd * kd;
-      const double* q = k.qe + 12 * r;
-      double s = 0;
+    for (int a = 0; a < na; a++) {
+      const double* Ca = C0 + 156 * a;
+      const double* ma = mom + (a * h + j) * 12;
       for (int row = 0; row < 12; row++)
-        s += (C0[row * 12 + c] + kd * C1[row * 12 + c] + kd2 * C2[row * 12 + c]) * q[row];
-      acc += s;
+        if ((rowmask[a] >> row) & 1u) acc += Ca[row * 12 + c] * ma[row];
     }
     k.g[v] = 2.0 * acc;
   }
-  // ---- reduced Hessian, one 3x3 block per stance pair (a >= b) (SolverMPC.cpp:395) ----
+  MPC_FOR(e, 9 * 144) {
+    const int ab = e / 144, ij = e - 144 * ab;
+    const int a = ab / 3, b = ab - 3 * a, i = ij / 12, j = ij - 12 * i;
+    double s = 0;
+    if (a < na && b < na) {
+      const double* Ca = C0 + 156 * a;
+      const double* Cb = C0 + 156 * b;
+      const unsigned mask = rowmask[a] & rowmask[b];
+      for (int q = 0; q < 12; q++)
+        if ((mask >> q) & 1u) s += Ca[q * 12 + i] * ((double)rec[MPC_REC_WEIGHTS + q] * Cb[q * 12 + j]);
+    }
+    k.M[e] = s;
+  }
+  cx.sync();
+  // ---- P11: reduced Hessian, one 3x3 block per stance pair (a >= b) (SolverMPC.cpp:395):
+  //   H[(i,la),(j,lb)] = 2 sum_{pa,pb} s_{pa,pb} M_{pa,pb}[la,lb] + 2 alpha I,
+  //   s_{pa,pb} = sum_{q=0..n} q^pa (q+d)^pb, d = i-j >= 0, n = h-1-i, from the power sums P_e(n) = sum q^e
+  //   (exact small integers in fp64 for every h <= 36). ----
   const double alpha = (double)rec[MPC_REC_ALPHA];
   const int nblk = ns * (ns + 1) / 2;
   MPC_FOR(e, nblk) {
@@ -471,20 +495,19 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
     const int b = e - a * (a + 1) / 2;
     const int ka = k.stance[a], kb = k.stance[b];
     const int i = ka >> 2, la = ka & 3, j = kb >> 2, lb = kb & 3;  // i >= j (stance[] is ascending)
-    const int d = i - j, n = h - 1 - i;
-    double s[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int q = 0; q <= n; q++) {  // exact small-integer sums
-      const double p1 = (double)q, p2 = p1 * p1, r1 = (double)(q + d), r2 = r1 * r1;
-      s[0][0] += 1.0; s[0][1] += r1; s[0][2] += r2;
-      s[1][0] += p1; s[1][1] += p1 * r1; s[1][2] += p1 * r2;
-      s[2][0] += p2; s[2][1] += p2 * r1; s[2][2] += p2 * r2;
-    }
+    const double d = (double)(i - j), n = (double)(h - 1 - i);
+    const double P0 = n + 1.0, P1 = n * (n + 1.0) * 0.5, P2 = n * (n + 1.0) * (2.0 * n + 1.0) / 6.0, P3 = P1 * P1;
+    const double P4 = n * (n + 1.0) * (2.0 * n + 1.0) * (3.0 * n * n + 3.0 * n - 1.0) / 30.0;
+    double s[3][3];
+    s[0][0] = P0;  s[0][1] = P1 + d * P0;  s[0][2] = P2 + 2.0 * d * P1 + d * d * P0;
+    s[1][0] = P1;  s[1][1] = P2 + d * P1;  s[1][2] = P3 + 2.0 * d * P2 + d * d * P1;
+    s[2][0] = P2;  s[2][1] = P3 + d * P2;  s[2][2] = P4 + 2.0 * d * P3 + d * d * P2;
     for (int ax = 0; ax < 3; ax++)
       for (int bx = 0; bx < 3; bx++) {
         const int ci = la * 3 + ax, cj = lb * 3 + bx;
         double acc = 0;
-        for (int pa = 0; pa < 3; pa++)
-          for (int pb = 0; pb < 3; pb++) acc += s[pa][pb] * k.M[(pa * 3 + pb) * 144 + ci * 12 + cj];
+        for (int pa = 0; pa < na; pa++)
+          for (int pb = 0; pb < na; pb++) acc += s[pa][pb] * k.M[(pa * 3 + pb) * 144 + ci * 12 + cj];
         double val = 2.0 * acc;
         if (a == b && ax == bx) val += 2.0 * alpha;
         k.Hm[(3 * a + ax) * k.ld + 3 * b + bx] = val;
@@ -558,7 +581,9 @@ MPC_HD void invert_spd(const Cx& cx, const Work& k) {
 template <int NT, int GR, int GC, int R, int C>
 __device__ __forceinline__ void invert_spd_tiled(const Work& k, int tid) {
   constexpr int NVP = GR * R;
+  constexpr int RATIO = GR / GC;
   static_assert(GR * GC == NT && GC * C == NVP, "tile grid must cover the padded matrix");
+  static_assert(GR % GC == 0 && GC % 2 == 0, "pivot slots must be compile-time: GR a multiple of GC, GC even");
   Scalars* sc = k.sc;
   const int nv = sc->nv, ld = k.ld;
   double* Hm = k.Hm;
@@ -571,47 +596,70 @@ __device__ __forceinline__ void invert_spd_tiled(const Work& k, int tid) {
       const int r = tr + GR * i, c = tc + GC * j;
       a[i][j] = (r < nv && c < nv) ? Hm[r * ld + c] : (r == c ? 1.0 : 0.0);
     }
+  // pivot order: p = q + GC*J for J = 0..C-1 (unrolled: J and the row slot I = J / RATIO are register
+  // indices known at compile time), q = 0..GC-1; any order gives the same inverse.  GC is even, so the
+  // parity of p (which of the two broadcast buffers) is the parity of q.
+  double* const ck0 = k.ck;
+  double* const ck1 = k.ck + (NVP + 2);
+  double* const wr0 = ck0 + tr;  // this thread's rows, written when it owns the pivot column / read as u
+  double* const wr1 = ck1 + tr;
+  const double* const rc0 = ck0 + tc;  // this thread's columns, read as v
+  const double* const rc1 = ck1 + tc;
   bool bad = false;
-  for (int p = 0; p < nv; p++) {
-    double* ck = k.ck + (p & 1) * (NVP + 2);
-    const int jp = p / GC, ip = p / GR;
-    if (tc == p % GC) {  // this thread holds R elements of column p (at j == jp)
 #pragma unroll
-      for (int j = 0; j < C; j++)
-        if (j == jp) {
+  for (int J = 0; J < C; J++) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int I = J / RATIO;              // compile-time after unrolling
+    const int trp0 = GC * (J % RATIO);    // row-grid coordinate of pivot q is trp0 + q
+    if (GC * J >= nv || bad) break;       // uniform
+#pragma unroll 1
+    for (int q = 0; q < GC; q += 2) {
 #pragma unroll
-          for (int i = 0; i < R; i++) ck[tr + GR * i] = a[i][j];
-          if (tr == p % GR) {
+      for (int e = 0; e < 2; e++) {
+        const int qq = q + e;
+        const int p = qq + GC * J;
+        if (p >= nv || bad) break;  // uniform
+        double* const wr = e ? wr1 : wr0;
+        const double* const rc = e ? rc1 : rc0;
+        double* const ckb = e ? ck1 : ck0;
+        const bool own_col = (tc == qq);
+        const bool own_piv = own_col && (tr == trp0 + qq);
+        if (own_col) {
 #pragma unroll
-            for (int i = 0; i < R; i++)
-              if (i == ip) {
-                const double d = a[i][j];
-                ck[p] = d - 1.0;
-                ck[NVP] = 1.0 / d;
-              }
+          for (int i = 0; i < R; i++) wr[GR * i] = a[i][J];
+          if (own_piv) {
+            const double d = a[I][J];
+            ckb[p] = d - 1.0;
+            ckb[NVP] = __drcp_rn(d);
           }
         }
-    }
-    __syncthreads();
-    const double dinv = ck[NVP];
-    if (!(dinv > 0.0 && dinv < 1e300)) { bad = true; break; }  // uniform: everyone reads the same value
-    double u[R], v[C];
+        __syncthreads();
+        const double dinv = ckb[NVP];
+        if (!(dinv > 0.0 && dinv < 1e300)) { bad = true; break; }  // uniform: everyone reads the same value
+        if (R <= C) {
+          double u[R], v[C];
 #pragma unroll
-    for (int i = 0; i < R; i++) u[i] = ck[tr + GR * i];
+          for (int i = 0; i < R; i++) u[i] = wr[GR * i] * dinv;
 #pragma unroll
-    for (int j = 0; j < C; j++) v[j] = ck[tc + GC * j] * dinv;
-#pragma unroll
-    for (int i = 0; i < R; i++)
-#pragma unroll
-      for (int j = 0; j < C; j++) a[i][j] = fma(-u[i], v[j], a[i][j]);
-    if (tc == p % GC && tr == p % GR) {
-#pragma unroll
-      for (int j = 0; j < C; j++)
-        if (j == jp) {
+          for (int j = 0; j < C; j++) v[j] = rc[GC * j];
 #pragma unroll
           for (int i = 0; i < R; i++)
-            if (i == ip) a[i][j] = -dinv;
+#pragma unroll
+            for (int j = 0; j < C; j++) a[i][j] = fma(-u[i], v[j], a[i][j]);
+        } else {
+          double u[R], v[C];
+#pragma unroll
+          for (int i = 0; i < R; i++) u[i] = wr[GR * i];
+#pragma unroll
+          for (int j = 0; j < C; j++) v[j] = rc[GC * j] * dinv;
+#pragma unroll
+          for (int i = 0; i < R; i++)
+#pragma unroll
+            for (int j = 0; j < C; j++) a[i][j] = fma(-u[i], v[j], a[i][j]);
         }
+        if (own_piv) a[I][J] = -dinv;
+      }
     }
   }
   if (bad) {

@@ -136,8 +136,8 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
     const float* rec = (const float*)(recbuf + (size_t)cur * P.stride);
     const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
 
-    if (P.H_out) {  // debug / parity entry: reduced QP only
-      mpc::assemble(cx, rec, gait, k);
+    mpc::assemble(cx, rec, gait, k);
+    if (P.H_out) {  // debug / parity entry: write the reduced QP out and stop
       const int nv = (k.sc->status == MPC_STATUS_OPTIMAL) ? k.sc->nv : 0;
       const int NU = 12 * P.h;
       if (threadIdx.x == 0 && P.nvar_out) P.nvar_out[b] = nv;
@@ -151,8 +151,6 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
       __syncthreads();
       continue;
     }
-
-    mpc::assemble(cx, rec, gait, k);
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
       if constexpr (R > 0) mpc::invert_spd_tiled<NT, GR, GC, R, C>(k, (int)threadIdx.x);
       else mpc::invert_spd(cx, k);
