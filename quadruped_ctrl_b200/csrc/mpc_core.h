@@ -104,7 +104,7 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
   o += 4 * (4 * h + 4 * h + 24 * h + m_cap + 1);
   o = (o + 15) / 16 * 16;
   L.off_union = o;
-  int gi = nv_cap * 2 + L.ck_len + (m_cap + 1) * 4;  // z, cvec, ck, w, r, u, tcol
+  int gi = nv_cap * 2 + L.ck_len + 1 + (m_cap + 1) * 4;  // z, cvec, ck (16-byte aligned), w, r, u, tcol
   int un = kAsmDoubles(h);
   int t_doubles = m_cap * L.ldT;
   int hm_doubles = nv_cap * L.ld;
@@ -162,6 +162,7 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
   k.z = gi;
   k.cvec = k.z + L.nv_cap;
   k.ck = k.cvec + L.nv_cap;
+  if (((uintptr_t)k.ck & 15) != 0) k.ck += 1;  // the register-resident inversion moves it 16 bytes at a time
   k.w = k.ck + L.ck_len;
   k.r = k.w + (L.m_cap + 1);
   k.u = k.r + (L.m_cap + 1);
@@ -566,115 +567,110 @@ MPC_HD void invert_spd(const Cx& cx, const Work& k) {
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------
-// Stage 2, register-tiled (device only): the same symmetric sweep with the matrix held in
-// registers.  NT = GR*GC threads form a GR x GC grid; thread (tr, tc) owns the R x C elements
-// (tr + GR*i, tc + GC*j) of the NVP x NVP matrix (NVP = GR*R = GC*C >= nv, padded with the
-// identity).  Per pivot p the owners of column p publish it once through shared memory
-// (double-buffered: one barrier per pivot) with slot p holding d-1 instead of d = a_pp, and
-// every thread applies ONE uniform rank-1 update  a_ij -= u_i * (u_j / d):
-//     i,j != p :  a_ij - c_i c_j / d                      (the Schur complement)
-//     j == p   :  c_i - c_i (d-1)/d = c_i / d             (the swept column)
-//     i == j == p: d - (d-1)^2/d = 2 - 1/d  -> patched to -1/d by its owner
-// so the inner loop is R*C DFMAs with no per-element predicates; shared memory carries only
-// R + C broadcast loads per thread per pivot instead of the whole matrix.
+// Stage 2, register-resident (device only): the same symmetric sweep with the matrix held in
+// registers as R x C tiles.  NT = GR*GC threads; thread (tr, tc), tr = tid / GC, tc = tid % GC, owns the
+// rows  tr + GR*i (i < R)  and the column pairs  2*GC*j2 + 2*tc + e  (j2 < C/2, e < 2) of the NVP x NVP
+// matrix, NVP = GR*R = GC*C >= nv (identity padding).  GC divides 32, so the GC owners of a row are
+// lanes of one warp.
+//
+// Pivots run in natural order.  Pivot p = GR*i + q lives in row slot i of the threads with tr == q, so
+// the pivot loop is R copies (i unrolled) of a run-time loop over q and every register index is a
+// compile-time constant.  Per pivot the owners publish ROW p (= column p, by symmetry) through shared
+// memory, double-buffered (one barrier per pivot), with slot p carrying d-1 instead of d = a_pp and
+// slot NVP carrying 1/d; every thread then applies ONE uniform rank-1 update
+//     a_rj -= (c_r/d) * c_j          with c = published row, c_p := d-1
+// which yields  a_rj - c_r c_j/d  (r,j != p),  c_j/d  (r == p or j == p)  and  2 - 1/d  at (p,p): every
+// swept diagonal entry ends exactly 2 above its true value -1/d (later updates are additive), so the fix
+// is a single "-2" on the diagonal when the result is stored.  The diagonal entries of a thread's R rows
+// are tracked in R extra registers (one more DFMA each per pivot) so that d and 1/d are available without
+// a run-time register index, and 1/d of the NEXT pivot is started before the bulk update so its latency
+// hides behind the R*C DFMAs.  Shared-memory traffic per thread per pivot: R 8-byte + C/2 16-byte
+// broadcast loads for R*C DFMAs (the kernel is otherwise bound by shared-memory load bandwidth, not fp64).
 // ---------------------------------------------------------------------------
-template <int NT, int GR, int GC, int R, int C>
-__device__ __forceinline__ void invert_spd_tiled(const Work& k, int tid) {
+template <int GR, int R, int GC, int C>
+__device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
   constexpr int NVP = GR * R;
-  constexpr int RATIO = GR / GC;
-  static_assert(GR * GC == NT && GC * C == NVP, "tile grid must cover the padded matrix");
-  static_assert(GR % GC == 0 && GC % 2 == 0, "pivot slots must be compile-time: GR a multiple of GC, GC even");
+  static_assert(GC * C == NVP && C % 2 == 0 && 32 % GC == 0, "tile grid must cover the padded matrix");
   Scalars* sc = k.sc;
   const int nv = sc->nv, ld = k.ld;
   double* Hm = k.Hm;
   const int tr = tid / GC, tc = tid % GC;
-  double a[R][C];
+  double a[R][C], dg[R];
 #pragma unroll
-  for (int i = 0; i < R; i++)
+  for (int i = 0; i < R; i++) {
+    const int r = tr + GR * i;
 #pragma unroll
     for (int j = 0; j < C; j++) {
-      const int r = tr + GR * i, c = tc + GC * j;
+      const int c = 2 * GC * (j / 2) + 2 * tc + (j & 1);
       a[i][j] = (r < nv && c < nv) ? Hm[r * ld + c] : (r == c ? 1.0 : 0.0);
     }
-  // pivot order: p = q + GC*J for J = 0..C-1 (unrolled: J and the row slot I = J / RATIO are register
-  // indices known at compile time), q = 0..GC-1; any order gives the same inverse.  GC is even, so the
-  // parity of p (which of the two broadcast buffers) is the parity of q.
-  double* const ck0 = k.ck;
-  double* const ck1 = k.ck + (NVP + 2);
-  double* const wr0 = ck0 + tr;  // this thread's rows, written when it owns the pivot column / read as u
-  double* const wr1 = ck1 + tr;
-  const double* const rc0 = ck0 + tc;  // this thread's columns, read as v
-  const double* const rc1 = ck1 + tc;
+    dg[i] = (r < nv) ? Hm[r * ld + r] : 1.0;
+  }
+  double* const buf0 = k.ck;
+  double* const buf1 = k.ck + (NVP + 2);
+  double dinv_mine = (tr == 0) ? __drcp_rn(dg[0]) : 0.0;  // 1/d of the pivot this thread's row group publishes next
   bool bad = false;
 #pragma unroll
-  for (int J = 0; J < C; J++) {
-    constexpr int dummy = 0;
-    (void)dummy;
-    const int I = J / RATIO;              // compile-time after unrolling
-    const int trp0 = GC * (J % RATIO);    // row-grid coordinate of pivot q is trp0 + q
-    if (GC * J >= nv || bad) break;       // uniform
+  for (int i = 0; i < R; i++) {
+    if (GR * i >= nv) break;  // uniform
 #pragma unroll 1
-    for (int q = 0; q < GC; q += 2) {
+    for (int q = 0; q < GR; q++) {
+      const int p = GR * i + q;
+      if (p >= nv) break;  // uniform
+      double* const cur = (q & 1) ? buf1 : buf0;  // GR is even: parity of p == parity of q
+      if (tr == q) {  // publish row p: compile-time registers a[i][*]
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int qq = q + e;
-        const int p = qq + GC * J;
-        if (p >= nv || bad) break;  // uniform
-        double* const wr = e ? wr1 : wr0;
-        const double* const rc = e ? rc1 : rc0;
-        double* const ckb = e ? ck1 : ck0;
-        const bool own_col = (tc == qq);
-        const bool own_piv = own_col && (tr == trp0 + qq);
-        if (own_col) {
-#pragma unroll
-          for (int i = 0; i < R; i++) wr[GR * i] = a[i][J];
-          if (own_piv) {
-            const double d = a[I][J];
-            ckb[p] = d - 1.0;
-            ckb[NVP] = __drcp_rn(d);
-          }
+        for (int j2 = 0; j2 < C / 2; j2++)
+          *reinterpret_cast<double2*>(cur + 2 * GC * j2 + 2 * tc) = make_double2(a[i][2 * j2], a[i][2 * j2 + 1]);
+        if (tc == 0) {  // same warp as the lane that just stored d into slot p: this store lands after it
+          cur[p] = dg[i] - 1.0;
+          cur[NVP] = dinv_mine;
         }
-        __syncthreads();
-        const double dinv = ckb[NVP];
-        if (!(dinv > 0.0 && dinv < 1e300)) { bad = true; break; }  // uniform: everyone reads the same value
-        if (R <= C) {
-          double u[R], v[C];
+      }
+      __syncthreads();
+      const double dinv = cur[NVP];
+      bad = bad || !(dinv > 0.0 && dinv < 1e300);
+      double u[R];
 #pragma unroll
-          for (int i = 0; i < R; i++) u[i] = wr[GR * i] * dinv;
+      for (int ii = 0; ii < R; ii++) {
+        const double c = cur[tr + GR * ii];
+        u[ii] = -c * dinv;
+        dg[ii] = fma(u[ii], c, dg[ii]);
+      }
+      // reciprocal of the next pivot, started before the bulk update (its row group: tr == (q+1) % GR)
+      if (q + 1 < GR) {
+        if (tr == q + 1) dinv_mine = __drcp_rn(dg[i]);
+      } else if (i + 1 < R) {
+        if (tr == 0) dinv_mine = __drcp_rn(dg[(i + 1 < R) ? i + 1 : i]);
+      }
 #pragma unroll
-          for (int j = 0; j < C; j++) v[j] = rc[GC * j];
+      for (int j2 = 0; j2 < C / 2; j2++) {
+        const double2 v = *reinterpret_cast<const double2*>(cur + 2 * GC * j2 + 2 * tc);
 #pragma unroll
-          for (int i = 0; i < R; i++)
-#pragma unroll
-            for (int j = 0; j < C; j++) a[i][j] = fma(-u[i], v[j], a[i][j]);
-        } else {
-          double u[R], v[C];
-#pragma unroll
-          for (int i = 0; i < R; i++) u[i] = wr[GR * i];
-#pragma unroll
-          for (int j = 0; j < C; j++) v[j] = rc[GC * j] * dinv;
-#pragma unroll
-          for (int i = 0; i < R; i++)
-#pragma unroll
-            for (int j = 0; j < C; j++) a[i][j] = fma(-u[i], v[j], a[i][j]);
+        for (int ii = 0; ii < R; ii++) {
+          a[ii][2 * j2] = fma(u[ii], v.x, a[ii][2 * j2]);
+          a[ii][2 * j2 + 1] = fma(u[ii], v.y, a[ii][2 * j2 + 1]);
         }
-        if (own_piv) a[I][J] = -dinv;
       }
     }
   }
-  if (bad) {
-    __syncthreads();
+  if (__syncthreads_or(bad)) {
     if (tid == 0) sc->status = MPC_STATUS_NOT_PD;
     __syncthreads();
     return;
   }
+  // store H^{-1} = -(swept matrix), taking the 2 off every (swept) diagonal entry
 #pragma unroll
-  for (int i = 0; i < R; i++)
+  for (int i = 0; i < R; i++) {
+    const int r = tr + GR * i;
+    if (r < nv) {
 #pragma unroll
-    for (int j = 0; j < C; j++) {
-      const int r = tr + GR * i, c = tc + GC * j;
-      if (r < nv && c < nv) Hm[r * ld + c] = -a[i][j];
+      for (int j = 0; j < C; j++) {
+        const int c = 2 * GC * (j / 2) + 2 * tc + (j & 1);
+        if (c < nv) Hm[r * ld + c] = (c == r) ? (2.0 - a[i][j]) : -a[i][j];
+      }
     }
+  }
   __syncthreads();
 }
 #endif

@@ -46,6 +46,7 @@ struct SolveParams {
   int max_iter;
   float* peers[kMaxPeers];
   int n_peers, rank_offset;
+  long long* phase_clk;  // optional [batch][8] SM-clock stamps at phase boundaries (profiling aid)
   int32_t* nvar_out;  // assemble-only mode when H_out != nullptr
   double* H_out;
   double* g_out;
@@ -98,9 +99,10 @@ __global__ void mpc_classify_kernel(const char* records, unsigned long long stri
   lists[c * max_batch + slot] = b;
 }
 
-// NT threads per CTA; GR x GC thread grid with R x C register tiles for the inversion (R == 0: the generic
-// shared/global-memory sweep, used by the catch-all class whose matrix does not fit in registers).
-template <int NT, int GR, int GC, int R, int C, int MINB>
+// NT threads per CTA.  R > 0: register-resident inversion with R x C tiles on a GR x GC thread grid (NT == GR*GC,
+// padded size GR*R == GC*C).  R == 0: the generic shared/global-memory sweep, used by the catch-all class whose
+// matrix does not fit in the register file of one SM.
+template <int NT, int GR, int R, int GC, int C, int MINB>
 __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) char smem[];
   const int count = P.count ? *P.count : P.batch;
@@ -136,7 +138,10 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
     const float* rec = (const float*)(recbuf + (size_t)cur * P.stride);
     const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
 
+    long long* clk = P.phase_clk ? P.phase_clk + (size_t)8 * b : nullptr;
+    if (clk && threadIdx.x == 0) clk[0] = clock64();
     mpc::assemble(cx, rec, gait, k);
+    if (clk && threadIdx.x == 0) clk[1] = clock64();
     if (P.H_out) {  // debug / parity entry: write the reduced QP out and stop
       const int nv = (k.sc->status == MPC_STATUS_OPTIMAL) ? k.sc->nv : 0;
       const int NU = 12 * P.h;
@@ -152,10 +157,16 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
       continue;
     }
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
-      if constexpr (R > 0) mpc::invert_spd_tiled<NT, GR, GC, R, C>(k, (int)threadIdx.x);
-      else mpc::invert_spd(cx, k);
+      if constexpr (R > 0) {
+        static_assert(R == 0 || NT == GR * GC, "thread grid");
+        mpc::invert_spd_tiles<GR, R, GC, C>(k, (int)threadIdx.x);
+      } else {
+        mpc::invert_spd(cx, k);
+      }
     }
+    if (clk && threadIdx.x == 0) clk[2] = clock64();
     if (k.sc->status == MPC_STATUS_OPTIMAL) mpc::active_set(cx, rec, gait, k, P.max_iter);
+    if (clk && threadIdx.x == 0) clk[3] = clock64();
     const int code = k.sc->status;
     if (code == mpc::STATUS_RETRY_BIG && P.retry_list) {
       if (threadIdx.x == 0) {
@@ -176,6 +187,7 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
       }
     }
     __syncthreads();
+    if (clk && threadIdx.x == 0) { clk[4] = clock64(); clk[5] = blockIdx.x; clk[6] = it; }
   }
 }
 
@@ -216,6 +228,8 @@ struct mpc_batch {
   float* peers[kMaxPeers] = {nullptr};
   int n_peers = 0, rank_offset = 0;
   float* gather_buf = nullptr;
+  long long* phase_clk = nullptr;
+  int ctas_per_sm_limit = 0;
   void* peer_open[kMaxPeers] = {nullptr};
   std::string err;
 };
@@ -232,17 +246,16 @@ namespace {
   } while (0)
 
 // kernel variants: padded size -> (threads, thread grid, register tile)
-enum { V_64 = 0, V_96, V_128, V_160, V_GENERIC, V_COUNT };
-#define MPC_VARIANT_CALL(v, EXPR)                                        \
-  switch (v) {                                                           \
-    case V_64: { auto kern = mpc_solve_kernel<128, 16, 8, 4, 8, 4>; EXPR; } break;      \
-    case V_96: { auto kern = mpc_solve_kernel<256, 16, 16, 6, 6, 2>; EXPR; } break;     \
-    case V_128: { auto kern = mpc_solve_kernel<256, 16, 16, 8, 8, 1>; EXPR; } break;    \
-    case V_160: { auto kern = mpc_solve_kernel<256, 16, 16, 10, 10, 1>; EXPR; } break;   \
-    default: { auto kern = mpc_solve_kernel<256, 0, 0, 0, 0, 1>; EXPR; } break;         \
+enum { V_64 = 0, V_96, V_128, V_GENERIC, V_COUNT };
+#define MPC_VARIANT_CALL(v, EXPR)                                                    \
+  switch (v) {                                                                       \
+    case V_64: { auto kern = mpc_solve_kernel<128, 16, 4, 8, 8, 4>; EXPR; } break;    \
+    case V_96: { auto kern = mpc_solve_kernel<256, 16, 6, 16, 6, 2>; EXPR; } break;   \
+    case V_128: { auto kern = mpc_solve_kernel<256, 16, 8, 16, 8, 1>; EXPR; } break;  \
+    default: { auto kern = mpc_solve_kernel<256, 0, 0, 0, 0, 1>; EXPR; } break;       \
   }
-const int kVariantThreads[V_COUNT] = {128, 256, 256, 256, 256};
-const int kVariantPad[V_COUNT] = {64, 96, 128, 160, 0};
+const int kVariantThreads[V_COUNT] = {128, 256, 256, 256};
+const int kVariantPad[V_COUNT] = {64, 96, 128, 0};
 
 int configure_kernel(mpc_batch* eng, ClassCfg& c) {
   // the attribute is per kernel instantiation: raise it to the device limit
@@ -266,7 +279,7 @@ int free_m_cap(int h, int nv_cap, int npad) {
   int m = 8;
   while (m < nv_cap) {
     const int mm = m + 1;
-    const int gi = mm * (mm | 1) + 2 * nv_cap + 2 * (npad + 2) + 4 * (mm + 1);
+    const int gi = mm * (mm | 1) + 2 * nv_cap + 2 * (npad + 2) + 1 + 4 * (mm + 1);
     if (gi > mpc::kAsmDoubles(h)) break;
     m = mm;
   }
@@ -276,15 +289,15 @@ int free_m_cap(int h, int nv_cap, int npad) {
 int build_classes(mpc_batch* eng) {
   const int h = eng->h, nv_max = 12 * h;
   std::vector<int> caps;
-  for (int c : {60, 96, 120, 156})
+  for (int c : {60, 96, 128})
     if (c < nv_max) caps.push_back(c);
-  caps.push_back(std::min(nv_max, 156));
+  if (nv_max <= 128) caps.push_back(nv_max);
   int max_smem = 0;
   CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, eng->device));
   for (int cap : caps) {
     ClassCfg c;
     c.nv_cap = cap;
-    c.variant = cap <= 64 ? V_64 : cap <= 96 ? V_96 : cap <= 128 ? V_128 : V_160;
+    c.variant = cap <= 64 ? V_64 : cap <= 96 ? V_96 : V_128;
     c.threads = kVariantThreads[c.variant];
     c.m_cap = free_m_cap(h, cap, kVariantPad[c.variant]);
     c.in_fast = 1;
@@ -326,6 +339,7 @@ void fill_params(const mpc_batch* eng, SolveParams& P, const void* records, int 
   P.solution = solution;
   P.status = status;
   P.max_iter = eng->max_iter;
+  P.phase_clk = eng->phase_clk;
   P.n_peers = eng->n_peers;
   P.rank_offset = eng->rank_offset;
   for (int q = 0; q < kMaxPeers; q++) P.peers[q] = eng->peers[q];
@@ -365,7 +379,9 @@ int solve_on_stream(mpc_batch* eng, const void* records, int batch, float* force
     P.g_out = g_out;
     const size_t slot = (size_t)(eng->ring_pos % kRing) * kMaxClasses + ci;
     if (eng->timed) CK(cudaEventRecord(eng->ring0[slot], st));
-    int rc = launch_solve(eng, c, P, std::min(c.grid, batch), st);
+    int grid = std::min(c.grid, batch);
+    if (eng->ctas_per_sm_limit > 0) grid = std::min(grid, eng->ctas_per_sm_limit * eng->sms);
+    int rc = launch_solve(eng, c, P, grid, st);
     if (rc) return rc;
     if (eng->timed) CK(cudaEventRecord(eng->ring1[slot], st));
   }
@@ -549,6 +565,18 @@ int mpc_batch_set_gather_peers(mpc_batch_t* eng, float* const* peers, int n_peer
 int mpc_batch_set_max_iterations(mpc_batch_t* eng, int max_iter) {
   if (!eng || max_iter < 1) return MPC_E_ARG;
   eng->max_iter = max_iter;
+  return MPC_OK;
+}
+
+int mpc_batch_set_phase_clock_buffer(mpc_batch_t* eng, long long* dev_buf) {
+  if (!eng) return MPC_E_ARG;
+  eng->phase_clk = dev_buf;
+  return MPC_OK;
+}
+
+int mpc_batch_set_ctas_per_sm_limit(mpc_batch_t* eng, int limit) {
+  if (!eng || limit < 0) return MPC_E_ARG;
+  eng->ctas_per_sm_limit = limit;
   return MPC_OK;
 }
 

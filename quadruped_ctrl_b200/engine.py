@@ -23,7 +23,7 @@ STATUS_OPTIMAL, STATUS_MAX_ITER, STATUS_BAD_INPUT, STATUS_NOT_PD, STATUS_NO_STAN
 # every symbol include/mpc_batch.h and include/convexMPC_interface.h declare
 BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_create", "mpc_batch_destroy",
                  "mpc_batch_solve_device", "mpc_batch_solve_host", "mpc_batch_assemble_device",
-                 "mpc_batch_set_gather_peers", "mpc_batch_set_max_iterations", "mpc_batch_set_timing",
+                 "mpc_batch_set_gather_peers", "mpc_batch_set_max_iterations", "mpc_batch_set_timing", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
                  "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
                  "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_class_kernel_ms", "mpc_batch_timing_mark",
                  "mpc_batch_timing_collect", "mpc_batch_host_buffers",
@@ -71,6 +71,8 @@ def lib():
     L.mpc_batch_set_gather_peers.argtypes = [vp, ctypes.POINTER(vp), i32, i32]
     L.mpc_batch_set_max_iterations.argtypes = [vp, i32]
     L.mpc_batch_set_timing.argtypes = [vp, i32]
+    L.mpc_batch_set_phase_clock_buffer.argtypes = [vp, vp]
+    L.mpc_batch_set_ctas_per_sm_limit.argtypes = [vp, i32]
     L.mpc_batch_num_classes.argtypes = [vp]
     L.mpc_batch_class_info.argtypes = [vp, i32, ctypes.POINTER(i32)]
     L.mpc_batch_kernel_launches.argtypes = [vp]
@@ -149,6 +151,15 @@ class MpcBatch:
 
     def set_timing(self, on):
         self._check(self._L.mpc_batch_set_timing(self._h, int(bool(on))), "set_timing")
+
+    def set_phase_clock_buffer(self, tensor):
+        """tensor: cuda int64 [max_batch, 8] (or None): per-problem clock64() stamps at phase boundaries."""
+        self._phase_buf = tensor
+        self._check(self._L.mpc_batch_set_phase_clock_buffer(self._h, tensor.data_ptr() if tensor is not None else None),
+                    "set_phase_clock_buffer")
+
+    def set_ctas_per_sm_limit(self, n):
+        self._check(self._L.mpc_batch_set_ctas_per_sm_limit(self._h, int(n)), "set_ctas_per_sm_limit")
 
     def last_solve_kernel_ms(self):
         return float(self._L.mpc_batch_last_solve_kernel_ms(self._h))

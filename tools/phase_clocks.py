@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Per-phase SM-clock breakdown of the solve kernel (profiling aid; run on the GPU box)."""
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from quadruped_ctrl_b200 import engine as E, workloads as W  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 else "config2"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+h = W.HORIZONS[name]
+rec = torch.from_numpy(W.CONFIGS[name](B)).cuda()
+eng = E.MpcBatch(h, B)
+if len(sys.argv) > 3:
+    eng.set_ctas_per_sm_limit(int(sys.argv[3]))
+for _ in range(3):
+    eng.solve_device(rec)
+buf = torch.zeros((B, 8), dtype=torch.int64, device="cuda")
+eng.set_phase_clock_buffer(buf)
+eng.solve_device(rec)
+torch.cuda.synchronize()
+c = buf.cpu().numpy()
+d = np.diff(c[:, :5], axis=1)
+names = ["assemble", "invert", "active_set", "scatter+sync"]
+print("%s B=%d: cycles per problem per CTA (median / mean / p95)" % (name, B))
+for i, n in enumerate(names):
+    print("  %-14s %8.0f %8.0f %8.0f" % (n, np.median(d[:, i]), d[:, i].mean(), np.percentile(d[:, i], 95)))
+tot = c[:, 4] - c[:, 0]
+print("  %-14s %8.0f %8.0f %8.0f" % ("total", np.median(tot), tot.mean(), np.percentile(tot, 95)))
+# gap between consecutive problems of the same CTA (record wait + loop overhead)
+order = np.lexsort((c[:, 6], c[:, 5]))
+cs = c[order]
+same = cs[1:, 5] == cs[:-1, 5]
+gap = (cs[1:, 0] - cs[:-1, 4])[same]
+print("  inter-problem gap median %.0f mean %.0f" % (np.median(gap), gap.mean()))
+first = cs[np.r_[True, ~same]]
+print("  kernel span (max end - min start) %.0f cycles; first-problem start spread %.0f" %
+      (c[:, 4].max() - c[:, 0].min(), first[:, 0].max() - first[:, 0].min()))
