@@ -134,9 +134,9 @@ int mpc_batch_set_max_iterations(mpc_batch_t* eng, int max_iter);
 /* Turns CUDA-event timing of the solve kernels on or off (off by default). */
 int mpc_batch_set_timing(mpc_batch_t* eng, int enabled);
 
-/* Profiling aid: when dev_buf (device memory, [max_batch][8] int64) is non-NULL the solve
+/* Profiling aid: when dev_buf (device memory, [max_batch][24] int64) is non-NULL the solve
  * kernel stamps clock64() per problem at: record landed, assembled, inverted, active set
- * done, outputs written; slots 5,6 = CTA index and its pass number.  NULL turns it off. */
+ * done, outputs written; slots 5,6 = CTA index and its pass number, 8..12 = stamps inside the assembly / active-set stages.  NULL turns it off. */
 int mpc_batch_set_phase_clock_buffer(mpc_batch_t* eng, long long* dev_buf);
 
 /* Tuning aid: caps the persistent grid of every class at limit * (number of SMs) CTAs;

@@ -76,7 +76,7 @@ struct Scalars {
   double sp, t1, t2, t, up, vnp, znp, dreg;
 };
 
-constexpr int kAsmDoubles(int h) { return 3 * 156 + 9 * 144 + 39 + 12 * h; }
+constexpr int kAsmDoubles(int h) { return 3 * 156 + 9 * 144 + 39 + 12 * h + 5 * h; }
 constexpr int kRedDoubles = 40;
 
 inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -99,12 +99,12 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
   o += 8 * nv_cap;
   L.off_x = o;
   o += 8 * nv_cap;
-  // ints: stance[4h] (k = step*4+leg of every stance pair), posk[4h], act[6*4h], W[m_cap+1]
+  // ints: stance[4h] (k = step*4+leg of every stance pair), posk[4h], amask[4h], W / Wia / Wiz [m_cap+1]
   L.off_ints = o;
-  o += 4 * (4 * h + 4 * h + 24 * h + m_cap + 1);
+  o += 4 * (3 * 4 * h + 3 * (m_cap + 1));
   o = (o + 15) / 16 * 16;
   L.off_union = o;
-  int gi = nv_cap * 2 + L.ck_len + 1 + (m_cap + 1) * 4;  // z, cvec, ck (16-byte aligned), w, r, u, tcol
+  int gi = L.ck_len + 1 + 4 * h + (m_cap + 1) * 6;  // ck (16-byte aligned), ub, Wca, Wcz, w, r, u, tcol
   int un = kAsmDoubles(h);
   int t_doubles = m_cap * L.ldT;
   int hm_doubles = nv_cap * L.ld;
@@ -126,14 +126,21 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
 struct Work {
   Scalars* sc;
   double *g, *x, *Hm, *T;
-  int *stance, *posk, *act, *W;
+  int *stance, *posk, *amask, *W, *Wia, *Wiz;
   // assembly view of the union
-  double *C, *M, *xs, *qe;
+  double *C, *M, *xs, *qe, *psum;
   // active-set view of the union
-  double *z, *cvec, *ck, *w, *r, *u, *tcol;
+  double *ck, *ub, *Wca, *Wcz, *w, *r, *u, *tcol;
   double* red;
   int ld, ldT, nv_cap, m_cap, h;
+  long long* clk;  // optional per-problem clock stamps (profiling aid), slots 8..23
 };
+
+#if defined(__CUDA_ARCH__)
+#define MPC_STAMP(k, cx, slot) do { if ((k).clk && (cx).tid == 0) (k).clk[slot] = clock64(); } while (0)
+#else
+#define MPC_STAMP(k, cx, slot) do { } while (0)
+#endif
 
 MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
   Work k;
@@ -143,13 +150,16 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
   int* ip = (int*)(fast + L.off_ints);
   k.stance = ip;
   k.posk = ip + 4 * L.h;
-  k.act = ip + 8 * L.h;
-  k.W = ip + 32 * L.h;
+  k.amask = ip + 8 * L.h;
+  k.W = ip + 12 * L.h;
+  k.Wia = k.W + (L.m_cap + 1);
+  k.Wiz = k.Wia + (L.m_cap + 1);
   double* un = (double*)(fast + L.off_union);
   k.C = un;
   k.M = un + 3 * 156;
   k.xs = k.M + 9 * 144;
   k.qe = k.xs + 39;
+  k.psum = k.qe + 12 * L.h;
   double* gi = un;
   if (L.big_in_fast) {
     k.T = gi;
@@ -159,11 +169,12 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
     k.Hm = (double*)(slab + L.slab_Hm);
     k.T = (double*)(slab + L.slab_T);
   }
-  k.z = gi;
-  k.cvec = k.z + L.nv_cap;
-  k.ck = k.cvec + L.nv_cap;
+  k.ck = gi;
   if (((uintptr_t)k.ck & 15) != 0) k.ck += 1;  // the register-resident inversion moves it 16 bytes at a time
-  k.w = k.ck + L.ck_len;
+  k.ub = k.ck + L.ck_len;
+  k.Wca = k.ub + 4 * L.h;
+  k.Wcz = k.Wca + (L.m_cap + 1);
+  k.w = k.Wcz + (L.m_cap + 1);
   k.r = k.w + (L.m_cap + 1);
   k.u = k.r + (L.m_cap + 1);
   k.tcol = k.u + (L.m_cap + 1);
@@ -173,6 +184,7 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
   k.nv_cap = L.nv_cap;
   k.m_cap = L.m_cap;
   k.h = L.h;
+  k.clk = nullptr;
   return k;
 }
 
@@ -181,28 +193,57 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
 // ---------------------------------------------------------------------------
 #if defined(__CUDACC__)
 struct Cta {
+  static constexpr bool kOneWarp = false;
   int tid, nt;
   __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
+// One warp of the CTA working alone (the latency-bound active-set stage): barriers are __syncwarp and
+// reductions are shuffles only.
+struct Warp {
+  static constexpr bool kOneWarp = true;
+  int tid, nt;  // lane, 32
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
 #endif
 struct OneThread {
+  static constexpr bool kOneWarp = false;
   int tid, nt;
   inline void sync() const {}
 };
 
-#define MPC_FOR(i, n) for (int i = cx.tid; i < (n); i += cx.nt)
+// Strided loops are deliberately NOT unrolled: the kernel is instruction-cache bound (32 KB L1.5 I-cache),
+// and these loops run a handful of iterations per thread.
+#define MPC_FOR(i, n) _Pragma("unroll 1") for (int i = cx.tid; i < (n); i += cx.nt)
 #define MPC_ONE if (cx.tid == 0)
 
 // Block-wide argmin of (val, idx) pairs; every thread passes its local best and
 // gets the global best back.  Ties resolve to the smaller idx (deterministic).
-template <class Cx>
-MPC_HD void block_argmin(const Cx& cx, double* red, double& val, int& idx) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
+// out of line on purpose (called from many places; see the I-cache note above)
+__device__ __noinline__ void warp_argmin(double& val, int& idx) {
+#pragma unroll 1
   for (int o = 16; o > 0; o >>= 1) {
     double v2 = __shfl_xor_sync(0xffffffffu, val, o);
     int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
     if (v2 < val || (v2 == val && i2 < idx)) { val = v2; idx = i2; }
   }
+}
+__device__ __noinline__ double warp_sum(double val) {
+#pragma unroll 1
+  for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+  return val;
+}
+__device__ __noinline__ double atan2_shared(double y, double x) { return atan2(y, x); }
+#define MPC_ATAN2 atan2_shared
+#else
+#define MPC_ATAN2 atan2
+#endif
+
+template <class Cx>
+MPC_HD void block_argmin(const Cx& cx, double* red, double& val, int& idx) {
+#if defined(__CUDA_ARCH__)
+  warp_argmin(val, idx);
+  if (Cx::kOneWarp) return;
   const int nw = (cx.nt + 31) >> 5;
   int* redi = (int*)(red + 16);
   cx.sync();  // scratch may still be read from a previous reduction
@@ -223,7 +264,8 @@ MPC_HD void block_argmin(const Cx& cx, double* red, double& val, int& idx) {
 template <class Cx>
 MPC_HD double block_sum(const Cx& cx, double* red, double val) {
 #if defined(__CUDA_ARCH__)
-  for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+  val = warp_sum(val);
+  if (Cx::kOneWarp) return val;
   const int nw = (cx.nt + 31) >> 5;
   cx.sync();
   if ((cx.tid & 31) == 0) red[cx.tid >> 5] = val;
@@ -310,7 +352,7 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
   double* Ax0 = x0 + 13;
   double* A2x0 = Ax0 + 13;
   double* mom = k.Hm;       // [3][h][12] moments of the tracking error; Hm is free until the H blocks are written
-  int* flag = k.act;        // 0/1 stance flags while the stance list is built (act[] proper is set up later)
+  int* flag = k.amask;      // 0/1 stance flags while the stance list is built (amask[] proper is set up later)
   const float fmax = rec[MPC_REC_FMAX];
 
   // ---- P0: reset, stance flags (SolverMPC.cpp:441-469: U_b(5k+4) = gait[k]*f_max "near zero" => eliminated) ----
@@ -336,6 +378,7 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
   }
   MPC_FOR(kk, 4 * h) {
     int pos = 0;
+#pragma unroll 4
     for (int q = 0; q < kk; q++) pos += flag[q];
     if (flag[kk]) { k.stance[pos] = kk; k.posk[kk] = pos; }
     else k.posk[kk] = -1;
@@ -350,15 +393,16 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
       scr[0] = cos(yaw);
       scr[1] = sin(yaw);
     }
-    if (cx.tid == 1 * lanes) x0[2] = atan2(2. * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
+    if (cx.tid == 1 * lanes) x0[2] = MPC_ATAN2(2. * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
     if (cx.tid == 2 * lanes) {
       double as = -2. * (qx * qz - qw * qy);
       if (!(as < .99999)) as = .99999;
       x0[1] = asin(as);
     }
-    if (cx.tid == 3 * lanes) x0[0] = atan2(2. * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
+    if (cx.tid == 3 * lanes) x0[0] = MPC_ATAN2(2. * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
   }
   cx.sync();
+  MPC_STAMP(k, cx, 8);
   // ---- P2: x_0 tail, B_c per leg (ct_ss_mats, SolverMPC.cpp:235-254; cross_mat :226-233) ----
   MPC_ONE {
     if (sc->status == MPC_STATUS_OPTIMAL && sc->ns == 0) sc->status = MPC_STATUS_NO_STANCE;
@@ -385,16 +429,17 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
     const double det = Iw[0][0] * (Iw[1][1] * Iw[2][2] - Iw[1][2] * Iw[2][1]) -
                        Iw[0][1] * (Iw[1][0] * Iw[2][2] - Iw[1][2] * Iw[2][0]) +
                        Iw[0][2] * (Iw[1][0] * Iw[2][1] - Iw[1][1] * Iw[2][0]);
+    const double rdet = 1.0 / det;  // one division; the adjugate entries are scaled by it
     double Ii[3][3];
-    Ii[0][0] = (Iw[1][1] * Iw[2][2] - Iw[1][2] * Iw[2][1]) / det;
-    Ii[0][1] = (Iw[0][2] * Iw[2][1] - Iw[0][1] * Iw[2][2]) / det;
-    Ii[0][2] = (Iw[0][1] * Iw[1][2] - Iw[0][2] * Iw[1][1]) / det;
-    Ii[1][0] = (Iw[1][2] * Iw[2][0] - Iw[1][0] * Iw[2][2]) / det;
-    Ii[1][1] = (Iw[0][0] * Iw[2][2] - Iw[0][2] * Iw[2][0]) / det;
-    Ii[1][2] = (Iw[0][2] * Iw[1][0] - Iw[0][0] * Iw[1][2]) / det;
-    Ii[2][0] = (Iw[1][0] * Iw[2][1] - Iw[1][1] * Iw[2][0]) / det;
-    Ii[2][1] = (Iw[0][1] * Iw[2][0] - Iw[0][0] * Iw[2][1]) / det;
-    Ii[2][2] = (Iw[0][0] * Iw[1][1] - Iw[0][1] * Iw[1][0]) / det;
+    Ii[0][0] = (Iw[1][1] * Iw[2][2] - Iw[1][2] * Iw[2][1]) * rdet;
+    Ii[0][1] = (Iw[0][2] * Iw[2][1] - Iw[0][1] * Iw[2][2]) * rdet;
+    Ii[0][2] = (Iw[0][1] * Iw[1][2] - Iw[0][2] * Iw[1][1]) * rdet;
+    Ii[1][0] = (Iw[1][2] * Iw[2][0] - Iw[1][0] * Iw[2][2]) * rdet;
+    Ii[1][1] = (Iw[0][0] * Iw[2][2] - Iw[0][2] * Iw[2][0]) * rdet;
+    Ii[1][2] = (Iw[0][2] * Iw[1][0] - Iw[0][0] * Iw[1][2]) * rdet;
+    Ii[2][0] = (Iw[1][0] * Iw[2][1] - Iw[1][1] * Iw[2][0]) * rdet;
+    Ii[2][1] = (Iw[0][1] * Iw[2][0] - Iw[0][0] * Iw[2][1]) * rdet;
+    Ii[2][2] = (Iw[0][0] * Iw[1][1] - Iw[0][1] * Iw[1][0]) * rdet;
     const double minv = 1.0 / (double)rec[MPC_REC_MASS];
     const double rx = rec[MPC_REC_R + b], ry = rec[MPC_REC_R + 4 + b], rz = rec[MPC_REC_R + 8 + b];
     const double cm[3][3] = {{0, -rz, ry}, {rz, 0, -rx}, {-ry, rx, 0}};
@@ -408,6 +453,7 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
     }
   }
   cx.sync();
+  MPC_STAMP(k, cx, 9);
   if (sc->status != MPC_STATUS_OPTIMAL) return;
   const double dt = (double)rec[MPC_REC_DT];
   // ---- P3: A B, A^2 B, A x0, A^2 x0 ----
@@ -438,17 +484,30 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
     k.qe[e] = (double)rec[MPC_REC_WEIGHTS + i] * (xr - (double)rec[MPC_REC_TRAJ + e]);
   }
   cx.sync();
+  MPC_STAMP(k, cx, 10);
   // ---- P8: moments mom[a][j][row] = sum_{r>=j} (r-j)^a q_e[r][row] ----
   const int na = (xd != 0.0) ? 3 : 2;  // without drag C2 == 0 and every k^2 term drops out
   MPC_FOR(e, na * 12 * h) {
     const int a = e / (12 * h), jr = e - a * 12 * h, j = jr / 12, row = jr - 12 * j;
     double acc = 0;
+#pragma unroll 2
     for (int r = j; r < h; r++) {
       const double kd = (double)(r - j);
       const double w = a == 0 ? 1.0 : (a == 1 ? kd : kd * kd);
       acc += w * k.qe[12 * r + row];
     }
     mom[e] = acc;
+  }
+  // power sums P_e(n) = sum_{q=0..n} q^e, e = 0..4, n = 0..h-1: exact integers (< 2^53 for h <= 36)
+  MPC_FOR(n, h) {
+    long long p1 = 0, p2 = 0, p3 = 0, p4 = 0;
+#pragma unroll 1
+    for (long long q = 1; q <= n; q++) { p1 += q; p2 += q * q; p3 += q * q * q; p4 += q * q * q * q; }
+    k.psum[5 * n + 0] = (double)(n + 1);
+    k.psum[5 * n + 1] = (double)p1;
+    k.psum[5 * n + 2] = (double)p2;
+    k.psum[5 * n + 3] = (double)p3;
+    k.psum[5 * n + 4] = (double)p4;
   }
   cx.sync();
   // ---- P9: reduced gradient g_v = 2 sum_a C_a[:,c]' mom[a][j] (SolverMPC.cpp:399), and the nine tables
@@ -459,29 +518,41 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
   MPC_FOR(v, nv) {
     const int sidx = v / 3, ax = v - 3 * sidx;
     const int kk = k.stance[sidx], j = kk >> 2, c = (kk & 3) * 3 + ax;
-    double acc = 0;
+    double acc0 = 0, acc1 = 0;  // two chains: the sum is latency-bound
     for (int a = 0; a < na; a++) {
       const double* Ca = C0 + 156 * a;
       const double* ma = mom + (a * h + j) * 12;
-      for (int row = 0; row < 12; row++)
-        if ((rowmask[a] >> row) & 1u) acc += Ca[row * 12 + c] * ma[row];
+      for (int row = 0; row < 12; row += 2) {
+        if ((rowmask[a] >> row) & 1u) acc0 += Ca[row * 12 + c] * ma[row];
+        if ((rowmask[a] >> (row + 1)) & 1u) acc1 += Ca[(row + 1) * 12 + c] * ma[row + 1];
+      }
     }
-    k.g[v] = 2.0 * acc;
+    k.g[v] = 2.0 * (acc0 + acc1);
   }
-  MPC_FOR(e, 9 * 144) {
-    const int ab = e / 144, ij = e - 144 * ab;
-    const int a = ab / 3, b = ab - 3 * a, i = ij / 12, j = ij - 12 * i;
-    double s = 0;
+  // one thread per (table, row): 12 independent accumulators, each weighted C_a entry loaded once
+  MPC_FOR(e, 9 * 12) {
+    const int ab = e / 12, i = e - 12 * ab;
+    const int a = ab / 3, b = ab - 3 * a;
     if (a < na && b < na) {
       const double* Ca = C0 + 156 * a;
       const double* Cb = C0 + 156 * b;
       const unsigned mask = rowmask[a] & rowmask[b];
-      for (int q = 0; q < 12; q++)
-        if ((mask >> q) & 1u) s += Ca[q * 12 + i] * ((double)rec[MPC_REC_WEIGHTS + q] * Cb[q * 12 + j]);
+      double acc[12];
+#pragma unroll
+      for (int j = 0; j < 12; j++) acc[j] = 0.0;
+      for (int q = 0; q < 12; q++) {
+        if ((mask >> q) & 1u) {
+          const double wa = (double)rec[MPC_REC_WEIGHTS + q] * Ca[q * 12 + i];
+#pragma unroll
+          for (int j = 0; j < 12; j++) acc[j] += wa * Cb[q * 12 + j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 12; j++) k.M[ab * 144 + i * 12 + j] = acc[j];
     }
-    k.M[e] = s;
   }
   cx.sync();
+  MPC_STAMP(k, cx, 11);
   // ---- P11: reduced Hessian, one 3x3 block per stance pair (a >= b) (SolverMPC.cpp:395):
   //   H[(i,la),(j,lb)] = 2 sum_{pa,pb} s_{pa,pb} M_{pa,pb}[la,lb] + 2 alpha I,
   //   s_{pa,pb} = sum_{q=0..n} q^pa (q+d)^pb, d = i-j >= 0, n = h-1-i, from the power sums P_e(n) = sum q^e
@@ -489,16 +560,16 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
   const double alpha = (double)rec[MPC_REC_ALPHA];
   const int nblk = ns * (ns + 1) / 2;
   MPC_FOR(e, nblk) {
-    // e -> (a, b) with a >= b:  a = floor((sqrt(8e+1)-1)/2)
-    int a = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+    // e -> (a, b) with a >= b:  a = floor((sqrt(8e+1)-1)/2), float estimate + exact integer correction
+    int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
     while ((a + 1) * (a + 2) / 2 <= e) a++;
     while (a * (a + 1) / 2 > e) a--;
     const int b = e - a * (a + 1) / 2;
     const int ka = k.stance[a], kb = k.stance[b];
     const int i = ka >> 2, la = ka & 3, j = kb >> 2, lb = kb & 3;  // i >= j (stance[] is ascending)
-    const double d = (double)(i - j), n = (double)(h - 1 - i);
-    const double P0 = n + 1.0, P1 = n * (n + 1.0) * 0.5, P2 = n * (n + 1.0) * (2.0 * n + 1.0) / 6.0, P3 = P1 * P1;
-    const double P4 = n * (n + 1.0) * (2.0 * n + 1.0) * (3.0 * n * n + 3.0 * n - 1.0) / 30.0;
+    const double d = (double)(i - j);
+    const double* P = k.psum + 5 * (h - 1 - i);
+    const double P0 = P[0], P1 = P[1], P2 = P[2], P3 = P[3], P4 = P[4];
     double s[3][3];
     s[0][0] = P0;  s[0][1] = P1 + d * P0;  s[0][2] = P2 + 2.0 * d * P1 + d * d * P0;
     s[1][0] = P1;  s[1][1] = P2 + d * P1;  s[1][2] = P3 + 2.0 * d * P2 + d * d * P1;
@@ -587,6 +658,19 @@ MPC_HD void invert_spd(const Cx& cx, const Work& k) {
 // hides behind the R*C DFMAs.  Shared-memory traffic per thread per pivot: R 8-byte + C/2 16-byte
 // broadcast loads for R*C DFMAs (the kernel is otherwise bound by shared-memory load bandwidth, not fp64).
 // ---------------------------------------------------------------------------
+// 1/d for a positive, finite, normal double: hardware seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps.
+// Branch-free, so every thread can run it next to the bulk update without diverging; non-positive or
+// non-finite d gives a result the caller's  dinv > 0 && dinv < 1e300  test rejects (inf / nan / negative).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+
 template <int GR, int R, int GC, int C>
 __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
   constexpr int NVP = GR * R;
@@ -608,7 +692,7 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
   }
   double* const buf0 = k.ck;
   double* const buf1 = k.ck + (NVP + 2);
-  double dinv_mine = (tr == 0) ? __drcp_rn(dg[0]) : 0.0;  // 1/d of the pivot this thread's row group publishes next
+  double dinv_mine = fast_rcp(dg[0]);  // 1/d of the pivot this thread's row group publishes next
   bool bad = false;
 #pragma unroll
   for (int i = 0; i < R; i++) {
@@ -637,12 +721,9 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
         u[ii] = -c * dinv;
         dg[ii] = fma(u[ii], c, dg[ii]);
       }
-      // reciprocal of the next pivot, started before the bulk update (its row group: tr == (q+1) % GR)
-      if (q + 1 < GR) {
-        if (tr == q + 1) dinv_mine = __drcp_rn(dg[i]);
-      } else if (i + 1 < R) {
-        if (tr == 0) dinv_mine = __drcp_rn(dg[(i + 1 < R) ? i + 1 : i]);
-      }
+      // reciprocal of the next pivot, started before the bulk update so that its latency hides behind the
+      // R*C DFMAs.  Every thread computes it for its own row (no divergence); only the owners' value is used.
+      dinv_mine = fast_rcp((q + 1 < GR) ? dg[i] : dg[(i + 1 < R) ? i + 1 : i]);
 #pragma unroll
       for (int j2 = 0; j2 < C / 2; j2++) {
         const double2 v = *reinterpret_cast<const double2*>(cur + 2 * GC * j2 + 2 * tc);
@@ -685,38 +766,58 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
 // violated by more than `vtol`, every dual is >= 0 by construction and x is the
 // stationary point of its working set, i.e. the KKT point of the strictly convex QP.
 // ---------------------------------------------------------------------------
+// Start of stage 3 (all threads): unconstrained optimum x = -Minv g, empty working set.
+template <class Cx>
+MPC_HD void active_set_init(const Cx& cx, const float* rec, const unsigned char* gait, const Work& k) {
+  Scalars* sc = k.sc;
+  const int nv = sc->nv, ld = k.ld, ns = sc->ns;
+  const double* Hm = k.Hm;
+  MPC_FOR(i, nv) {  // four independent partial sums: the chain is latency-, not throughput-bound
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int j = 0;
+#pragma unroll 1
+    for (; j + 3 < nv; j += 4) {
+      a0 += Hm[j * ld + i] * k.g[j];
+      a1 += Hm[(j + 1) * ld + i] * k.g[j + 1];
+      a2 += Hm[(j + 2) * ld + i] * k.g[j + 2];
+      a3 += Hm[(j + 3) * ld + i] * k.g[j + 3];
+    }
+#pragma unroll 1
+    for (; j < nv; j++) a0 += Hm[j * ld + i] * k.g[j];
+    k.x[i] = -((a0 + a1) + (a2 + a3));
+  }
+  MPC_FOR(j, ns) {
+    k.amask[j] = 0;
+    k.ub[j] = (double)((float)gait[k.stance[j]] * rec[MPC_REC_FMAX]);  // U_b(5k+4), a float product upstream
+  }
+  cx.sync();
+  MPC_STAMP(k, cx, 12);
+}
+
 template <class Cx>
 MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait, const Work& k, int max_iter) {
+  (void)gait;
   Scalars* sc = k.sc;
   const int nv = sc->nv, ns = sc->ns, ld = k.ld, ldT = k.ldT;
-  const int ncons = 6 * ns;
   const double mu_inv = 1.0 / (double)rec[MPC_REC_MU];
-  const double fmax = (double)rec[MPC_REC_FMAX];
   const double* Hm = k.Hm;
   double* T = k.T;
   const double vtol = 1e-9;
 
-  MPC_FOR(i, nv) {
-    double acc = 0;
-    for (int j = 0; j < nv; j++) acc += Hm[j * ld + i] * k.g[j];
-    k.x[i] = -acc;
-  }
-  MPC_FOR(c, ncons) k.act[c] = -1;
-  cx.sync();
-
   for (;;) {
-    // ---- most violated row -------------------------------------------------
+    // ---- most violated row: one stance pair per thread, its six slacks from (fx, fy, fz) ----
     double best = -vtol;
     int bidx = 0x7fffffff;
-    MPC_FOR(c, ncons) {
-      if (k.act[c] >= 0) continue;
-      const Row rw = make_row(c, mu_inv);
-      const int t = c % 6;
-      const double b = (t == 5) ? -(double)((float)gait[k.stance[c / 6]] * (float)fmax) : 0.0;
-      const double sl = rw.ca * k.x[rw.ia] + rw.cz * k.x[rw.iz] - b;
-      if (sl < best) { best = sl; bidx = c; }
+    MPC_FOR(j, ns) {
+      const double fx = k.x[3 * j], fy = k.x[3 * j + 1], fz = k.x[3 * j + 2];
+      const int mask = k.amask[j];
+      const double sl[6] = {fx * mu_inv + fz, fz - fx * mu_inv, fy * mu_inv + fz, fz - fy * mu_inv, fz, k.ub[j] - fz};
+#pragma unroll
+      for (int t = 0; t < 6; t++)
+        if (!((mask >> t) & 1) && sl[t] < best) { best = sl[t]; bidx = 6 * j + t; }
     }
     block_argmin(cx, k.red, best, bidx);
+    if (sc->iters == 0) MPC_STAMP(k, cx, 13);
     if (bidx == 0x7fffffff) break;  // uniform
     if (sc->iters >= max_iter) {
       cx.sync();
@@ -726,7 +827,7 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
     }
     const int p = bidx;
     const Row rp = make_row(p, mu_inv);
-    const double bp = (p % 6 == 5) ? -(double)((float)gait[k.stance[p / 6]] * (float)fmax) : 0.0;
+    const double bp = (p % 6 == 5) ? -k.ub[p / 6] : 0.0;
     cx.sync();
     MPC_ONE { sc->iters++; sc->up = 0.0; }
     cx.sync();
@@ -736,7 +837,8 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       const int m = sc->m;
       // w_a = n_a' Minv n_p,  vnp = n_p' Minv n_p
       MPC_FOR(a, m) {
-        const Row ra = make_row(k.W[a], mu_inv);
+        Row ra;
+        ra.ia = k.Wia[a]; ra.iz = k.Wiz[a]; ra.ca = k.Wca[a]; ra.cz = k.Wcz[a];
         k.w[a] = row_minv_row(Hm, ld, ra, rp);
       }
       const double vnp = row_minv_row(Hm, ld, rp, rp);
@@ -744,6 +846,7 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       // r = T w   (T symmetric: walk columns for contiguous reads)
       MPC_FOR(a, m) {
         double acc = 0;
+#pragma unroll 1
         for (int b = 0; b < m; b++) acc += T[b * ldT + a] * k.w[b];
         k.r[a] = acc;
       }
@@ -758,8 +861,11 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
           if (q < tbest) { tbest = q; tidx = a; }
         }
       }
-      const double wr = block_sum(cx, k.red, part);
-      block_argmin(cx, k.red, tbest, tidx);
+      double wr = 0.0;
+      if (m > 0) {  // uniform
+        wr = block_sum(cx, k.red, part);
+        block_argmin(cx, k.red, tbest, tidx);
+      }
       const double znp = vnp - wr;
       const bool dependent = !(znp > 1e-11 * vnp);
       const double spc = rp.ca * k.x[rp.ia] + rp.cz * k.x[rp.iz] - bp;  // current slack of p (< 0)
@@ -767,36 +873,18 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       const double t1 = (tidx == 0x7fffffff) ? 1e300 : tbest;
       const double t = t1 < t2 ? t1 : t2;
       if (t >= 1e300) { fail = true; break; }  // infeasible (cannot happen: f = 0 is feasible)
-      // coefficient vector c = n_p - N r, gathered per variable through act[]
-      MPC_FOR(v, nv) {
-        const int j = v / 3, ax = v - 3 * j;
-        double cv = 0.0;
-        if (rp.iz == v) cv += rp.cz;
-        if (rp.ca != 0.0 && rp.ia == v) cv += rp.ca;
-        const int* aj = k.act + 6 * j;
-        if (ax == 0) {
-          if (aj[0] >= 0) cv -= k.r[aj[0]] * mu_inv;
-          if (aj[1] >= 0) cv += k.r[aj[1]] * mu_inv;
-        } else if (ax == 1) {
-          if (aj[2] >= 0) cv -= k.r[aj[2]] * mu_inv;
-          if (aj[3] >= 0) cv += k.r[aj[3]] * mu_inv;
-        } else {
-          for (int q = 0; q < 5; q++)
-            if (aj[q] >= 0) cv -= k.r[aj[q]];
-          if (aj[5] >= 0) cv += k.r[aj[5]];
-        }
-        k.cvec[v] = cv;
-      }
-      cx.sync();
-      // x += t * Minv c  (skipped when p is linearly dependent on W: pure dual step)
+      // x += t * Minv (n_p - N r): every row touches <= 2 variables, so z is a combination of at most 2(m+1)
+      // rows of Minv (skipped when p is linearly dependent on W: pure dual step)
       if (!dependent) {
         MPC_FOR(i, nv) {
-          double acc = 0;
-          for (int j = 0; j < nv; j++) {
-            const double cj = k.cvec[j];
-            if (cj != 0.0) acc += cj * Hm[j * ld + i];
+          double acc0 = rp.cz * Hm[rp.iz * ld + i], acc1 = rp.ca * Hm[rp.ia * ld + i];
+#pragma unroll 1
+          for (int a = 0; a < m; a++) {
+            const double ra = k.r[a];
+            acc0 -= ra * k.Wcz[a] * Hm[k.Wiz[a] * ld + i];
+            acc1 -= ra * k.Wca[a] * Hm[k.Wia[a] * ld + i];
           }
-          k.x[i] += t * acc;
+          k.x[i] += t * (acc0 + acc1);
         }
       }
       MPC_FOR(a, m) k.u[a] -= t * k.r[a];
@@ -809,6 +897,7 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
           return;
         }
         const double dinv = 1.0 / znp;
+#pragma unroll 1
         for (int e = cx.tid; e < m * m; e += cx.nt) {
           const int a = e / m, b = e - a * m;
           T[a * ldT + b] += k.r[a] * k.r[b] * dinv;
@@ -820,8 +909,9 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
         MPC_ONE {
           T[m * ldT + m] = dinv;
           k.W[m] = p;
+          k.Wia[m] = rp.ia; k.Wiz[m] = rp.iz; k.Wca[m] = rp.ca; k.Wcz[m] = rp.cz;
           k.u[m] = sc->up + t;
-          k.act[p] = m;
+          k.amask[p / 6] |= 1 << (p % 6);
           sc->m = m + 1;
         }
         cx.sync();
@@ -832,6 +922,7 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       MPC_FOR(a, m) k.tcol[a] = T[a0 * ldT + a];
       cx.sync();
       const double taa_inv = 1.0 / k.tcol[a0];
+#pragma unroll 1
       for (int e = cx.tid; e < m * m; e += cx.nt) {
         const int a = e / m, b = e - a * m;
         if (a != a0 && b != a0) T[a * ldT + b] -= k.tcol[a] * k.tcol[b] * taa_inv;
@@ -849,16 +940,18 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       cx.sync();
       MPC_ONE {
         sc->up += t;
-        k.act[k.W[a0]] = -1;
+        const int cdrop = k.W[a0];
+        k.amask[cdrop / 6] &= ~(1 << (cdrop % 6));
         if (a0 != last) {
           k.W[a0] = k.W[last];
+          k.Wia[a0] = k.Wia[last]; k.Wiz[a0] = k.Wiz[last]; k.Wca[a0] = k.Wca[last]; k.Wcz[a0] = k.Wcz[last];
           k.u[a0] = k.u[last];
-          k.act[k.W[a0]] = a0;
         }
         sc->m = last;
       }
       cx.sync();
     }
+    if (sc->iters == 1) MPC_STAMP(k, cx, 14);
     if (fail) {
       cx.sync();
       MPC_ONE sc->status = MPC_STATUS_MAX_ITER;
@@ -901,6 +994,7 @@ MPC_HD int solve_problem(const Cx& cx, const float* rec, const unsigned char* ga
   if (k.sc->status != MPC_STATUS_OPTIMAL) return k.sc->status;
   invert_spd(cx, k);
   if (k.sc->status != MPC_STATUS_OPTIMAL) return k.sc->status;
+  active_set_init(cx, rec, gait, k);
   active_set(cx, rec, gait, k, max_iter);
   return k.sc->status;
 }

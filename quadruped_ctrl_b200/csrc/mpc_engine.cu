@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -44,9 +45,10 @@ struct SolveParams {
   char* slab;
   mpc::Layout L;
   int max_iter;
+  int warp_mode;
   float* peers[kMaxPeers];
   int n_peers, rank_offset;
-  long long* phase_clk;  // optional [batch][8] SM-clock stamps at phase boundaries (profiling aid)
+  long long* phase_clk;  // optional [batch][24] SM-clock stamps at phase boundaries (profiling aid)
   int32_t* nvar_out;  // assemble-only mode when H_out != nullptr
   double* H_out;
   double* g_out;
@@ -138,7 +140,8 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
     const float* rec = (const float*)(recbuf + (size_t)cur * P.stride);
     const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
 
-    long long* clk = P.phase_clk ? P.phase_clk + (size_t)8 * b : nullptr;
+    long long* clk = P.phase_clk ? P.phase_clk + (size_t)24 * b : nullptr;
+    const_cast<mpc::Work&>(k).clk = clk;
     if (clk && threadIdx.x == 0) clk[0] = clock64();
     mpc::assemble(cx, rec, gait, k);
     if (clk && threadIdx.x == 0) clk[1] = clock64();
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
       continue;
     }
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
+      mpc::active_set_init(cx, rec, gait, k);
       if constexpr (R > 0) {
         static_assert(R == 0 || NT == GR * GC, "thread grid");
         mpc::invert_spd_tiles<GR, R, GC, C>(k, (int)threadIdx.x);
@@ -165,7 +169,17 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
       }
     }
     if (clk && threadIdx.x == 0) clk[2] = clock64();
-    if (k.sc->status == MPC_STATUS_OPTIMAL) mpc::active_set(cx, rec, gait, k, P.max_iter);
+    if (k.sc->status == MPC_STATUS_OPTIMAL) {
+      mpc::active_set_init(cx, rec, gait, k);
+      if constexpr (R > 0) {
+        // shared-memory classes: the active-set loop is a chain of tiny steps, so one warp runs it with
+        // __syncwarp / shuffles instead of CTA barriers; the other warps wait at the barrier below
+        if (P.warp_mode) { if (threadIdx.x < 32) mpc::active_set(mpc::Warp{(int)threadIdx.x, 32}, rec, gait, k, P.max_iter); } else mpc::active_set(cx, rec, gait, k, P.max_iter);
+        __syncthreads();
+      } else {
+        mpc::active_set(cx, rec, gait, k, P.max_iter);
+      }
+    }
     if (clk && threadIdx.x == 0) clk[3] = clock64();
     const int code = k.sc->status;
     if (code == mpc::STATUS_RETRY_BIG && P.retry_list) {
@@ -279,7 +293,7 @@ int free_m_cap(int h, int nv_cap, int npad) {
   int m = 8;
   while (m < nv_cap) {
     const int mm = m + 1;
-    const int gi = mm * (mm | 1) + 2 * nv_cap + 2 * (npad + 2) + 1 + 4 * (mm + 1);
+    const int gi = mm * (mm | 1) + std::max(2 * (npad + 2), nv_cap) + 1 + 4 * h + 6 * (mm + 1);
     if (gi > mpc::kAsmDoubles(h)) break;
     m = mm;
   }
@@ -339,6 +353,7 @@ void fill_params(const mpc_batch* eng, SolveParams& P, const void* records, int 
   P.solution = solution;
   P.status = status;
   P.max_iter = eng->max_iter;
+  P.warp_mode = getenv("MPC_BLOCK_GI") ? 0 : 1;
   P.phase_clk = eng->phase_clk;
   P.n_peers = eng->n_peers;
   P.rank_offset = eng->rank_offset;

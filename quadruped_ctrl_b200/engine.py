@@ -153,7 +153,7 @@ class MpcBatch:
         self._check(self._L.mpc_batch_set_timing(self._h, int(bool(on))), "set_timing")
 
     def set_phase_clock_buffer(self, tensor):
-        """tensor: cuda int64 [max_batch, 8] (or None): per-problem clock64() stamps at phase boundaries."""
+        """tensor: cuda int64 [max_batch, 24] (or None): per-problem clock64() stamps at phase boundaries."""
         self._phase_buf = tensor
         self._check(self._L.mpc_batch_set_phase_clock_buffer(self._h, tensor.data_ptr() if tensor is not None else None),
                     "set_phase_clock_buffer")

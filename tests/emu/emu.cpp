@@ -41,7 +41,10 @@ int emu_solve_batch(const void* records, int batch, int h, int nv_cap, int m_cap
       if (g_out)
         for (int i = 0; i < k.sc->nv; i++) g_out[(size_t)b * NU + i] = k.g[i];
       invert_spd(cx, k);
-      if (k.sc->status == MPC_STATUS_OPTIMAL) active_set(cx, rec, gait, k, max_iter);
+      if (k.sc->status == MPC_STATUS_OPTIMAL) {
+        active_set_init(cx, rec, gait, k);
+        active_set(cx, rec, gait, k, max_iter);
+      }
     }
     int32_t st = 0;
     scatter(cx, k, forces + 12 * b, solution ? solution + (size_t)NU * b : nullptr, &st);

@@ -17,7 +17,7 @@ if len(sys.argv) > 3:
     eng.set_ctas_per_sm_limit(int(sys.argv[3]))
 for _ in range(3):
     eng.solve_device(rec)
-buf = torch.zeros((B, 8), dtype=torch.int64, device="cuda")
+buf = torch.zeros((B, 24), dtype=torch.int64, device="cuda")
 eng.set_phase_clock_buffer(buf)
 eng.solve_device(rec)
 torch.cuda.synchronize()
@@ -27,6 +27,15 @@ names = ["assemble", "invert", "active_set", "scatter+sync"]
 print("%s B=%d: cycles per problem per CTA (median / mean / p95)" % (name, B))
 for i, n in enumerate(names):
     print("  %-14s %8.0f %8.0f %8.0f" % (n, np.median(d[:, i]), d[:, i].mean(), np.percentile(d[:, i], 95)))
+sub = [("asm: P0-P1 (flags, checks, trig)", 0, 8), ("asm: P2 (B_c per leg)", 8, 9), ("asm: P3-P7 (C0,C1,C2,qe)", 9, 10),
+       ("asm: P8-P9 (moments, g, M_ab)", 10, 11), ("asm: P11 (H blocks)", 11, 1), ("gi: x = -Minv g", 2, 12),
+       ("gi: iterations", 12, 3), ("gi: first search", 12, 13), ("gi: first working-set change", 13, 14)]
+iters = None
+for n, a, b in sub:
+    sel = (c[:, a] > 0) & (c[:, b] > 0)
+    dd = (c[:, b] - c[:, a])[sel]
+    print("    %-36s %8.0f %8.0f %8.0f" % (n, np.median(dd), dd.mean(), np.percentile(dd, 95)))
+its = None
 tot = c[:, 4] - c[:, 0]
 print("  %-14s %8.0f %8.0f %8.0f" % ("total", np.median(tot), tot.mean(), np.percentile(tot, 95)))
 # gap between consecutive problems of the same CTA (record wait + loop overhead)
