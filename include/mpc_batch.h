@@ -92,7 +92,8 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch);
 void mpc_batch_destroy(mpc_batch_t* eng);
 
 /* Device-resident solve, asynchronous on `cuda_stream` (a cudaStream_t; NULL =
- * legacy default stream).
+ * legacy default stream).  Uses slot 0's device scratch: do not overlap two
+ * device-resident solves of one engine on different streams.
  *   records_dev  [batch * mpc_record_stride(h)] bytes, 16-byte aligned
  *   forces_dev   [batch * 12] fp32: first-horizon-step forces, force[leg*3+axis],
  *                world frame, exactly what get_solution(0..11) returns upstream
@@ -108,6 +109,17 @@ int mpc_batch_solve_device(mpc_batch_t* eng, const void* records_dev, int batch,
 int mpc_batch_solve_host(mpc_batch_t* eng, const void* records_host, int batch,
                          float* forces_host, double* solution_host,
                          int32_t* status_host);
+
+/* Pipelined host-resident solve.  The engine has two slots (0, 1), each with its own stream, pinned
+ * staging and device buffers.  submit stages `records_host` into the slot and queues H2D, kernels and
+ * D2H on the slot's stream without waiting for the GPU; wait blocks until that slot is done and copies
+ * the results out (pass the slot's own pinned pointers from mpc_batch_host_buffers to skip the copies).
+ * Alternating slots overlaps one batch's transfers and host-side packing with the other's kernels.
+ * mpc_batch_solve_host == submit(slot 0) + wait(slot 0). */
+int mpc_batch_submit_host(mpc_batch_t* eng, int slot, const void* records_host, int batch,
+                          int want_solution);
+int mpc_batch_wait_host(mpc_batch_t* eng, int slot, float* forces_host, double* solution_host,
+                        int32_t* status_host);
 
 /* Debug / parity entry: assembles the reduced QP only and writes it out.
  *   nvar_dev [batch] int32: reduced variable count nv = 3 * (#stance (step,leg))
@@ -143,6 +155,10 @@ int mpc_batch_set_phase_clock_buffer(mpc_batch_t* eng, long long* dev_buf);
  * 0 restores the occupancy-derived default. */
 int mpc_batch_set_ctas_per_sm_limit(mpc_batch_t* eng, int limit);
 
+/* Turns timing on for ONE size class only (two events per solve instead of two per class);
+ * idx = -1 times every class again. */
+int mpc_batch_set_timed_class(mpc_batch_t* eng, int idx);
+
 /* Size classes the engine sorts problems into (by reduced variable count).
  * info[6] = { nv_cap, m_cap, threads per CTA, grid, shared-memory bytes per CTA,
  *             1 if the QP tile lives in shared memory (0: per-CTA global slab) }. */
@@ -161,11 +177,11 @@ float mpc_batch_last_class_kernel_ms(mpc_batch_t* eng, int idx);
  * since the mark (CUDA events recorded on each call's own stream). */
 void mpc_batch_timing_mark(mpc_batch_t* eng);
 int mpc_batch_timing_collect(mpc_batch_t* eng, int idx, float* mean_ms, int* n_solves);
-/* The engine's pinned host staging buffers ([max_batch] records / forces / solution /
+/* Slot `slot`'s pinned host staging buffers ([max_batch] records / forces / solution /
  * status).  A caller that fills *records and passes these same pointers to
- * mpc_batch_solve_host skips the pageable->pinned copies. */
-int mpc_batch_host_buffers(mpc_batch_t* eng, void** records, float** forces, double** solution,
-                           int32_t** status);
+ * mpc_batch_solve_host (slot 0) / submit_host / wait_host skips the pageable->pinned copies. */
+int mpc_batch_host_buffers(mpc_batch_t* eng, int slot, void** records, float** forces,
+                           double** solution, int32_t** status);
 /* Human-readable description of the last error on this engine ("" if none). */
 const char* mpc_batch_last_error(const mpc_batch_t* eng);
 /* Library-level: text of the last error when no engine exists (create failed). */

@@ -82,17 +82,32 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                : "memory");
 }
 
+// One thread per problem: counts the stance (step,leg) pairs of its gait table (16-byte loads: the table starts
+// 16-byte aligned inside the record), picks the size class and appends the problem to that class's list.  Also
+// zeroes the OTHER parity's counters for the next solve, so no memset sits between solves.
 __global__ void mpc_classify_kernel(const char* records, unsigned long long stride, int h, int batch, int n_classes,
-                                    const int* __restrict__ class_cap, int* lists, int* counts, int max_batch) {
+                                    const int* __restrict__ class_cap, int* lists, int* counts, int* counts_next,
+                                    int max_batch) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < kMaxClasses) counts_next[b] = 0;
   if (b >= batch) return;
   const float* rec = (const float*)(records + stride * b);
-  const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * h);
   const float fmax = rec[MPC_REC_FMAX];
+  const uint4* g4 = (const uint4*)((const char*)rec + 4 * (MPC_REC_TRAJ + 12 * h));
+  const int nbytes = 4 * h;
   int ns = 0;
-  for (int k = 0; k < 4 * h; k++) {
-    const float ub = (float)gait[k] * fmax;
-    ns += !((double)ub < 0.01 && (double)ub > -0.01);
+  for (int q = 0; q * 16 < nbytes; q++) {
+    const uint4 v = g4[q];  // bytes past 4h are the record's zero padding (stride is rounded up to 16)
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        if (q * 16 + i * 4 + e < nbytes) {
+          const float ub = (float)((w[i] >> (8 * e)) & 0xffu) * fmax;
+          ns += !((double)ub < 0.01 && (double)ub > -0.01);
+        }
+      }
   }
   const int nv = 3 * ns;
   int c = 0;
@@ -218,25 +233,33 @@ thread_local std::string g_err;
 struct mpc_batch {
   int device = 0, h = 0, max_batch = 0, sms = 0;
   size_t stride = 0;
-  cudaStream_t stream = nullptr;  // owned, used by the host-resident entry
-  char* rec_dev = nullptr;
-  float* forces_dev = nullptr;
-  double* sol_dev = nullptr;
-  int32_t* status_dev = nullptr;
-  char* rec_pin = nullptr;
-  float* forces_pin = nullptr;
-  double* sol_pin = nullptr;
-  int32_t* status_pin = nullptr;
-  int* lists = nullptr;
-  int* counts = nullptr;
+  // Two independent slots (stream + staging + device scratch) so that the host entry can be pipelined:
+  // slot k's H2D / kernels / D2H overlap the host's packing of slot 1-k.  Slot 0 serves the synchronous calls.
+  struct Slot {
+    cudaStream_t stream = nullptr;
+    char* rec_dev = nullptr;
+    float* forces_dev = nullptr;
+    double* sol_dev = nullptr;
+    int32_t* status_dev = nullptr;
+    char* rec_pin = nullptr;
+    float* forces_pin = nullptr;
+    double* sol_pin = nullptr;
+    int32_t* status_pin = nullptr;
+    int* lists = nullptr;   // [classes][max_batch] problem ids per size class
+    int* counts = nullptr;  // [2][classes], double-buffered by solve parity
+    int parity = 0;
+    char* slab = nullptr;   // per-CTA global workspace of the catch-all class
+    int pending_batch = 0;
+    bool pending_solution = false;
+  } s[2];
   int* caps_dev = nullptr;
-  char* slab = nullptr;
   std::vector<ClassCfg> classes;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // timing ring: event pairs around every class kernel of the last kRing solves (no sync while recording)
   std::vector<cudaEvent_t> ring0, ring1;
   long ring_pos = 0, ring_mark = 0;
   bool timed = false;
+  int timed_class = -1;  // -1: events around every class kernel; k: around class k's kernel only
   long launches = 0;
   int max_iter = 4000;
   float* peers[kMaxPeers] = {nullptr};
@@ -367,43 +390,47 @@ int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int gr
   return MPC_OK;
 }
 
-int solve_on_stream(mpc_batch* eng, const void* records, int batch, float* forces, double* solution, int32_t* status,
-                    cudaStream_t st, int32_t* nvar_out, double* H_out, double* g_out) {
+int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, float* forces, double* solution,
+                    int32_t* status, cudaStream_t st, int32_t* nvar_out, double* H_out, double* g_out) {
   if (batch == 0) return MPC_OK;
   const int nc = (int)eng->classes.size();
-  CK(cudaMemsetAsync(eng->counts, 0, sizeof(int) * kMaxClasses, st));
+  mpc_batch::Slot& S = eng->s[slot];
+  // class counters are double-buffered by solve parity: this solve's classify kernel zeroes the other set
+  int* counts = S.counts + (S.parity ? kMaxClasses : 0);
+  int* counts_next = S.counts + (S.parity ? 0 : kMaxClasses);
+  S.parity ^= 1;
   mpc_classify_kernel<<<(batch + 127) / 128, 128, 0, st>>>((const char*)records, eng->stride, eng->h, batch, nc,
-                                                           eng->caps_dev, eng->lists, eng->counts, eng->max_batch);
+                                                           eng->caps_dev, S.lists, counts, counts_next, eng->max_batch);
   eng->launches++;
   CK(cudaGetLastError());
-  if (eng->timed) CK(cudaEventRecord(eng->ev0, st));
+  const bool time_all = eng->timed && eng->timed_class < 0;
+  if (time_all) CK(cudaEventRecord(eng->ev0, st));
   for (int ci = 0; ci < nc; ci++) {
     const ClassCfg& c = eng->classes[ci];
     SolveParams P;
     fill_params(eng, P, records, batch, forces, solution, status);
-    P.list = eng->lists + (size_t)ci * eng->max_batch;
-    P.count = eng->counts + ci;
+    P.list = S.lists + (size_t)ci * eng->max_batch;
+    P.count = counts + ci;
     P.L = c.L;
-    P.slab = c.in_fast ? nullptr : eng->slab;
+    P.slab = c.in_fast ? nullptr : S.slab;
     if (ci != nc - 1) {
-      P.retry_list = eng->lists + (size_t)(nc - 1) * eng->max_batch;
-      P.retry_count = eng->counts + (nc - 1);
+      P.retry_list = S.lists + (size_t)(nc - 1) * eng->max_batch;
+      P.retry_count = counts + (nc - 1);
     }
     P.nvar_out = nvar_out;
     P.H_out = H_out;
     P.g_out = g_out;
     const size_t slot = (size_t)(eng->ring_pos % kRing) * kMaxClasses + ci;
-    if (eng->timed) CK(cudaEventRecord(eng->ring0[slot], st));
+    const bool time_this = eng->timed && (eng->timed_class < 0 || eng->timed_class == ci);
+    if (time_this) CK(cudaEventRecord(eng->ring0[slot], st));
     int grid = std::min(c.grid, batch);
     if (eng->ctas_per_sm_limit > 0) grid = std::min(grid, eng->ctas_per_sm_limit * eng->sms);
     int rc = launch_solve(eng, c, P, grid, st);
     if (rc) return rc;
-    if (eng->timed) CK(cudaEventRecord(eng->ring1[slot], st));
+    if (time_this) CK(cudaEventRecord(eng->ring1[slot], st));
   }
-  if (eng->timed) {
-    CK(cudaEventRecord(eng->ev1, st));
-    eng->ring_pos++;
-  }
+  if (time_all) CK(cudaEventRecord(eng->ev1, st));
+  if (eng->timed) eng->ring_pos++;
   return MPC_OK;
 }
 
@@ -452,7 +479,6 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
   eng->sms = prop.multiProcessorCount;
   eng->stride = mpc_record_stride(horizon);
   CKC(cudaSetDevice(device));
-  CKC(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&eng->ev0));
   CKC(cudaEventCreate(&eng->ev1));
   eng->ring0.assign((size_t)kRing * kMaxClasses, nullptr);
@@ -464,22 +490,27 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
   int rc = build_classes(eng);
   if (rc) return fail(rc);
   const size_t B = (size_t)max_batch, NU = 12 * (size_t)horizon;
-  CKC(cudaMalloc(&eng->rec_dev, B * eng->stride));
-  CKC(cudaMalloc(&eng->forces_dev, B * 12 * sizeof(float)));
-  CKC(cudaMalloc(&eng->sol_dev, B * NU * sizeof(double)));
-  CKC(cudaMalloc(&eng->status_dev, B * sizeof(int32_t)));
-  CKC(cudaMallocHost(&eng->rec_pin, B * eng->stride));
-  CKC(cudaMallocHost(&eng->forces_pin, B * 12 * sizeof(float)));
-  CKC(cudaMallocHost(&eng->sol_pin, B * NU * sizeof(double)));
-  CKC(cudaMallocHost(&eng->status_pin, B * sizeof(int32_t)));
-  CKC(cudaMalloc(&eng->lists, sizeof(int) * kMaxClasses * B));
-  CKC(cudaMalloc(&eng->counts, sizeof(int) * kMaxClasses));
+  const ClassCfg& big = eng->classes.back();
+  for (int q = 0; q < 2; q++) {
+    mpc_batch::Slot& S = eng->s[q];
+    CKC(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    CKC(cudaMalloc(&S.rec_dev, B * eng->stride));
+    CKC(cudaMalloc(&S.forces_dev, B * 12 * sizeof(float)));
+    CKC(cudaMalloc(&S.sol_dev, B * NU * sizeof(double)));
+    CKC(cudaMalloc(&S.status_dev, B * sizeof(int32_t)));
+    CKC(cudaMallocHost(&S.rec_pin, B * eng->stride));
+    CKC(cudaMallocHost(&S.forces_pin, B * 12 * sizeof(float)));
+    CKC(cudaMallocHost(&S.sol_pin, B * NU * sizeof(double)));
+    CKC(cudaMallocHost(&S.status_pin, B * sizeof(int32_t)));
+    CKC(cudaMalloc(&S.lists, sizeof(int) * kMaxClasses * B));
+    CKC(cudaMalloc(&S.counts, sizeof(int) * 2 * kMaxClasses));
+    CKC(cudaMemset(S.counts, 0, sizeof(int) * 2 * kMaxClasses));
+    CKC(cudaMalloc(&S.slab, big.L.slab_bytes * (size_t)big.grid));
+  }
   CKC(cudaMalloc(&eng->caps_dev, sizeof(int) * kMaxClasses));
   int caps[kMaxClasses] = {0};
   for (size_t i = 0; i < eng->classes.size(); i++) caps[i] = eng->classes[i].nv_cap;
   CKC(cudaMemcpy(eng->caps_dev, caps, sizeof(caps), cudaMemcpyHostToDevice));
-  const ClassCfg& big = eng->classes.back();
-  CKC(cudaMalloc(&eng->slab, big.L.slab_bytes * (size_t)big.grid));
 #undef CKC
   *out = eng;
   return MPC_OK;
@@ -491,25 +522,28 @@ void mpc_batch_destroy(mpc_batch_t* eng) {
   for (int q = 0; q < kMaxPeers; q++)
     if (eng->peer_open[q]) cudaIpcCloseMemHandle(eng->peer_open[q]);
   cudaFree(eng->gather_buf);
-  cudaFree(eng->rec_dev);
-  cudaFree(eng->forces_dev);
-  cudaFree(eng->sol_dev);
-  cudaFree(eng->status_dev);
-  cudaFreeHost(eng->rec_pin);
-  cudaFreeHost(eng->forces_pin);
-  cudaFreeHost(eng->sol_pin);
-  cudaFreeHost(eng->status_pin);
-  cudaFree(eng->lists);
-  cudaFree(eng->counts);
+  for (int q = 0; q < 2; q++) {
+    mpc_batch::Slot& S = eng->s[q];
+    cudaFree(S.rec_dev);
+    cudaFree(S.forces_dev);
+    cudaFree(S.sol_dev);
+    cudaFree(S.status_dev);
+    cudaFreeHost(S.rec_pin);
+    cudaFreeHost(S.forces_pin);
+    cudaFreeHost(S.sol_pin);
+    cudaFreeHost(S.status_pin);
+    cudaFree(S.lists);
+    cudaFree(S.counts);
+    cudaFree(S.slab);
+    if (S.stream) cudaStreamDestroy(S.stream);
+  }
   cudaFree(eng->caps_dev);
-  cudaFree(eng->slab);
   if (eng->ev0) cudaEventDestroy(eng->ev0);
   if (eng->ev1) cudaEventDestroy(eng->ev1);
   for (cudaEvent_t e : eng->ring0)
     if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : eng->ring1)
     if (e) cudaEventDestroy(e);
-  if (eng->stream) cudaStreamDestroy(eng->stream);
   delete eng;
 }
 
@@ -521,8 +555,57 @@ int mpc_batch_solve_device(mpc_batch_t* eng, const void* records_dev, int batch,
     return MPC_E_ARG;
   }
   CK(cudaSetDevice(eng->device));
-  return solve_on_stream(eng, records_dev, batch, forces_dev, solution_dev, status_dev, (cudaStream_t)cuda_stream,
+  return solve_on_stream(eng, 0, records_dev, batch, forces_dev, solution_dev, status_dev, (cudaStream_t)cuda_stream,
                          nullptr, nullptr, nullptr);
+}
+
+int mpc_batch_submit_host(mpc_batch_t* eng, int slot, const void* records_host, int batch, int want_solution) {
+  if (!eng) return MPC_E_ARG;
+  if (slot < 0 || slot > 1 || !records_host || batch < 0 || batch > eng->max_batch) {
+    eng->err = "mpc_batch_submit_host: bad argument";
+    return MPC_E_ARG;
+  }
+  CK(cudaSetDevice(eng->device));
+  mpc_batch::Slot& S = eng->s[slot];
+  S.pending_batch = batch;
+  S.pending_solution = want_solution != 0;
+  if (batch == 0) return MPC_OK;
+  const size_t NU = 12 * (size_t)eng->h;
+  // pageable -> pinned staging on the host (skipped when the caller filled the slot's pinned buffer in place),
+  // then H2D, kernels and D2H queued on the slot's stream; nothing here waits for the GPU
+  if (records_host != (const void*)S.rec_pin) memcpy(S.rec_pin, records_host, (size_t)batch * eng->stride);
+  CK(cudaMemcpyAsync(S.rec_dev, S.rec_pin, (size_t)batch * eng->stride, cudaMemcpyHostToDevice, S.stream));
+  int rc = solve_on_stream(eng, slot, S.rec_dev, batch, S.forces_dev, want_solution ? S.sol_dev : nullptr, S.status_dev,
+                           S.stream, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(S.forces_pin, S.forces_dev, (size_t)batch * 12 * sizeof(float), cudaMemcpyDeviceToHost, S.stream));
+  if (want_solution)
+    CK(cudaMemcpyAsync(S.sol_pin, S.sol_dev, (size_t)batch * NU * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+  CK(cudaMemcpyAsync(S.status_pin, S.status_dev, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, S.stream));
+  return MPC_OK;
+}
+
+int mpc_batch_wait_host(mpc_batch_t* eng, int slot, float* forces_host, double* solution_host, int32_t* status_host) {
+  if (!eng) return MPC_E_ARG;
+  if (slot < 0 || slot > 1) {
+    eng->err = "mpc_batch_wait_host: bad slot";
+    return MPC_E_ARG;
+  }
+  mpc_batch::Slot& S = eng->s[slot];
+  const int batch = S.pending_batch;
+  if (solution_host && !S.pending_solution) {
+    eng->err = "mpc_batch_wait_host: the solution was not requested at submit time";
+    return MPC_E_ARG;
+  }
+  CK(cudaSetDevice(eng->device));
+  CK(cudaStreamSynchronize(S.stream));
+  const size_t NU = 12 * (size_t)eng->h;
+  if (forces_host && forces_host != S.forces_pin) memcpy(forces_host, S.forces_pin, (size_t)batch * 12 * sizeof(float));
+  if (solution_host && solution_host != S.sol_pin)
+    memcpy(solution_host, S.sol_pin, (size_t)batch * NU * sizeof(double));
+  if (status_host && status_host != S.status_pin) memcpy(status_host, S.status_pin, (size_t)batch * sizeof(int32_t));
+  S.pending_batch = 0;
+  return MPC_OK;
 }
 
 int mpc_batch_solve_host(mpc_batch_t* eng, const void* records_host, int batch, float* forces_host,
@@ -532,29 +615,9 @@ int mpc_batch_solve_host(mpc_batch_t* eng, const void* records_host, int batch, 
     eng->err = "mpc_batch_solve_host: bad argument";
     return MPC_E_ARG;
   }
-  if (batch == 0) return MPC_OK;
-  CK(cudaSetDevice(eng->device));
-  const size_t NU = 12 * (size_t)eng->h;
-  cudaStream_t st = eng->stream;
-  // pageable -> pinned staging on the host, then one async H2D; callers that already hold
-  // pinned memory pay one memcpy (the record block is < 1 KB per problem)
-  if (records_host != (const void*)eng->rec_pin) memcpy(eng->rec_pin, records_host, (size_t)batch * eng->stride);
-  CK(cudaMemcpyAsync(eng->rec_dev, eng->rec_pin, (size_t)batch * eng->stride, cudaMemcpyHostToDevice, st));
-  int rc = solve_on_stream(eng, eng->rec_dev, batch, eng->forces_dev, solution_host ? eng->sol_dev : nullptr,
-                           eng->status_dev, st, nullptr, nullptr, nullptr);
+  int rc = mpc_batch_submit_host(eng, 0, records_host, batch, solution_host != nullptr);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(eng->forces_pin, eng->forces_dev, (size_t)batch * 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (solution_host)
-    CK(cudaMemcpyAsync(eng->sol_pin, eng->sol_dev, (size_t)batch * NU * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (status_host)
-    CK(cudaMemcpyAsync(eng->status_pin, eng->status_dev, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  if (forces_host != eng->forces_pin) memcpy(forces_host, eng->forces_pin, (size_t)batch * 12 * sizeof(float));
-  if (solution_host && solution_host != eng->sol_pin)
-    memcpy(solution_host, eng->sol_pin, (size_t)batch * NU * sizeof(double));
-  if (status_host && status_host != eng->status_pin)
-    memcpy(status_host, eng->status_pin, (size_t)batch * sizeof(int32_t));
-  return MPC_OK;
+  return mpc_batch_wait_host(eng, 0, forces_host, solution_host, status_host);
 }
 
 int mpc_batch_assemble_device(mpc_batch_t* eng, const void* records_dev, int batch, int32_t* nvar_dev, double* H_dev,
@@ -565,7 +628,7 @@ int mpc_batch_assemble_device(mpc_batch_t* eng, const void* records_dev, int bat
     return MPC_E_ARG;
   }
   CK(cudaSetDevice(eng->device));
-  return solve_on_stream(eng, records_dev, batch, eng->forces_dev, nullptr, nullptr, (cudaStream_t)cuda_stream,
+  return solve_on_stream(eng, 0, records_dev, batch, eng->s[0].forces_dev, nullptr, nullptr, (cudaStream_t)cuda_stream,
                          nvar_dev, H_dev, g_dev);
 }
 
@@ -598,13 +661,21 @@ int mpc_batch_set_ctas_per_sm_limit(mpc_batch_t* eng, int limit) {
 int mpc_batch_set_timing(mpc_batch_t* eng, int enabled) {
   if (!eng) return MPC_E_ARG;
   eng->timed = enabled != 0;
+  eng->timed_class = -1;
+  return MPC_OK;
+}
+
+int mpc_batch_set_timed_class(mpc_batch_t* eng, int idx) {
+  if (!eng || idx < -1 || idx >= (int)eng->classes.size()) return MPC_E_ARG;
+  eng->timed = true;
+  eng->timed_class = idx;
   return MPC_OK;
 }
 
 long mpc_batch_kernel_launches(const mpc_batch_t* eng) { return eng ? eng->launches : 0; }
 
 float mpc_batch_last_solve_kernel_ms(mpc_batch_t* eng) {
-  if (!eng || !eng->timed) return -1.f;
+  if (!eng || !eng->timed || eng->timed_class >= 0) return -1.f;
   float ms = -1.f;
   if (cudaEventSynchronize(eng->ev1) != cudaSuccess) return -1.f;
   if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) != cudaSuccess) return -1.f;
@@ -642,12 +713,14 @@ int mpc_batch_timing_collect(mpc_batch_t* eng, int idx, float* mean_ms, int* n_s
   return MPC_OK;
 }
 
-int mpc_batch_host_buffers(mpc_batch_t* eng, void** records, float** forces, double** solution, int32_t** status) {
-  if (!eng) return MPC_E_ARG;
-  if (records) *records = eng->rec_pin;
-  if (forces) *forces = eng->forces_pin;
-  if (solution) *solution = eng->sol_pin;
-  if (status) *status = eng->status_pin;
+int mpc_batch_host_buffers(mpc_batch_t* eng, int slot, void** records, float** forces, double** solution,
+                           int32_t** status) {
+  if (!eng || slot < 0 || slot > 1) return MPC_E_ARG;
+  mpc_batch::Slot& S = eng->s[slot];
+  if (records) *records = S.rec_pin;
+  if (forces) *forces = S.forces_pin;
+  if (solution) *solution = S.sol_pin;
+  if (status) *status = S.status_pin;
   return MPC_OK;
 }
 

@@ -22,8 +22,9 @@ STATUS_OPTIMAL, STATUS_MAX_ITER, STATUS_BAD_INPUT, STATUS_NOT_PD, STATUS_NO_STAN
 
 # every symbol include/mpc_batch.h and include/convexMPC_interface.h declare
 BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_create", "mpc_batch_destroy",
-                 "mpc_batch_solve_device", "mpc_batch_solve_host", "mpc_batch_assemble_device",
-                 "mpc_batch_set_gather_peers", "mpc_batch_set_max_iterations", "mpc_batch_set_timing", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
+                 "mpc_batch_solve_device", "mpc_batch_solve_host", "mpc_batch_submit_host", "mpc_batch_wait_host",
+                 "mpc_batch_assemble_device",
+                 "mpc_batch_set_gather_peers", "mpc_batch_set_max_iterations", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
                  "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
                  "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_class_kernel_ms", "mpc_batch_timing_mark",
                  "mpc_batch_timing_collect", "mpc_batch_host_buffers",
@@ -67,10 +68,13 @@ def lib():
     L.mpc_batch_destroy.restype = None
     L.mpc_batch_solve_device.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.mpc_batch_solve_host.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.mpc_batch_submit_host.argtypes = [vp, i32, vp, i32, i32]
+    L.mpc_batch_wait_host.argtypes = [vp, i32, vp, vp, vp]
     L.mpc_batch_assemble_device.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.mpc_batch_set_gather_peers.argtypes = [vp, ctypes.POINTER(vp), i32, i32]
     L.mpc_batch_set_max_iterations.argtypes = [vp, i32]
     L.mpc_batch_set_timing.argtypes = [vp, i32]
+    L.mpc_batch_set_timed_class.argtypes = [vp, i32]
     L.mpc_batch_set_phase_clock_buffer.argtypes = [vp, vp]
     L.mpc_batch_set_ctas_per_sm_limit.argtypes = [vp, i32]
     L.mpc_batch_num_classes.argtypes = [vp]
@@ -84,7 +88,7 @@ def lib():
     L.mpc_batch_timing_mark.argtypes = [vp]
     L.mpc_batch_timing_mark.restype = None
     L.mpc_batch_timing_collect.argtypes = [vp, i32, ctypes.POINTER(f32), ctypes.POINTER(i32)]
-    L.mpc_batch_host_buffers.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+    L.mpc_batch_host_buffers.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                          ctypes.POINTER(vp)]
     L.mpc_batch_last_error.argtypes = [vp]
     L.mpc_batch_last_error.restype = ctypes.c_char_p
@@ -164,6 +168,9 @@ class MpcBatch:
     def last_solve_kernel_ms(self):
         return float(self._L.mpc_batch_last_solve_kernel_ms(self._h))
 
+    def set_timed_class(self, idx):
+        self._check(self._L.mpc_batch_set_timed_class(self._h, int(idx)), "set_timed_class")
+
     def last_class_kernel_ms(self, idx):
         return float(self._L.mpc_batch_last_class_kernel_ms(self._h, int(idx)))
 
@@ -177,12 +184,13 @@ class MpcBatch:
                     "timing_collect")
         return float(ms.value), int(n.value)
 
-    def host_buffers(self):
-        """numpy views of the engine's pinned staging buffers: (records [max_batch, stride] u8,
+    def host_buffers(self, slot=0):
+        """numpy views of slot `slot`'s pinned staging buffers: (records [max_batch, stride] u8,
         forces [max_batch, 12] f32, solution [max_batch, 12h] f64, status [max_batch] i32).  Passing these to
-        solve_host skips the pageable->pinned copies."""
+        solve_host / submit_host / wait_host skips the pageable->pinned copies."""
         ptrs = [ctypes.c_void_p() for _ in range(4)]
-        self._check(self._L.mpc_batch_host_buffers(self._h, *[ctypes.byref(p) for p in ptrs]), "host_buffers")
+        self._check(self._L.mpc_batch_host_buffers(self._h, int(slot), *[ctypes.byref(p) for p in ptrs]),
+                    "host_buffers")
         B, NU = self.max_batch, 12 * self.horizon
 
         def view(p, nbytes, dtype, shape):
@@ -250,6 +258,23 @@ class MpcBatch:
                                           sol.ctypes.data if want_solution else None, status.ctypes.data)
         self._check(rc, "mpc_batch_solve_host")
         return forces, sol, status
+
+    def submit_host(self, slot, records, want_solution=False):
+        """Queues H2D + kernels + D2H for `records` (numpy uint8 [B, stride]) on slot 0 or 1; returns at once."""
+        records = np.ascontiguousarray(records, np.uint8)
+        assert records.shape[1] == self.stride
+        rc = self._L.mpc_batch_submit_host(self._h, int(slot), records.ctypes.data, records.shape[0],
+                                           int(bool(want_solution)))
+        self._check(rc, "mpc_batch_submit_host")
+
+    def wait_host(self, slot, out_forces=None, out_solution=None, out_status=None):
+        """Waits for slot `slot` and copies its results into the given numpy arrays (None: left in the slot's
+        pinned buffers, see host_buffers)."""
+        rc = self._L.mpc_batch_wait_host(self._h, int(slot),
+                                         out_forces.ctypes.data if out_forces is not None else None,
+                                         out_solution.ctypes.data if out_solution is not None else None,
+                                         out_status.ctypes.data if out_status is not None else None)
+        self._check(rc, "mpc_batch_wait_host")
 
     def assemble_device(self, records, stream=None):
         """Parity entry: the reduced QP only.  Returns (nv [B] int32, H [B,12h,12h] f64, g [B,12h] f64)."""

@@ -207,3 +207,26 @@ def test_working_set_overflow_is_requeued_not_dropped(oracle, cuda_engine_factor
     o = oracle.solve_batch(rec, h, 64, "port")
     assert rel(sol, o["sol"]).max() < 1e-6
     assert E.status_iterations(status).max() > m_cap   # at least one problem really did overflow the tile
+
+
+def test_pipelined_host_entry_matches_synchronous(cuda_engine_factory):
+    """submit_host / wait_host on alternating slots return exactly what solve_host returns."""
+    eng = cuda_engine_factory(10, 512)
+    batches = [W.config2(512, 10, 100 + i) for i in range(5)]
+    ref = [eng.solve_host(b, want_solution=True) for b in batches]
+    got = []
+    for i, b in enumerate(batches):
+        eng.submit_host(i & 1, b, want_solution=True)
+        if i > 0:
+            f = np.empty((512, 12), np.float32)
+            s = np.empty((512, 120), np.float64)
+            st = np.empty(512, np.int32)
+            eng.wait_host((i - 1) & 1, f, s, st)
+            got.append((f, s, st))
+    f = np.empty((512, 12), np.float32)
+    s = np.empty((512, 120), np.float64)
+    st = np.empty(512, np.int32)
+    eng.wait_host((len(batches) - 1) & 1, f, s, st)
+    got.append((f, s, st))
+    for (rf, rs, rst), (gf, gs, gst) in zip(ref, got):
+        assert np.array_equal(rf, gf) and np.array_equal(rs, gs) and np.array_equal(rst, gst)
