@@ -86,7 +86,7 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
   Layout L;
   L.h = h;
   L.nv_cap = nv_cap;
-  // register-tiled inversion: two (npad + 2)-long buffers (double-buffered pivot column + 1/pivot)
+  // register-resident inversion: two (npad + 2)-long buffers (double-buffered pivot row + 1/pivot)
   L.ck_len = npad > 0 ? 2 * (npad + 2) : nv_cap;
   L.m_cap = m_cap;
   L.ld = nv_cap | 1;
@@ -594,45 +594,69 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
 // After sweeping every index the array holds -H^{-1}; the sign is flipped at the
 // end.  A non-positive pivot means H is not positive definite.
 // ---------------------------------------------------------------------------
+// Generic form for a matrix in shared or global memory (the catch-all size class, whose matrix lives in an
+// L2-resident global slab).  One pivot per pass: blocking several pivots per pass (rank-k updates) would cut
+// the traffic by k, but block sweeps are numerically unusable here -- the k x k diagonal blocks inherit the
+// alpha-regularised internal-force null space (cond ~ 1e4) and the one-shot Schur complement then loses
+// 3 digits per doubling of k (measured: |Minv H - I| 3e-12 at k=1, 1e-9 at k=2, 9e-6 at k=4, 1e-3 at k=8).
+// Only the lower triangle is updated (4x4 register tiles, uniform rank-1 update with the pivot slot holding
+// d-1 as in the register-resident version); the pivot row is gathered from row p (j <= p) and column p
+// (i > p); the result is mirrored, negated and the 2 taken off the diagonal in one final pass.
 template <class Cx>
 MPC_HD void invert_spd(const Cx& cx, const Work& k) {
   Scalars* sc = k.sc;
   const int nv = sc->nv, ld = k.ld;
   double* Hm = k.Hm;
   double* ck = k.ck;
-  // thread -> (row group, column): columns fastest so that a warp shares one row
-  int cols = 1;
-  while (cols < nv && cols < cx.nt) cols <<= 1;
-  const int rgroups = cx.nt / cols > 0 ? cx.nt / cols : 1;
-  const int jc = cx.tid % cols, ig = cx.tid / cols;
+  const int nt4 = (nv + 3) / 4;
+  const int ntiles = nt4 * (nt4 + 1) / 2;
   for (int p = 0; p < nv; p++) {
-    const double d = Hm[p * ld + p];
+    MPC_FOR(i, nv) {
+      const double v = (i <= p) ? Hm[p * ld + i] : Hm[i * ld + p];
+      ck[i] = (i == p) ? v - 1.0 : v;
+    }
+    cx.sync();
+    const double d = ck[p] + 1.0;
     if (!(d > 0.0)) {  // uniform: every thread reads the same pivot
       cx.sync();
       MPC_ONE sc->status = MPC_STATUS_NOT_PD;
       cx.sync();
       return;
     }
-    MPC_FOR(i, nv) ck[i] = Hm[p * ld + i];
-    cx.sync();
     const double dinv = 1.0 / d;
-    if (ig < rgroups) {
-      for (int j = jc; j < nv; j += cols) {
-        const double cj = ck[j] * dinv;
-        for (int i = ig; i < nv; i += rgroups) {
-          double val;
-          if (i == p) val = (j == p) ? -dinv : cj;
-          else if (j == p) val = ck[i] * dinv;
-          else val = Hm[i * ld + j] - ck[i] * cj;
-          Hm[i * ld + j] = val;
-        }
+    MPC_FOR(t, ntiles) {
+      int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+      while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
+      while (bi * (bi + 1) / 2 > t) bi--;
+      const int bj = t - bi * (bi + 1) / 2;
+      const int i0 = 4 * bi, j0 = 4 * bj;
+      double u[4], v[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        u[e] = (i0 + e < nv) ? -ck[i0 + e] * dinv : 0.0;
+        v[e] = (j0 + e < nv) ? ck[j0 + e] : 0.0;
       }
+#pragma unroll
+      for (int di = 0; di < 4; di++)
+#pragma unroll
+        for (int dj = 0; dj < 4; dj++) {
+          const int i = i0 + di, j = j0 + dj;
+          if (i < nv && j <= i) Hm[i * ld + j] += u[di] * v[dj];
+        }
     }
     cx.sync();
   }
-  if (ig < rgroups)
-    for (int j = jc; j < nv; j += cols)
-      for (int i = ig; i < nv; i += rgroups) Hm[i * ld + j] = -Hm[i * ld + j];
+  // mirror the lower triangle, negate, take the 2 off the (swept) diagonal
+  MPC_FOR(e, nv * nv) {
+    const int i = e / nv, j = e - i * nv;
+    if (j < i) {
+      const double v = -Hm[i * ld + j];
+      Hm[i * ld + j] = v;
+      Hm[j * ld + i] = v;
+    } else if (j == i) {
+      Hm[i * ld + i] = 2.0 - Hm[i * ld + i];
+    }
+  }
   cx.sync();
 }
 
@@ -674,12 +698,13 @@ __device__ __forceinline__ double fast_rcp(double d) {
 template <int GR, int R, int GC, int C>
 __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
   constexpr int NVP = GR * R;
+  constexpr int BUF = NVP + 2;
   static_assert(GC * C == NVP && C % 2 == 0 && 32 % GC == 0, "tile grid must cover the padded matrix");
   Scalars* sc = k.sc;
   const int nv = sc->nv, ld = k.ld;
   double* Hm = k.Hm;
-  const int tr = tid / GC, tc = tid % GC;
-  double a[R][C], dg[R];
+  const int tr = tid / GC, tc = tid % GC, lane = tid & 31;
+  double a[R][C];
 #pragma unroll
   for (int i = 0; i < R; i++) {
     const int r = tr + GR * i;
@@ -688,15 +713,28 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
       const int c = 2 * GC * (j / 2) + 2 * tc + (j & 1);
       a[i][j] = (r < nv && c < nv) ? Hm[r * ld + c] : (r == c ? 1.0 : 0.0);
     }
-    dg[i] = (r < nv) ? Hm[r * ld + r] : 1.0;
   }
+  // two broadcast buffers (even / odd pivot): slots 0..NVP-1 the pivot row, slot NVP = 1/d
   double* const buf0 = k.ck;
-  double* const buf1 = k.ck + (NVP + 2);
-  double dinv_mine = fast_rcp(dg[0]);  // 1/d of the pivot this thread's row group publishes next
+  double* const buf1 = k.ck + BUF;
   bool bad = false;
 #pragma unroll
   for (int i = 0; i < R; i++) {
     if (GR * i >= nv) break;  // uniform
+    // diagonal entry of this thread's row in slot i (row r = tr + GR*i, not pivoted yet, so the tile copy is the
+    // exact Schur complement): it sits in the lane with tc == (r/2) % GC at local column 2*(r/(2*GC)) + (r&1);
+    // a compile-time select chain + one shuffle inside the row group fetches it.  Tracked from here on with one
+    // DFMA per pivot so that d and 1/d of the coming pivots never need a run-time register index.
+    double dg;
+    {
+      const int r = tr + GR * i;
+      const int jj = 2 * (r / (2 * GC)) + (r & 1);
+      double mine = 0.0;
+#pragma unroll
+      for (int j = 0; j < C; j++) mine = (j == jj) ? a[i][j] : mine;
+      dg = __shfl_sync(0xffffffffu, mine, (lane & ~(GC - 1)) + ((r / 2) % GC));
+    }
+    double dinv_mine = fast_rcp(dg);  // 1/d of the pivot this thread's row group publishes next
 #pragma unroll 1
     for (int q = 0; q < GR; q++) {
       const int p = GR * i + q;
@@ -707,7 +745,7 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
         for (int j2 = 0; j2 < C / 2; j2++)
           *reinterpret_cast<double2*>(cur + 2 * GC * j2 + 2 * tc) = make_double2(a[i][2 * j2], a[i][2 * j2 + 1]);
         if (tc == 0) {  // same warp as the lane that just stored d into slot p: this store lands after it
-          cur[p] = dg[i] - 1.0;
+          cur[p] = dg - 1.0;
           cur[NVP] = dinv_mine;
         }
       }
@@ -719,11 +757,12 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
       for (int ii = 0; ii < R; ii++) {
         const double c = cur[tr + GR * ii];
         u[ii] = -c * dinv;
-        dg[ii] = fma(u[ii], c, dg[ii]);
+        if (ii == i) dg = fma(u[ii], c, dg);
       }
-      // reciprocal of the next pivot, started before the bulk update so that its latency hides behind the
-      // R*C DFMAs.  Every thread computes it for its own row (no divergence); only the owners' value is used.
-      dinv_mine = fast_rcp((q + 1 < GR) ? dg[i] : dg[(i + 1 < R) ? i + 1 : i]);
+      // reciprocal of the next pivot of this block, started before the bulk update so that its latency hides
+      // behind the R*C DFMAs.  Every thread computes it for its own row (branch-free: a divergent or
+      // warp-selective version puts the reciprocal's latency back on the barrier's critical path).
+      dinv_mine = fast_rcp(dg);
 #pragma unroll
       for (int j2 = 0; j2 < C / 2; j2++) {
         const double2 v = *reinterpret_cast<const double2*>(cur + 2 * GC * j2 + 2 * tc);
@@ -799,7 +838,9 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
   (void)gait;
   Scalars* sc = k.sc;
   const int nv = sc->nv, ns = sc->ns, ld = k.ld, ldT = k.ldT;
-  const double mu_inv = 1.0 / (double)rec[MPC_REC_MU];
+  // 1/mu as the reference forms it: a float (f_block is fpt = float, SolverMPC.cpp:361-372, and A_red goes
+  // through a float temporary, :516), e.g. exactly 2.5 for mu = 0.4f rather than 2.49999996...
+  const double mu_inv = (double)(1.0f / rec[MPC_REC_MU]);
   const double* Hm = k.Hm;
   double* T = k.T;
   const double vtol = 1e-9;
@@ -874,8 +915,9 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       const double t = t1 < t2 ? t1 : t2;
       if (t >= 1e300) { fail = true; break; }  // infeasible (cannot happen: f = 0 is feasible)
       // x += t * Minv (n_p - N r): every row touches <= 2 variables, so z is a combination of at most 2(m+1)
-      // rows of Minv (skipped when p is linearly dependent on W: pure dual step)
-      if (!dependent) {
+      // rows of Minv.  Applied in the (numerically) dependent case too: there z is only round-off-small, not
+      // zero, and x and u must move with the same (r, t) for stationarity x = -Minv (g - N u) to survive.
+      {
         MPC_FOR(i, nv) {
           double acc0 = rp.cz * Hm[rp.iz * ld + i], acc1 = rp.ca * Hm[rp.ia * ld + i];
 #pragma unroll 1
@@ -957,6 +999,39 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       MPC_ONE sc->status = MPC_STATUS_MAX_ITER;
       cx.sync();
       break;
+    }
+  }
+  // ---- polish: x and u are always updated with the same r, so stationarity x = -Minv (g - N u) holds to
+  // round-off whatever the accuracy of the explicitly updated T; what drifts with T is the feasibility
+  // n_a'x = b_a of the working set.  Two passes of iterative refinement with T as the approximate inverse of
+  // S = N'Minv N (du = T (b - N'x); u += du; x += Minv N du) restore it to round-off.
+  const int m = sc->m;
+  if (sc->status == MPC_STATUS_OPTIMAL && m > 0) {
+    for (int pass = 0; pass < 2; pass++) {
+      MPC_FOR(a, m) {
+        const double b = (k.W[a] % 6 == 5) ? -k.ub[k.W[a] / 6] : 0.0;
+        k.w[a] = b - (k.Wca[a] * k.x[k.Wia[a]] + k.Wcz[a] * k.x[k.Wiz[a]]);
+      }
+      cx.sync();
+      MPC_FOR(a, m) {
+        double acc = 0;
+#pragma unroll 1
+        for (int b = 0; b < m; b++) acc += T[b * ldT + a] * k.w[b];
+        k.r[a] = acc;
+      }
+      cx.sync();
+      MPC_FOR(i, nv) {
+        double acc0 = 0, acc1 = 0;
+#pragma unroll 1
+        for (int a = 0; a < m; a++) {
+          const double ra = k.r[a];
+          acc0 += ra * k.Wcz[a] * Hm[k.Wiz[a] * ld + i];
+          acc1 += ra * k.Wca[a] * Hm[k.Wia[a] * ld + i];
+        }
+        k.x[i] += acc0 + acc1;
+      }
+      MPC_FOR(a, m) k.u[a] += k.r[a];
+      cx.sync();
     }
   }
 }

@@ -33,7 +33,7 @@ def emu_lib():
         so = os.path.join(ROOT, "tests", "emu", "libmpc_emu.so")
         core = os.path.join(ROOT, "quadruped_ctrl_b200", "csrc", "mpc_core.h")
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", src, "-o", so])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Wno-unknown-pragmas", "-fPIC", "-shared", src, "-o", so])
         _EMU = ctypes.CDLL(so)
     return _EMU
 

@@ -11,7 +11,19 @@
 
 #include "../../quadruped_ctrl_b200/csrc/mpc_core.h"
 
+static std::vector<double> g_dbg_u, g_dbg_minv;
+static std::vector<int> g_dbg_W;
+static int g_dbg_nv = 0, g_dbg_m = 0;
+
 extern "C" {
+
+// debugging aid: working set, duals and inverse of the LAST problem solved
+int emu_debug_last(int* W, double* u, double* minv, int* nv) {
+  for (int i = 0; i < g_dbg_m; i++) { W[i] = g_dbg_W[i]; u[i] = g_dbg_u[i]; }
+  for (size_t i = 0; i < g_dbg_minv.size(); i++) minv[i] = g_dbg_minv[i];
+  *nv = g_dbg_nv;
+  return g_dbg_m;
+}
 
 // Runs `batch` records through the kernel body with one emulated thread.
 //   nv_cap / m_cap <= 0 -> worst case (12h).  H_out/g_out (optional): the reduced QP
@@ -46,6 +58,10 @@ int emu_solve_batch(const void* records, int batch, int h, int nv_cap, int m_cap
         active_set(cx, rec, gait, k, max_iter);
       }
     }
+    g_dbg_m = k.sc->m; g_dbg_nv = k.sc->nv;
+    g_dbg_W.assign(k.W, k.W + g_dbg_m); g_dbg_u.assign(k.u, k.u + g_dbg_m);
+    g_dbg_minv.resize((size_t)g_dbg_nv * g_dbg_nv);
+    for (int i = 0; i < g_dbg_nv; i++) for (int j = 0; j < g_dbg_nv; j++) g_dbg_minv[(size_t)i * g_dbg_nv + j] = k.Hm[i * k.ld + j];
     int32_t st = 0;
     scatter(cx, k, forces + 12 * b, solution ? solution + (size_t)NU * b : nullptr, &st);
     if (info) {

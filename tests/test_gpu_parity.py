@@ -4,7 +4,7 @@ Tolerances (north_star): first-step 12 forces within 1e-4 relative of the refere
 The reference assembles the QP in fp32; its own rounding cloud around the exact (fp64) answer is
 measured here as |oracle32 - oracle64| and reported beside the GPU numbers.  The GPU assembles
 in fp64, so it is compared
-  * with oracle64 (reference qpOASES on the fp64-assembled QP) at 1e-6 on the whole 12h solution,
+  * with oracle64 (reference qpOASES on the fp64-assembled QP) at 1e-9 on the whole 12h solution,
   * with oracle32 (the reference-faithful path) at 1e-4 on the first-step forces for every problem
     whose oracle32 answer is itself within 2e-5 of oracle64 (the well-conditioned set).
 """
@@ -46,7 +46,7 @@ def test_forces_match_oracle(name, batch, oracle, cuda_engine_factory):
     # whole 12h solution against the fp64 truth
     e64 = rel(sol, o64["sol"])
     print("\n[%s] B=%d backend=%s  |gpu-o64| max %.2e  med %.2e" % (name, B, backend, e64[ok64].max(), np.median(e64)))
-    assert e64[ok64].max() < 1e-6
+    assert e64[ok64].max() < 1e-9   # agreement with the reference solver to round-off (fp64 QP)
     # first-step forces against the reference-faithful fp32 path, on its well-conditioned set
     cloud = rel(o32["forces"], o64["forces"])
     e32 = rel(forces.astype(np.float64), o32["forces"])
@@ -98,7 +98,7 @@ def test_golden_fixture(name, cuda_engine_factory):
     forces, sol, status = eng.solve_host(rec, want_solution=True)
     assert (E.status_code(status) == E.STATUS_OPTIMAL).all()
     ok = G[name + "_o64_rc"] == 0
-    assert rel(sol, G[name + "_o64_sol"])[ok].max() < 1e-6
+    assert rel(sol, G[name + "_o64_sol"])[ok].max() < 1e-9
     cloud = rel(G[name + "_o32_sol"][:, :12], G[name + "_o64_sol"][:, :12])
     e32 = rel(forces, G[name + "_o32_sol"][:, :12])
     ok32 = ok & (G[name + "_o32_rc"] == 0)
