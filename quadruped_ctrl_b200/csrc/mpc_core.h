@@ -624,25 +624,47 @@ MPC_HD void invert_spd(const Cx& cx, const Work& k) {
       return;
     }
     const double dinv = 1.0 / d;
-    MPC_FOR(t, ntiles) {
-      int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-      while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
-      while (bi * (bi + 1) / 2 > t) bi--;
-      const int bj = t - bi * (bi + 1) / 2;
-      const int i0 = 4 * bi, j0 = 4 * bj;
-      double u[4], v[4];
+    // two tiles per iteration with all loads issued before the arithmetic: the matrix sits in L2 (catch-all
+    // class), so the pass is bound by outstanding loads per thread
+    for (int t0 = cx.tid; t0 < ntiles; t0 += 2 * cx.nt) {
+      double acc[2][4][4];
+      int ti0[2], tj0[2];
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        u[e] = (i0 + e < nv) ? -ck[i0 + e] * dinv : 0.0;
-        v[e] = (j0 + e < nv) ? ck[j0 + e] : 0.0;
+      for (int s2 = 0; s2 < 2; s2++) {
+        const int t = t0 + s2 * cx.nt;
+        int bi = 0, bj = 0;
+        if (t < ntiles) {
+          bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+          while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
+          while (bi * (bi + 1) / 2 > t) bi--;
+          bj = t - bi * (bi + 1) / 2;
+        }
+        ti0[s2] = (t < ntiles) ? 4 * bi : nv;  // nv: nothing in range
+        tj0[s2] = 4 * bj;
+#pragma unroll
+        for (int di = 0; di < 4; di++)
+#pragma unroll
+          for (int dj = 0; dj < 4; dj++) {
+            const int i = ti0[s2] + di, j = tj0[s2] + dj;
+            acc[s2][di][dj] = (i < nv && j <= i) ? Hm[i * ld + j] : 0.0;
+          }
       }
 #pragma unroll
-      for (int di = 0; di < 4; di++)
+      for (int s2 = 0; s2 < 2; s2++) {
+        double u[4], v[4];
 #pragma unroll
-        for (int dj = 0; dj < 4; dj++) {
-          const int i = i0 + di, j = j0 + dj;
-          if (i < nv && j <= i) Hm[i * ld + j] += u[di] * v[dj];
+        for (int e = 0; e < 4; e++) {
+          u[e] = (ti0[s2] + e < nv) ? -ck[ti0[s2] + e] * dinv : 0.0;
+          v[e] = (tj0[s2] + e < nv) ? ck[tj0[s2] + e] : 0.0;
         }
+#pragma unroll
+        for (int di = 0; di < 4; di++)
+#pragma unroll
+          for (int dj = 0; dj < 4; dj++) {
+            const int i = ti0[s2] + di, j = tj0[s2] + dj;
+            if (i < nv && j <= i) Hm[i * ld + j] = acc[s2][di][dj] + u[di] * v[dj];
+          }
+      }
     }
     cx.sync();
   }
