@@ -66,6 +66,38 @@ size_t mpc_record_stride(int horizon);
 /* Byte offset of the gait table inside a record. */
 size_t mpc_record_gait_offset(int horizon);
 
+/* ------------------------------------------------------------------------
+ * Tick record (SURVEY 8f, rows N1 + N2): the compact per-robot input of one MPC
+ * tick, from which the engine builds the problem record ON THE DEVICE -- the
+ * reference does this on the host in ConvexMPCLocomotion::updateMPCIfNeeded
+ * (ConvexMPCLocomotion.cpp:498-577: reference trajectory), solveDenseMPC
+ * (:592-621: r = pFoot - position, weights, alpha) and
+ * OffsetDurationGait::getMpcTable (Gait.cpp:142-166: contact table).
+ * 68 32-bit words (272 bytes, 16-byte aligned), fp32 unless noted:
+ *   0..2 p   3..5 vWorld   6..9 q(w,x,y,z)   10..12 omegaWorld
+ *   13..24  pFoot[leg*3+axis], WORLD foot positions (not COM-relative)
+ *   25 yaw (seResult.rpy[2])   26 x_drag (x_comp_integral)   27 alpha
+ *   28..39 weights   40..42 I_body   43 mass   44 dtMPC   45 mu   46 f_max
+ *   47 body_height
+ *   48,49 rpy_comp[0..1]           (standing: _roll_des, _pitch_des)
+ *   50    _yaw_des_true            (standing: stand_traj[5])
+ *   51,52 world_position_desired   (standing: stand_traj[0], stand_traj[1])
+ *   53    _yaw_turn_rate   54,55 v_des_world x,y
+ *   56 (int32) 1 when current_gait == 4 (standing trajectory, :515-531)
+ *   57 (int32) gait iteration (_iteration after Gait::setIterations)
+ *   58..61 (int32) offsets[4]   62..65 (int32) durations[4]   66,67 reserved
+ * The gait has `horizon` segments (nIterations == horizonLength upstream).
+ * ---------------------------------------------------------------------- */
+enum {
+  MPC_TICK_P = 0, MPC_TICK_V = 3, MPC_TICK_Q = 6, MPC_TICK_W = 10, MPC_TICK_PFOOT = 13,
+  MPC_TICK_YAW = 25, MPC_TICK_XDRAG = 26, MPC_TICK_ALPHA = 27, MPC_TICK_WEIGHTS = 28,
+  MPC_TICK_IBODY = 40, MPC_TICK_MASS = 43, MPC_TICK_DT = 44, MPC_TICK_MU = 45, MPC_TICK_FMAX = 46,
+  MPC_TICK_HEIGHT = 47, MPC_TICK_RPY_COMP = 48, MPC_TICK_YAW_DES = 50, MPC_TICK_POS_DES = 51,
+  MPC_TICK_YAW_RATE = 53, MPC_TICK_VDES = 54, MPC_TICK_STANDING = 56, MPC_TICK_ITERATION = 57,
+  MPC_TICK_OFFSETS = 58, MPC_TICK_DURATIONS = 62, MPC_TICK_WORDS = 68
+};
+#define MPC_TICK_STRIDE (4 * MPC_TICK_WORDS)
+
 /* Per-problem status word written next to the forces:
  *   bits 0..7   code (MPC_STATUS_*), bits 8..31 working-set iterations taken. */
 enum {
@@ -120,6 +152,19 @@ int mpc_batch_submit_host(mpc_batch_t* eng, int slot, const void* records_host, 
                           int want_solution);
 int mpc_batch_wait_host(mpc_batch_t* eng, int slot, float* forces_host, double* solution_host,
                         int32_t* status_host);
+
+/* Builds problem records from tick records on the device (one thread per robot), asynchronously on
+ * `cuda_stream`.  records_dev [batch * mpc_record_stride(h)].  state_out_dev (optional, [batch*4] fp32)
+ * receives what the reference writes back into its controller state at this point:
+ * world_position_desired x, y after the 0.1 m clamp (ConvexMPCLocomotion.cpp:536-545), the next
+ * x_comp_integral (:636-640) and 0. */
+int mpc_batch_build_records_device(mpc_batch_t* eng, const void* ticks_dev, int batch,
+                                   void* records_dev, float* state_out_dev, void* cuda_stream);
+/* Build + solve in one call: records go to the engine's own device buffer (slot 0) and never
+ * leave the GPU. */
+int mpc_batch_solve_ticks_device(mpc_batch_t* eng, const void* ticks_dev, int batch,
+                                 float* forces_dev, double* solution_dev, int32_t* status_dev,
+                                 float* state_out_dev, void* cuda_stream);
 
 /* Debug / parity entry: assembles the reduced QP only and writes it out.
  *   nvar_dev [batch] int32: reduced variable count nv = 3 * (#stance (step,leg))

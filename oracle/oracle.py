@@ -20,7 +20,8 @@ _LIB = None
 def build(force=False):
     """Compiles liboracle.so and, when /root/reference is present, _ref/libqpoases_ref.so."""
     need = force or not os.path.exists(os.path.join(_HERE, "liboracle.so"))
-    src_t = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("mpc_oracle.cpp", "qp_port.cpp", "Makefile"))
+    src_t = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("mpc_oracle.cpp", "qp_port.cpp", "tick_oracle.cpp",
+                                                                   "Makefile"))
     if not need and os.path.getmtime(os.path.join(_HERE, "liboracle.so")) < src_t:
         need = True
     ref_missing = os.path.isdir("/root/reference/src/qpOASES") and not os.path.exists(
@@ -50,6 +51,9 @@ def lib():
         L.oracle_get_solution.argtypes = [ctypes.c_int]
         L.oracle_get_solution.restype = ctypes.c_double
         L.oracle_configure.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.oracle_build_records.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                           ctypes.c_void_p]
+        L.oracle_build_records.restype = None
         L.oracle_load_qpoases(os.path.join(_HERE, "_ref", "libqpoases_ref.so").encode())
         _LIB = L
     return _LIB
@@ -112,3 +116,16 @@ def solve_batch_parallel(records, horizon, precision=32, backend=None, workers=N
     with mp.get_context("fork").Pool(len(chunks)) as pool:
         parts = pool.map(_worker, [(c, horizon, precision, backend) for c in chunks])
     return np.concatenate(parts, 0)
+
+
+def build_records(ticks, horizon):
+    """ticks: float32-viewable [B, 68] tick records (include/mpc_batch.h).  Returns (records uint8 [B, stride],
+    state_out float32 [B, 4]) as the reference's host code would produce them."""
+    L = lib()
+    ticks = np.ascontiguousarray(ticks).view(np.float32).reshape(-1, 68)
+    B = ticks.shape[0]
+    stride = L.oracle_record_stride(horizon)
+    rec = np.zeros((B, stride), np.uint8)
+    st = np.zeros((B, 4), np.float32)
+    L.oracle_build_records(ticks.ctypes.data, B, horizon, rec.ctypes.data, st.ctypes.data)
+    return rec, st

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "mpc_core.h"
+#include "mpc_ticks.h"
 
 namespace {
 
@@ -114,6 +115,15 @@ __global__ void mpc_classify_kernel(const char* records, unsigned long long stri
   while (c < n_classes - 1 && nv > class_cap[c]) c++;
   const int slot = atomicAdd(&counts[c], 1);
   lists[c * max_batch + slot] = b;
+}
+
+// Tick records -> problem records, one robot per thread (SURVEY 8f N1 + N2; body in mpc_ticks.h).
+__global__ void mpc_build_records_kernel(const float* ticks, int batch, int h, char* records,
+                                         unsigned long long stride, float* state_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  mpc::build_record_from_tick(ticks + (size_t)b * MPC_TICK_WORDS, h, records + stride * b, (size_t)stride,
+                              state_out ? state_out + 4 * (size_t)b : nullptr);
 }
 
 // NT threads per CTA.  R > 0: register-resident inversion with R x C tiles on a GR x GC thread grid (NT == GR*GC,
@@ -622,6 +632,30 @@ int mpc_batch_solve_host(mpc_batch_t* eng, const void* records_host, int batch, 
   int rc = mpc_batch_submit_host(eng, 0, records_host, batch, solution_host != nullptr);
   if (rc) return rc;
   return mpc_batch_wait_host(eng, 0, forces_host, solution_host, status_host);
+}
+
+int mpc_batch_build_records_device(mpc_batch_t* eng, const void* ticks_dev, int batch, void* records_dev,
+                                   float* state_out_dev, void* cuda_stream) {
+  if (!eng) return MPC_E_ARG;
+  if (!ticks_dev || !records_dev || batch < 0 || batch > eng->max_batch || ((uintptr_t)records_dev & 15)) {
+    eng->err = "mpc_batch_build_records_device: bad argument";
+    return MPC_E_ARG;
+  }
+  if (batch == 0) return MPC_OK;
+  CK(cudaSetDevice(eng->device));
+  mpc_build_records_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(
+      (const float*)ticks_dev, batch, eng->h, (char*)records_dev, eng->stride, state_out_dev);
+  eng->launches++;
+  CK(cudaGetLastError());
+  return MPC_OK;
+}
+
+int mpc_batch_solve_ticks_device(mpc_batch_t* eng, const void* ticks_dev, int batch, float* forces_dev,
+                                 double* solution_dev, int32_t* status_dev, float* state_out_dev, void* cuda_stream) {
+  if (!eng) return MPC_E_ARG;
+  int rc = mpc_batch_build_records_device(eng, ticks_dev, batch, eng->s[0].rec_dev, state_out_dev, cuda_stream);
+  if (rc) return rc;
+  return mpc_batch_solve_device(eng, eng->s[0].rec_dev, batch, forces_dev, solution_dev, status_dev, cuda_stream);
 }
 
 int mpc_batch_assemble_device(mpc_batch_t* eng, const void* records_dev, int batch, int32_t* nvar_dev, double* H_dev,

@@ -23,7 +23,7 @@ STATUS_OPTIMAL, STATUS_MAX_ITER, STATUS_BAD_INPUT, STATUS_NOT_PD, STATUS_NO_STAN
 # every symbol include/mpc_batch.h and include/convexMPC_interface.h declare
 BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_create", "mpc_batch_destroy",
                  "mpc_batch_solve_device", "mpc_batch_solve_host", "mpc_batch_submit_host", "mpc_batch_wait_host",
-                 "mpc_batch_assemble_device",
+                 "mpc_batch_assemble_device", "mpc_batch_build_records_device", "mpc_batch_solve_ticks_device",
                  "mpc_batch_set_gather_peers", "mpc_batch_set_max_iterations", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
                  "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
                  "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_class_kernel_ms", "mpc_batch_timing_mark",
@@ -71,6 +71,8 @@ def lib():
     L.mpc_batch_submit_host.argtypes = [vp, i32, vp, i32, i32]
     L.mpc_batch_wait_host.argtypes = [vp, i32, vp, vp, vp]
     L.mpc_batch_assemble_device.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.mpc_batch_build_records_device.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.mpc_batch_solve_ticks_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.mpc_batch_set_gather_peers.argtypes = [vp, ctypes.POINTER(vp), i32, i32]
     L.mpc_batch_set_max_iterations.argtypes = [vp, i32]
     L.mpc_batch_set_timing.argtypes = [vp, i32]
@@ -275,6 +277,39 @@ class MpcBatch:
                                          out_solution.ctypes.data if out_solution is not None else None,
                                          out_status.ctypes.data if out_status is not None else None)
         self._check(rc, "mpc_batch_wait_host")
+
+    def build_records_device(self, ticks, records=None, want_state=True, stream=None):
+        """ticks: cuda tensor [B, 68] of 32-bit words (ticks.pack_ticks).  Builds the problem records on the
+        device.  Returns (records uint8 [B, stride], state_out float32 [B, 4] | None)."""
+        torch = _torch()
+        assert ticks.is_cuda and ticks.is_contiguous() and ticks.element_size() * ticks.shape[1] == 272
+        B = ticks.shape[0]
+        dev = ticks.device
+        if records is None:
+            records = torch.empty((B, self.stride), dtype=torch.uint8, device=dev)
+        state = torch.empty((B, 4), dtype=torch.float32, device=dev) if want_state else None
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = self._L.mpc_batch_build_records_device(self._h, ticks.data_ptr(), B, records.data_ptr(),
+                                                    state.data_ptr() if state is not None else None, st.cuda_stream)
+        self._check(rc, "mpc_batch_build_records_device")
+        return records, state
+
+    def solve_ticks_device(self, ticks, want_solution=False, want_state=True, stream=None):
+        """Build + solve on the device: tick records in, (forces, solution | None, status, state_out | None) out."""
+        torch = _torch()
+        assert ticks.is_cuda and ticks.is_contiguous() and ticks.element_size() * ticks.shape[1] == 272
+        B = ticks.shape[0]
+        dev = ticks.device
+        forces = torch.empty((B, 12), dtype=torch.float32, device=dev)
+        sol = torch.empty((B, 12 * self.horizon), dtype=torch.float64, device=dev) if want_solution else None
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        state = torch.empty((B, 4), dtype=torch.float32, device=dev) if want_state else None
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = self._L.mpc_batch_solve_ticks_device(self._h, ticks.data_ptr(), B, forces.data_ptr(),
+                                                  sol.data_ptr() if sol is not None else None, status.data_ptr(),
+                                                  state.data_ptr() if state is not None else None, st.cuda_stream)
+        self._check(rc, "mpc_batch_solve_ticks_device")
+        return forces, sol, status, state
 
     def assemble_device(self, records, stream=None):
         """Parity entry: the reduced QP only.  Returns (nv [B] int32, H [B,12h,12h] f64, g [B,12h] f64)."""

@@ -32,8 +32,10 @@ def emu_lib():
         src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
         so = os.path.join(ROOT, "tests", "emu", "libmpc_emu.so")
         core = os.path.join(ROOT, "quadruped_ctrl_b200", "csrc", "mpc_core.h")
-        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Wno-unknown-pragmas", "-fPIC", "-shared", src, "-o", so])
+        ticks = os.path.join(ROOT, "quadruped_ctrl_b200", "csrc", "mpc_ticks.h")
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core),
+                                                                 os.path.getmtime(ticks)):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Wno-unknown-pragmas", "-ffp-contract=off", "-fPIC", "-shared", src, "-o", so])
         _EMU = ctypes.CDLL(so)
     return _EMU
 
@@ -54,3 +56,16 @@ def emu_solve(rec, h, nv_cap=0, m_cap=0, want_qp=False, max_iter=100000):
                            vp(g.ctypes.data) if want_qp else None)
     assert rc == 0, rc
     return dict(forces=f, sol=sol, nv=info[:, 0], m=info[:, 1], iters=info[:, 2], status=info[:, 3], H=H, g=g)
+
+
+def emu_build_records(ticks, h):
+    """Host build of the device-side tick -> record builder."""
+    from quadruped_ctrl_b200 import records as R
+    L = emu_lib()
+    ticks = np.ascontiguousarray(ticks).view(np.float32).reshape(-1, 68)
+    B = ticks.shape[0]
+    rec = np.full((B, R.record_stride(h)), 0xCD, np.uint8)
+    st = np.zeros((B, 4), np.float32)
+    L.emu_build_records(ctypes.c_void_p(ticks.ctypes.data), B, h, ctypes.c_void_p(rec.ctypes.data),
+                        ctypes.c_void_p(st.ctypes.data))
+    return rec, st

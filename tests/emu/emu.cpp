@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../quadruped_ctrl_b200/csrc/mpc_core.h"
+#include "../../quadruped_ctrl_b200/csrc/mpc_ticks.h"
 
 static std::vector<double> g_dbg_u, g_dbg_minv;
 static std::vector<int> g_dbg_W;
@@ -72,6 +73,14 @@ int emu_solve_batch(const void* records, int batch, int h, int nv_cap, int m_cap
     }
   }
   return 0;
+}
+
+// Host build of the device-side record builder (csrc/mpc_ticks.h), one robot at a time.
+void emu_build_records(const float* ticks, int batch, int h, unsigned char* records, float* state_out) {
+  const size_t stride = ((size_t)(4 * (MPC_REC_TRAJ + 12 * h) + 4 * h) + 15) / 16 * 16;
+  for (int b = 0; b < batch; b++)
+    mpc::build_record_from_tick(ticks + (size_t)b * MPC_TICK_WORDS, h, (char*)records + stride * b, stride,
+                                state_out ? state_out + 4 * b : nullptr);
 }
 
 }  // extern "C"

@@ -230,3 +230,27 @@ def test_pipelined_host_entry_matches_synchronous(cuda_engine_factory):
     got.append((f, s, st))
     for (rf, rs, rst), (gf, gs, gst) in zip(ref, got):
         assert np.array_equal(rf, gf) and np.array_equal(rs, gs) and np.array_equal(rst, gst)
+
+
+def test_device_record_builder_is_byte_exact(oracle, cuda_engine_factory):
+    """SURVEY 8f N1 + N2: records built on the device from tick records equal the oracle's restatement of the
+    reference's host code (ConvexMPCLocomotion.cpp:498-640, Gait.cpp:142-166) byte for byte, and solving the
+    ticks equals solving those records."""
+    from quadruped_ctrl_b200 import ticks as T
+    for h, mixed, B in ((10, False, 1000), (20, True, 300), (16, True, 300)):
+        tk = T.synth_ticks(B, h, 11 + h, mixed_gaits=mixed)
+        rec_o, st_o = oracle.build_records(tk, h)
+        eng = cuda_engine_factory(h, B)
+        d_tk = torch.from_numpy(tk).cuda()
+        rec_d, st_d = eng.build_records_device(d_tk)
+        torch.cuda.synchronize()
+        assert np.array_equal(rec_d.cpu().numpy(), rec_o)
+        assert np.array_equal(st_d.cpu().numpy(), st_o)
+        f1, s1, c1, st2 = eng.solve_ticks_device(d_tk, want_solution=True)
+        f2, s2, c2 = eng.solve_device(torch.from_numpy(rec_o).cuda(), want_solution=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(f1.cpu().numpy(), f2.cpu().numpy())
+        assert np.array_equal(s1.cpu().numpy(), s2.cpu().numpy())
+        assert np.array_equal(c1.cpu().numpy(), c2.cpu().numpy())
+        assert np.array_equal(st2.cpu().numpy(), st_o)
+        assert (E.status_code(c1.cpu().numpy()) == E.STATUS_OPTIMAL).all()
