@@ -186,11 +186,17 @@ def run_ours(args):
     forces = torch.empty((B, 12), dtype=torch.float32, device=dev)
     status = torch.empty((B,), dtype=torch.int32, device=dev)
     gathered = torch.empty((world * B, 12), dtype=torch.float32, device=dev) if world > 1 else None
+    peer = world > 1 and args.gather == "peer"
+    if peer:  # fused: the solve kernel stores every force straight into all ranks' gather buffers over NVLink
+        gathered = eng.setup_peer_gather(world * B, rank * B)
 
     def step(i):
         eng.solve_device(dev_sets[i % n_sets], forces=forces, status=status)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, forces)
+            if peer:
+                eng.gather_sync()  # device-side flag exchange over NVLink: everybody's stores have landed
+            else:
+                dist.all_gather_into_tensor(gathered, forces)
 
     def barrier():
         if world > 1:
@@ -276,7 +282,9 @@ def run_ours(args):
                                    "friction-cone rows per step, seed 1234+" % (B, h),
                        "l2": "inputs rotate over %d distinct record sets (%.0f MB > 126 MB L2), no flush needed"
                              % (n_sets, n_sets * B * stride / 1e6),
-                       "collective": "all_gather_into_tensor of [N*B,12] fp32 forces" if world > 1 else "none (N=1)",
+                       "collective": ("none (N=1)" if world == 1 else
+                                      "peer stores from the solve kernel + device-side flag barrier (no NCCL on the path)" if peer else
+                                      "all_gather_into_tensor of [N*B,12] fp32 forces"),
                        "classes": classes},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * stride,
                     "d2h_bytes_per_step": B * 48 + B * 4,
@@ -309,6 +317,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
+                    help="N>1: NCCL all-gather of the forces (default) or the kernel's fused peer-store epilogue")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -183,6 +183,23 @@ int mpc_batch_assemble_device(mpc_batch_t* eng, const void* records_dev, int bat
 int mpc_batch_set_gather_peers(mpc_batch_t* eng, float* const* peers, int n_peers,
                                int rank_offset);
 
+/* The same over CUDA IPC for one-process-per-GPU jobs:
+ *   1. every rank: gather_alloc -> its gather buffer [world_batch*12] fp32 + the 64-byte IPC handle;
+ *   2. the ranks exchange the handles (any transport, e.g. torch.distributed.all_gather);
+ *   3. every rank: gather_connect(handles[world][64], world, rank, rank_offset) opens the peers'
+ *      buffers and arms the epilogue (rank_offset = first global row of this rank's shard).
+ * After a solve on every rank and one cross-rank barrier, every rank's buffer (gather_buffer)
+ * holds the forces of the whole batch; no separate all-gather runs. */
+int mpc_batch_gather_alloc(mpc_batch_t* eng, int world_batch, void* ipc_handle_out);
+int mpc_batch_gather_connect(mpc_batch_t* eng, const void* ipc_handles, int world, int rank,
+                             int rank_offset);
+void* mpc_batch_gather_buffer(mpc_batch_t* eng);
+/* The cross-rank barrier of the fused gather, on the device: queued on `cuda_stream` after a solve,
+ * it tells every peer (a release store into its flag word over NVLink) that this rank's rows have
+ * landed and waits until every peer has said the same here.  Work queued behind it on the stream
+ * sees the complete gather buffer.  Every rank must call it once per solve. */
+int mpc_batch_gather_sync(mpc_batch_t* eng, void* cuda_stream);
+
 /* Iteration cap of the active-set loop (working-set additions); default 4000.
  * The reference caps qpOASES at nWSR = 100 (SolverMPC.cpp:435) and returns stale
  * memory beyond it; this engine reports MPC_STATUS_MAX_ITER instead. */

@@ -342,9 +342,7 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
   const int h = k.h;
   Scalars* sc = k.sc;
   double* B = k.M;          // 13x12   (the M region is free until the C_a are final)
-  double* t1 = B + 156;     // A B
-  double* t2 = t1 + 156;    // A^2 B
-  double* scr = t2 + 156;   // cos(yaw), sin(yaw)
+  double* scr = B + 156;    // cos(yaw), sin(yaw)
   double* C0 = k.C;
   double* C1 = C0 + 156;
   double* C2 = C1 + 156;
@@ -456,19 +454,17 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
   MPC_STAMP(k, cx, 9);
   if (sc->status != MPC_STATUS_OPTIMAL) return;
   const double dt = (double)rec[MPC_REC_DT];
-  // ---- P3: A B, A^2 B, A x0, A^2 x0 ----
+  // ---- P3: exact discretisation B_d = dt B + dt^2/2 AB + dt^3/6 A^2 B (c2qp, SolverMPC.cpp:87-101), straight
+  //          from B_c (A B and A^2 B have at most three terms per entry), and A x0, A^2 x0 ----
   MPC_FOR(e, 156) {
     const int i = e / 12, j = e - 12 * i;
-    t1[e] = apply_A(B, 12, i, j, yc, ys, xd);
-    t2[e] = apply_A2(B, 12, i, j, xd);
+    C0[e] = dt * B[e] + (dt * dt / 2.0) * apply_A(B, 12, i, j, yc, ys, xd) +
+            (dt * dt * dt / 6.0) * apply_A2(B, 12, i, j, xd);
   }
   MPC_FOR(e, 13) {
     Ax0[e] = apply_A(x0, 1, e, 0, yc, ys, xd);
     A2x0[e] = apply_A2(x0, 1, e, 0, xd);
   }
-  cx.sync();
-  // ---- P5: exact discretisation B_d = dt B + dt^2/2 AB + dt^3/6 A^2 B (c2qp, SolverMPC.cpp:87-101) ----
-  MPC_FOR(e, 156) C0[e] = dt * B[e] + (dt * dt / 2.0) * t1[e] + (dt * dt * dt / 6.0) * t2[e];
   cx.sync();
   // ---- P7: Phi_k = A_d^k B_d = C0 + k C1 + k^2 C2 with C1 = dt A B_d, C2 = dt^2/2 A^2 B_d;
   //          weighted tracking error q_e[r] = Q (A_d^{r+1} x0 - x_d[r]) (SolverMPC.cpp:335-347,399) ----
@@ -499,14 +495,15 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
     mom[e] = acc;
   }
   // power sums P_e(n) = sum_{q=0..n} q^e, e = 0..4, n = 0..h-1: exact integers (< 2^53 for h <= 36)
-  MPC_FOR(n, h) {
-    long long p1 = 0, p2 = 0, p3 = 0, p4 = 0;
-#pragma unroll 1
-    for (long long q = 1; q <= n; q++) { p1 += q; p2 += q * q; p3 += q * q * q; p4 += q * q * q * q; }
+  MPC_FOR(n, h) {  // closed forms in integer arithmetic (n <= 35: every product below fits in 32 bits)
+    const int n1 = n * (n + 1);
+    const int p1 = n1 / 2;
+    const int p2 = n1 * (2 * n + 1) / 6;
+    const int p4 = (n1 * (2 * n + 1)) * (3 * n * n + 3 * n - 1) / 30;  // <= 35*36*71*3779 = 338,069,340
     k.psum[5 * n + 0] = (double)(n + 1);
     k.psum[5 * n + 1] = (double)p1;
     k.psum[5 * n + 2] = (double)p2;
-    k.psum[5 * n + 3] = (double)p3;
+    k.psum[5 * n + 3] = (double)p1 * (double)p1;
     k.psum[5 * n + 4] = (double)p4;
   }
   cx.sync();

@@ -126,6 +126,25 @@ __global__ void mpc_build_records_kernel(const float* ticks, int batch, int h, c
                               state_out ? state_out + 4 * (size_t)b : nullptr);
 }
 
+// Device-side barrier of the fused gather: after this rank's solve kernels have completed (stream order), tell every
+// peer "my rows of epoch E have landed" through its flag word, then wait until every peer has said the same here.
+__global__ void mpc_gather_signal_kernel(unsigned* const* peer_flags, int world, int rank, unsigned epoch) {
+  const int q = threadIdx.x;
+  if (q < world && peer_flags[q]) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[q] + rank), "r"(epoch) : "memory");
+  }
+}
+__global__ void mpc_gather_wait_kernel(const unsigned* my_flags, int world, unsigned epoch) {
+  const int q = threadIdx.x;
+  if (q < world) {
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + q) : "memory");
+    } while ((int)(v - epoch) < 0);
+  }
+}
+
 // NT threads per CTA.  R > 0: register-resident inversion with R x C tiles on a GR x GC thread grid (NT == GR*GC,
 // padded size GR*R == GC*C).  R == 0: the generic shared/global-memory sweep, used by the catch-all class whose
 // matrix does not fit in the register file of one SM.
@@ -274,7 +293,11 @@ struct mpc_batch {
   int max_iter = 4000;
   float* peers[kMaxPeers] = {nullptr};
   int n_peers = 0, rank_offset = 0;
-  float* gather_buf = nullptr;
+  float* gather_buf = nullptr;   // [gather_rows*12] fp32 forces, then kMaxPeers flag words (one per rank)
+  int gather_rows = 0;
+  int gather_world = 0, gather_rank = 0;
+  unsigned gather_epoch = 0;
+  unsigned** peer_flags_dev = nullptr;
   long long* phase_clk = nullptr;
   int ctas_per_sm_limit = 0;
   void* peer_open[kMaxPeers] = {nullptr};
@@ -536,6 +559,7 @@ void mpc_batch_destroy(mpc_batch_t* eng) {
   for (int q = 0; q < kMaxPeers; q++)
     if (eng->peer_open[q]) cudaIpcCloseMemHandle(eng->peer_open[q]);
   cudaFree(eng->gather_buf);
+  cudaFree(eng->peer_flags_dev);
   for (int q = 0; q < 2; q++) {
     mpc_batch::Slot& S = eng->s[q];
     cudaFree(S.rec_dev);
@@ -677,6 +701,64 @@ int mpc_batch_set_gather_peers(mpc_batch_t* eng, float* const* peers, int n_peer
   eng->rank_offset = rank_offset;
   return MPC_OK;
 }
+
+int mpc_batch_gather_alloc(mpc_batch_t* eng, int world_batch, void* ipc_handle_out) {
+  if (!eng || world_batch < 1 || !ipc_handle_out) return MPC_E_ARG;
+  CK(cudaSetDevice(eng->device));
+  if (eng->gather_buf) CK(cudaFree(eng->gather_buf));
+  eng->gather_buf = nullptr;
+  const size_t bytes = (size_t)world_batch * 12 * sizeof(float) + kMaxPeers * sizeof(unsigned);
+  CK(cudaMalloc(&eng->gather_buf, bytes));
+  CK(cudaMemset(eng->gather_buf, 0, bytes));
+  eng->gather_rows = world_batch;
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, eng->gather_buf));
+  static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  return MPC_OK;
+}
+
+int mpc_batch_gather_connect(mpc_batch_t* eng, const void* ipc_handles, int world, int rank, int rank_offset) {
+  if (!eng || !ipc_handles || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !eng->gather_buf)
+    return MPC_E_ARG;
+  CK(cudaSetDevice(eng->device));
+  float* peers[kMaxPeers] = {nullptr};
+  for (int q = 0; q < world; q++) {
+    if (q == rank) {
+      peers[q] = eng->gather_buf;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)ipc_handles + 64 * (size_t)q, 64);
+    void* ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    eng->peer_open[q] = ptr;
+    peers[q] = (float*)ptr;
+  }
+  unsigned* flags[kMaxPeers] = {nullptr};
+  for (int q = 0; q < world; q++) flags[q] = (unsigned*)(peers[q] + (size_t)eng->gather_rows * 12);
+  if (!eng->peer_flags_dev) CK(cudaMalloc(&eng->peer_flags_dev, sizeof(flags)));
+  CK(cudaMemcpy(eng->peer_flags_dev, flags, sizeof(flags), cudaMemcpyHostToDevice));
+  eng->gather_world = world;
+  eng->gather_rank = rank;
+  eng->gather_epoch = 0;
+  return mpc_batch_set_gather_peers(eng, peers, world, rank_offset);
+}
+
+int mpc_batch_gather_sync(mpc_batch_t* eng, void* cuda_stream) {
+  if (!eng || !eng->peer_flags_dev || eng->gather_world < 1) return MPC_E_ARG;
+  CK(cudaSetDevice(eng->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const unsigned epoch = ++eng->gather_epoch;
+  mpc_gather_signal_kernel<<<1, 32, 0, st>>>(eng->peer_flags_dev, eng->gather_world, eng->gather_rank, epoch);
+  mpc_gather_wait_kernel<<<1, 32, 0, st>>>((const unsigned*)(eng->gather_buf + (size_t)eng->gather_rows * 12),
+                                           eng->gather_world, epoch);
+  eng->launches += 2;
+  CK(cudaGetLastError());
+  return MPC_OK;
+}
+
+void* mpc_batch_gather_buffer(mpc_batch_t* eng) { return eng ? eng->gather_buf : nullptr; }
 
 int mpc_batch_set_max_iterations(mpc_batch_t* eng, int max_iter) {
   if (!eng || max_iter < 1) return MPC_E_ARG;

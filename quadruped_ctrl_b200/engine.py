@@ -24,7 +24,8 @@ STATUS_OPTIMAL, STATUS_MAX_ITER, STATUS_BAD_INPUT, STATUS_NOT_PD, STATUS_NO_STAN
 BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_create", "mpc_batch_destroy",
                  "mpc_batch_solve_device", "mpc_batch_solve_host", "mpc_batch_submit_host", "mpc_batch_wait_host",
                  "mpc_batch_assemble_device", "mpc_batch_build_records_device", "mpc_batch_solve_ticks_device",
-                 "mpc_batch_set_gather_peers", "mpc_batch_set_max_iterations", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
+                 "mpc_batch_set_gather_peers", "mpc_batch_gather_alloc", "mpc_batch_gather_connect",
+                 "mpc_batch_gather_buffer", "mpc_batch_gather_sync", "mpc_batch_set_max_iterations", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
                  "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
                  "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_class_kernel_ms", "mpc_batch_timing_mark",
                  "mpc_batch_timing_collect", "mpc_batch_host_buffers",
@@ -74,6 +75,11 @@ def lib():
     L.mpc_batch_build_records_device.argtypes = [vp, vp, i32, vp, vp, vp]
     L.mpc_batch_solve_ticks_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.mpc_batch_set_gather_peers.argtypes = [vp, ctypes.POINTER(vp), i32, i32]
+    L.mpc_batch_gather_alloc.argtypes = [vp, i32, vp]
+    L.mpc_batch_gather_connect.argtypes = [vp, vp, i32, i32, i32]
+    L.mpc_batch_gather_sync.argtypes = [vp, vp]
+    L.mpc_batch_gather_buffer.argtypes = [vp]
+    L.mpc_batch_gather_buffer.restype = vp
     L.mpc_batch_set_max_iterations.argtypes = [vp, i32]
     L.mpc_batch_set_timing.argtypes = [vp, i32]
     L.mpc_batch_set_timed_class.argtypes = [vp, i32]
@@ -220,6 +226,36 @@ class MpcBatch:
         n = len(peer_ptrs)
         arr = (ctypes.c_void_p * max(n, 1))(*[ctypes.c_void_p(int(p)) for p in peer_ptrs])
         self._check(self._L.mpc_batch_set_gather_peers(self._h, arr, n, int(rank_offset)), "set_gather_peers")
+
+    def setup_peer_gather(self, world_batch, rank_offset, group=None):
+        """Fused shard-and-gather: allocates this rank's [world_batch, 12] gather buffer, exchanges CUDA IPC
+        handles over torch.distributed and arms the solve kernel's peer-store epilogue.  Returns the local
+        gather buffer as a cuda tensor (valid after a solve on every rank + one barrier)."""
+        torch = _torch()
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        handle = (ctypes.c_char * 64)()
+        self._check(self._L.mpc_batch_gather_alloc(self._h, int(world_batch), ctypes.addressof(handle)),
+                    "mpc_batch_gather_alloc")
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).cuda(self.device)
+        allh = torch.empty((world, 64), dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        blob = allh.cpu().numpy().tobytes()
+        self._check(self._L.mpc_batch_gather_connect(self._h, blob, world, rank, int(rank_offset)),
+                    "mpc_batch_gather_connect")
+        ptr = self._L.mpc_batch_gather_buffer(self._h)
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (int(world_batch), 12), "typestr": "<f4", "data": (int(ptr), False),
+                                        "version": 2, "strides": None}
+        self._gather_keepalive = _Buf()
+        return torch.as_tensor(self._gather_keepalive, device=torch.device("cuda", self.device))
+
+    def gather_sync(self, stream=None):
+        """Device-side cross-rank barrier of the fused gather, queued on `stream` (default: current)."""
+        torch = _torch()
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self._check(self._L.mpc_batch_gather_sync(self._h, st.cuda_stream), "mpc_batch_gather_sync")
 
     # ---- solves ---------------------------------------------------------------------------
     def solve_device(self, records, forces=None, solution=None, status=None, want_solution=False,

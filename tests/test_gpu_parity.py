@@ -254,3 +254,16 @@ def test_device_record_builder_is_byte_exact(oracle, cuda_engine_factory):
         assert np.array_equal(c1.cpu().numpy(), c2.cpu().numpy())
         assert np.array_equal(st2.cpu().numpy(), st_o)
         assert (E.status_code(c1.cpu().numpy()) == E.STATUS_OPTIMAL).all()
+
+
+def test_fused_peer_gather_two_gpus():
+    """N>1 on real GPUs: the solve kernel's peer-store epilogue + device-side flag barrier fill every rank's gather
+    buffer with exactly what an NCCL all-gather returns (tests/gpu_peer_gather_check.py under torchrun)."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu_peer_gather_check.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", script], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
