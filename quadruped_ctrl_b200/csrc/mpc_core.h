@@ -763,7 +763,10 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
 #pragma unroll
         for (int j2 = 0; j2 < C / 2; j2++)
           *reinterpret_cast<double2*>(cur + 2 * GC * j2 + 2 * tc) = make_double2(a[i][2 * j2], a[i][2 * j2 + 1]);
-        if (tc == 0) {  // same warp as the lane that just stored d into slot p: this store lands after it
+        // slot p was just written (with d) by the lane of this row group that holds column p: the SAME lane
+        // overwrites it with d-1 (program order of one thread, no cross-lane ordering needed); every lane of
+        // the group tracks the same dg
+        if (tc == ((p >> 1) % GC)) {
           cur[p] = dg - 1.0;
           cur[NVP] = dinv_mine;
         }
@@ -933,6 +936,7 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       const double t1 = (tidx == 0x7fffffff) ? 1e300 : tbest;
       const double t = t1 < t2 ? t1 : t2;
       if (t >= 1e300) { fail = true; break; }  // infeasible (cannot happen: f = 0 is feasible)
+      cx.sync();  // every thread has read x (slack of p) before anybody moves x
       // x += t * Minv (n_p - N r): every row touches <= 2 variables, so z is a combination of at most 2(m+1)
       // rows of Minv.  Applied in the (numerically) dependent case too: there z is only round-off-small, not
       // zero, and x and u must move with the same (r, t) for stationarity x = -Minv (g - N u) to survive.
