@@ -76,7 +76,7 @@ struct Scalars {
   double sp, t1, t2, t, up, vnp, znp, dreg;
 };
 
-constexpr int kAsmDoubles(int h) { return 3 * 156 + 9 * 144 + 39 + 12 * h + 5 * h; }
+constexpr int kAsmDoubles(int h) { return 3 * 156 + 6 * 144 + 39 + 12 * h + 5 * h; }
 constexpr int kRedDoubles = 40;
 
 inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -157,7 +157,7 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
   double* un = (double*)(fast + L.off_union);
   k.C = un;
   k.M = un + 3 * 156;
-  k.xs = k.M + 9 * 144;
+  k.xs = k.M + 6 * 144;
   k.qe = k.xs + 39;
   k.psum = k.qe + 12 * L.h;
   double* gi = un;
@@ -507,7 +507,7 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
     k.psum[5 * n + 4] = (double)p4;
   }
   cx.sync();
-  // ---- P9: reduced gradient g_v = 2 sum_a C_a[:,c]' mom[a][j] (SolverMPC.cpp:399), and the nine tables
+  // ---- P9: reduced gradient g_v = 2 sum_a C_a[:,c]' mom[a][j] (SolverMPC.cpp:399), and the tables
   //          M_ab = C_a' Q C_b (12x12).  Row supports: C0 rows 0..11, C1 rows {0..5,11}, C2 row {5}.
   //          M overlays B,t1,t2,scr, which are dead: the barrier above is the last point anything reads them. ----
   const int nv = sc->nv, ns = sc->ns;
@@ -526,11 +526,12 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
     }
     k.g[v] = 2.0 * (acc0 + acc1);
   }
-  // one thread per (table, row): 12 independent accumulators, each weighted C_a entry loaded once
-  MPC_FOR(e, 9 * 12) {
-    const int ab = e / 12, i = e - 12 * ab;
-    const int a = ab / 3, b = ab - 3 * a;
-    if (a < na && b < na) {
+  // six tables M_ab, a <= b (M_ba = M_ab'); one thread per (table, row): 12 independent accumulators, each
+  // weighted C_a entry loaded once
+  MPC_FOR(e, 6 * 12) {
+    const int tb = e / 12, i = e - 12 * tb;
+    const int a = tb < 3 ? 0 : (tb < 5 ? 1 : 2), b = tb < 3 ? tb : (tb < 5 ? tb - 2 : 2);
+    if (b < na) {  // a <= b
       const double* Ca = C0 + 156 * a;
       const double* Cb = C0 + 156 * b;
       const unsigned mask = rowmask[a] & rowmask[b];
@@ -545,7 +546,7 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
         }
       }
 #pragma unroll
-      for (int j = 0; j < 12; j++) k.M[ab * 144 + i * 12 + j] = acc[j];
+      for (int j = 0; j < 12; j++) k.M[tb * 144 + i * 12 + j] = acc[j];
     }
   }
   cx.sync();
@@ -576,7 +577,12 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
         const int ci = la * 3 + ax, cj = lb * 3 + bx;
         double acc = 0;
         for (int pa = 0; pa < na; pa++)
-          for (int pb = 0; pb < na; pb++) acc += s[pa][pb] * k.M[(pa * 3 + pb) * 144 + ci * 12 + cj];
+          for (int pb = 0; pb < na; pb++) {
+            // table of (min, max): 00 01 02 11 12 22 -> 0..5; the lower-index pair is stored, the other is its transpose
+            const int lo = pa < pb ? pa : pb, hi = pa < pb ? pb : pa;
+            const int tb = lo * 3 - (lo * (lo - 1)) / 2 + (hi - lo);
+            acc += s[pa][pb] * k.M[tb * 144 + (pa <= pb ? ci * 12 + cj : cj * 12 + ci)];
+          }
         double val = 2.0 * acc;
         if (a == b && ax == bx) val += 2.0 * alpha;
         k.Hm[(3 * a + ax) * k.ld + 3 * b + bx] = val;
@@ -714,11 +720,21 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return x;
 }
 
+// Symmetry: the tile (row slot i, column-pair slot j2) of every thread lies in the GR x 2GC super-block
+// rows [GR*i, GR*i+GR) x columns [2GC*j2, 2GC*j2+2GC).  Super-blocks strictly above the diagonal are never
+// loaded, updated or stored (a compile-time predicate, the same for all threads): their entries are the
+// transposes of entries in kept blocks.  For R = 4 that is 20 instead of 32 DFMAs per pivot.  The part of pivot
+// row p that falls into skipped blocks is published from column p instead (other threads, still compile-time
+// register indices).
+template <int GR, int GC>
+__host__ __device__ constexpr bool sweep_block_kept(int i, int j2) { return 2 * GC * j2 <= GR * i + GR - 1; }
+
 template <int GR, int R, int GC, int C>
 __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
   constexpr int NVP = GR * R;
   constexpr int BUF = NVP + 2;
   static_assert(GC * C == NVP && C % 2 == 0 && 32 % GC == 0, "tile grid must cover the padded matrix");
+  static_assert((2 * GC) % GR == 0 || GR % (2 * GC) == 0, "super-block indices of a row slot must be compile-time");
   Scalars* sc = k.sc;
   const int nv = sc->nv, ld = k.ld;
   double* Hm = k.Hm;
@@ -729,6 +745,7 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
     const int r = tr + GR * i;
 #pragma unroll
     for (int j = 0; j < C; j++) {
+      if (!sweep_block_kept<GR, GC>(i, j / 2)) continue;
       const int c = 2 * GC * (j / 2) + 2 * tc + (j & 1);
       a[i][j] = (r < nv && c < nv) ? Hm[r * ld + c] : (r == c ? 1.0 : 0.0);
     }
@@ -741,57 +758,72 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
   for (int i = 0; i < R; i++) {
     if (GR * i >= nv) break;  // uniform
     // diagonal entry of this thread's row in slot i (row r = tr + GR*i, not pivoted yet, so the tile copy is the
-    // exact Schur complement): it sits in the lane with tc == (r/2) % GC at local column 2*(r/(2*GC)) + (r&1);
-    // a compile-time select chain + one shuffle inside the row group fetches it.  Tracked from here on with one
-    // DFMA per pivot so that d and 1/d of the coming pivots never need a run-time register index.
+    // exact Schur complement): it sits in the lane with tc == (r/2) % GC at local column 2*(r/(2*GC)) + (r&1)
+    // (a kept, diagonal super-block); a compile-time select chain + one shuffle inside the row group fetches
+    // it.  Tracked from here on with one DFMA per pivot so that d and 1/d of the coming pivots never need a
+    // run-time register index.
     double dg;
     {
       const int r = tr + GR * i;
       const int jj = 2 * (r / (2 * GC)) + (r & 1);
       double mine = 0.0;
 #pragma unroll
-      for (int j = 0; j < C; j++) mine = (j == jj) ? a[i][j] : mine;
+      for (int j = 0; j < C; j++)
+        if (sweep_block_kept<GR, GC>(i, j / 2)) mine = (j == jj) ? a[i][j] : mine;
       dg = __shfl_sync(0xffffffffu, mine, (lane & ~(GC - 1)) + ((r / 2) % GC));
     }
     double dinv_mine = fast_rcp(dg);  // 1/d of the pivot this thread's row group publishes next
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int jc = (GR * i) / (2 * GC);  // column super-block of the pivots of this row slot (compile-time)
 #pragma unroll 1
-    for (int q = 0; q < GR; q++) {
-      const int p = GR * i + q;
-      if (p >= nv) break;  // uniform
-      double* const cur = (q & 1) ? buf1 : buf0;  // GR is even: parity of p == parity of q
-      if (tr == q) {  // publish row p: compile-time registers a[i][*]
+    for (int q0 = 0; q0 < GR; q0 += 2) {
 #pragma unroll
-        for (int j2 = 0; j2 < C / 2; j2++)
-          *reinterpret_cast<double2*>(cur + 2 * GC * j2 + 2 * tc) = make_double2(a[i][2 * j2], a[i][2 * j2 + 1]);
-        // slot p was just written (with d) by the lane of this row group that holds column p: the SAME lane
-        // overwrites it with d-1 (program order of one thread, no cross-lane ordering needed); every lane of
-        // the group tracks the same dg
-        if (tc == ((p >> 1) % GC)) {
-          cur[p] = dg - 1.0;
-          cur[NVP] = dinv_mine;
+      for (int e = 0; e < 2; e++) {  // e = parity of q = parity of p: which buffer, which half of a column pair
+        const int q = q0 + e;
+        const int p = GR * i + q;
+        if (p >= nv) break;  // uniform (and p+1 >= nv follows)
+        double* const cur = e ? buf1 : buf0;
+        if (tr == q) {  // row owners: the part of row p inside kept super-blocks, compile-time registers
+#pragma unroll
+          for (int j2 = 0; j2 < C / 2; j2++)
+            if (sweep_block_kept<GR, GC>(i, j2))
+              *reinterpret_cast<double2*>(cur + 2 * GC * j2 + 2 * tc) = make_double2(a[i][2 * j2], a[i][2 * j2 + 1]);
+          // slot p was just written (with d) by the lane of this row group that holds column p: the SAME lane
+          // overwrites it with d-1 (program order of one thread); every lane of the group tracks the same dg
+          if (tc == ((p >> 1) % GC)) {
+            cur[p] = dg - 1.0;
+            cur[NVP] = dinv_mine;
+          }
         }
-      }
-      __syncthreads();
-      const double dinv = cur[NVP];
-      bad = bad || !(dinv > 0.0 && dinv < 1e300);
-      double u[R];
+        if (tc == ((p % (2 * GC)) >> 1)) {  // column holders: the part of row p inside skipped super-blocks
 #pragma unroll
-      for (int ii = 0; ii < R; ii++) {
-        const double c = cur[tr + GR * ii];
-        u[ii] = -c * dinv;
-        if (ii == i) dg = fma(u[ii], c, dg);
-      }
-      // reciprocal of the next pivot of this block, started before the bulk update so that its latency hides
-      // behind the R*C DFMAs.  Every thread computes it for its own row (branch-free: a divergent or
-      // warp-selective version puts the reciprocal's latency back on the barrier's critical path).
-      dinv_mine = fast_rcp(dg);
-#pragma unroll
-      for (int j2 = 0; j2 < C / 2; j2++) {
-        const double2 v = *reinterpret_cast<const double2*>(cur + 2 * GC * j2 + 2 * tc);
+          for (int i2 = 0; i2 < R; i2++)
+            if (!sweep_block_kept<GR, GC>(i, (GR * i2) / (2 * GC))) cur[tr + GR * i2] = a[i2][2 * jc + e];
+        }
+        __syncthreads();
+        const double dinv = cur[NVP];
+        bad = bad || !(dinv > 0.0 && dinv < 1e300);
+        double u[R];
 #pragma unroll
         for (int ii = 0; ii < R; ii++) {
-          a[ii][2 * j2] = fma(u[ii], v.x, a[ii][2 * j2]);
-          a[ii][2 * j2 + 1] = fma(u[ii], v.y, a[ii][2 * j2 + 1]);
+          const double c = cur[tr + GR * ii];
+          u[ii] = -c * dinv;
+          if (ii == i) dg = fma(u[ii], c, dg);
+        }
+        // reciprocal of the next pivot of this block, started before the bulk update so that its latency hides
+        // behind the DFMAs.  Every thread computes it for its own row (branch-free: a divergent or
+        // warp-selective version puts the reciprocal's latency back on the barrier's critical path).
+        dinv_mine = fast_rcp(dg);
+#pragma unroll
+        for (int j2 = 0; j2 < C / 2; j2++) {
+          const double2 v = *reinterpret_cast<const double2*>(cur + 2 * GC * j2 + 2 * tc);
+#pragma unroll
+          for (int ii = 0; ii < R; ii++) {
+            if (!sweep_block_kept<GR, GC>(ii, j2)) continue;
+            a[ii][2 * j2] = fma(u[ii], v.x, a[ii][2 * j2]);
+            a[ii][2 * j2 + 1] = fma(u[ii], v.y, a[ii][2 * j2 + 1]);
+          }
         }
       }
     }
@@ -801,15 +833,21 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
     __syncthreads();
     return;
   }
-  // store H^{-1} = -(swept matrix), taking the 2 off every (swept) diagonal entry
+  // store H^{-1} = -(swept matrix), taking the 2 off every (swept) diagonal entry; entries whose transpose lies
+  // in a skipped super-block are written to both places
 #pragma unroll
   for (int i = 0; i < R; i++) {
     const int r = tr + GR * i;
     if (r < nv) {
 #pragma unroll
       for (int j = 0; j < C; j++) {
+        if (!sweep_block_kept<GR, GC>(i, j / 2)) continue;
         const int c = 2 * GC * (j / 2) + 2 * tc + (j & 1);
-        if (c < nv) Hm[r * ld + c] = (c == r) ? (2.0 - a[i][j]) : -a[i][j];
+        if (c < nv) {
+          const double val = (c == r) ? (2.0 - a[i][j]) : -a[i][j];
+          Hm[r * ld + c] = val;
+          if (!sweep_block_kept<GR, GC>(c / GR, r / (2 * GC))) Hm[c * ld + r] = val;
+        }
       }
     }
   }
