@@ -853,6 +853,178 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
   }
   __syncthreads();
 }
+
+// ---------------------------------------------------------------------------
+// Stage 2, register-resident, CIRCULANT symmetric storage: the same sweep, but with a kept-block pattern that is
+// invariant under a cyclic relabelling of the indices, so that ONE copy of the pivot body serves every pivot
+// (the triangular pattern above needs R copies with different register indices: at R = 8 that is 33 KB of SASS,
+// more than the 32 KB L1.5 instruction cache, and the kernel stalls on instruction fetch).
+//
+// Requires square super-blocks: S := GR = 2*GC, NB := R = C/2 blocks per side, NVP = S*NB.  Thread (tr, tc) holds,
+// for its row slot i (row tr + S*i of the CURRENT frame) the column blocks J = (i - dl) mod NB for dl = 0..D,
+// D = NB/2, columns S*J + 2*tc + e:  a[i][dl][e].  Every unordered block pair {I, J} has a representative
+// ((I - J) mod NB <= D or (J - I) mod NB <= D); pairs at distance 0 and D are held twice, which is harmless.
+// After the S pivots of block 0 the frame is rotated by one block (index k -> k - S mod NVP): a[i] <- a[i+1],
+// dl unchanged.  NB rotations bring the frame back to the original labelling.
+//
+// Row nv of the padded matrix (free when nv < NVP) optionally carries the gradient g: the sweep turns it into
+// H^{-1} g, so the unconstrained optimum x = -H^{-1} g needs no matrix-vector product afterwards.
+//
+// kWarp: the NT = 32 threads are one warp working alone (__syncwarp instead of CTA barriers).
+// kPacked: H^{-1} is stored as a packed lower triangle, Hm[i*(i+1)/2 + j], j <= i.
+// ---------------------------------------------------------------------------
+MPC_HD int tri_index(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+template <int GR, int R, int GC, int C, bool kWarp, bool kPacked>
+__device__ __forceinline__ void invert_spd_circ(const Work& k, int tid, bool with_g) {
+  constexpr int S = GR, NB = R, D = NB / 2, NVP = S * NB, BUF = NVP + 2;
+  static_assert(GR == 2 * GC && C == 2 * R && NB % 2 == 0 && NB >= 2, "square super-blocks, even block count");
+  Scalars* sc = k.sc;
+  const int nv = sc->nv, ld = k.ld;
+  double* Hm = k.Hm;
+  const int tr = tid / GC, tc = tid % GC;
+  auto sync = [&]() { if (kWarp) __syncwarp(); else __syncthreads(); };
+  double a[R][D + 1][2];
+  const bool gaug = with_g && nv < NVP;
+#pragma unroll
+  for (int i = 0; i < R; i++) {
+    const int r = tr + S * i;
+#pragma unroll
+    for (int dl = 0; dl <= D; dl++) {
+      const int J = (i - dl + NB) % NB;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = S * J + 2 * tc + e;
+        double v;
+        if (r < nv && c < nv) v = kPacked ? Hm[tri_index(r, c)] : Hm[r * ld + c];
+        else if (gaug && r == nv && c < nv) v = k.g[c];
+        else if (gaug && c == nv && r < nv) v = k.g[r];
+        else v = (r == c) ? 1.0 : 0.0;
+        a[i][dl][e] = v;
+      }
+    }
+  }
+  double* const buf0 = k.ck;
+  double* const buf1 = k.ck + BUF;
+  bool bad = false;
+  sync();  // everybody has read Hm / g before the buffers (which may overlay nothing) and Hm are rewritten
+  // publish pivot row q of the current frame into `dst` (all threads call it; compile-time register indices)
+  auto publish = [&](double* dst, int q, int e) {  // e == q & 1
+    if (tr == q) {
+#pragma unroll
+      for (int dl = 0; dl <= D; dl++) {
+        const int J = (NB - dl) % NB;
+        *reinterpret_cast<double2*>(dst + S * J + 2 * tc) = make_double2(a[0][dl][0], a[0][dl][1]);
+      }
+    }
+    if (tc == (q >> 1)) {
+#pragma unroll
+      for (int J = 1; J < D; J++) dst[tr + S * J] = a[J][J][e];
+    }
+    // slot q was just written (with d) by this same thread as part of its column pair: program order
+    const double rd = fast_rcp(a[0][0][e]);  // every thread (branch-free, overlaps with the bulk update); owner stores
+    if (tr == q && tc == (q >> 1)) {
+      dst[q] = a[0][0][e] - 1.0;
+      dst[NVP] = rd;
+    }
+  };
+  int p0 = 0;
+#pragma unroll 1
+  for (int b = 0; b < NB; b++, p0 += S) {
+    if (p0 < nv) {  // uniform
+      publish(buf0, 0, 0);
+#pragma unroll 1
+      for (int q0 = 0; q0 < S; q0 += 2) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int q = q0 + e;
+          if (p0 + q >= nv) break;  // uniform
+          double* const cur = e ? buf1 : buf0;
+          double* const nxt = e ? buf0 : buf1;
+          sync();
+          const double dinv = cur[NVP];
+          bad = bad || !(dinv > 0.0 && dinv < 1e300);
+          double u[R];
+#pragma unroll
+          for (int i = 0; i < R; i++) u[i] = -cur[tr + S * i] * dinv;
+          double2 v[NB];
+#pragma unroll
+          for (int J = 0; J < NB; J++) v[J] = *reinterpret_cast<const double2*>(cur + S * J + 2 * tc);
+          // look-ahead: first the entries the NEXT pivot's publication reads (row slot 0 and the column entries
+          // a[J][J][.]), then that publication, then the rest of the update -- the stores and the reciprocal overlap
+          // with the bulk of the DFMAs
+#pragma unroll
+          for (int dl = 0; dl <= D; dl++) {
+            const int J = (NB - dl) % NB;
+            a[0][dl][0] = fma(u[0], v[J].x, a[0][dl][0]);
+            a[0][dl][1] = fma(u[0], v[J].y, a[0][dl][1]);
+          }
+#pragma unroll
+          for (int J = 1; J < D; J++) {
+            a[J][J][0] = fma(u[J], v[0].x, a[J][J][0]);
+            a[J][J][1] = fma(u[J], v[0].y, a[J][J][1]);
+          }
+          if (q + 1 < S && p0 + q + 1 < nv) publish(nxt, q + 1, e ^ 1);  // uniform condition
+#pragma unroll
+          for (int i = 1; i < R; i++) {
+#pragma unroll
+            for (int dl = 0; dl <= D; dl++) {
+              if (i < D && dl == i) continue;  // done above
+              const int J = (i - dl + NB) % NB;
+              a[i][dl][0] = fma(u[i], v[J].x, a[i][dl][0]);
+              a[i][dl][1] = fma(u[i], v[J].y, a[i][dl][1]);
+            }
+          }
+        }
+      }
+      sync();  // the last pivot's buffer has been read by everybody before the next block publishes into buf0
+    }
+    // rotate the frame by one block
+#pragma unroll
+    for (int dl = 0; dl <= D; dl++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const double t0 = a[0][dl][e];
+#pragma unroll
+        for (int i = 0; i + 1 < R; i++) a[i][dl][e] = a[i + 1][dl][e];
+        a[R - 1][dl][e] = t0;
+      }
+  }
+  const bool any_bad = kWarp ? (__any_sync(0xffffffffu, bad) != 0) : (__syncthreads_or(bad) != 0);
+  if (any_bad) {
+    if (tid == 0) sc->status = MPC_STATUS_NOT_PD;
+    sync();
+    return;
+  }
+  // store H^{-1} = -(swept matrix) with the 2 taken off the diagonal; one writer per unordered pair (block pairs at
+  // distance 0 and D are held in both orientations: the lower-triangular one writes); row nv -> x = -H^{-1} g
+#pragma unroll
+  for (int i = 0; i < R; i++) {
+    const int r = tr + S * i;
+#pragma unroll
+    for (int dl = 0; dl <= D; dl++) {
+      const int J = (i - dl + NB) % NB;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = S * J + 2 * tc + e;
+        const double raw = a[i][dl][e];
+        if (r < nv && c < nv) {
+          const bool twice = (dl == 0) || (dl == D);
+          if (!twice || r >= c) {
+            const double val = (c == r) ? (2.0 - raw) : -raw;
+            if (kPacked) Hm[tri_index(r, c)] = val;
+            else { Hm[r * ld + c] = val; if (r != c) Hm[c * ld + r] = val; }
+          }
+        } else if (gaug && r == nv && c < nv) {
+          k.x[c] = -raw;
+        } else if (gaug && c == nv && r < nv && !(dl == 0 || dl == D)) {
+          k.x[r] = -raw;
+        }
+      }
+    }
+  }
+  sync();
+}
 #endif
 
 // ---------------------------------------------------------------------------

@@ -50,6 +50,7 @@ struct SolveParams {
   float* peers[kMaxPeers];
   int n_peers, rank_offset;
   long long* phase_clk;  // optional [batch][24] SM-clock stamps at phase boundaries (profiling aid)
+  int debug_stop;        // profiling aid (env MPC_DEBUG_STOP): 1 stop after assembly, 2 after the inversion; forces are NOT valid
   int32_t* nvar_out;  // assemble-only mode when H_out != nullptr
   double* H_out;
   double* g_out;
@@ -203,22 +204,40 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
       __syncthreads();
       continue;
     }
+    if (P.debug_stop == 1) { __syncthreads(); continue; }
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
-      mpc::active_set_init(cx, rec, gait, k);
       if constexpr (R > 0) {
         static_assert(R == 0 || NT == GR * GC, "thread grid");
+#ifdef MPC_CIRC
+        if constexpr (GR == 2 * GC && C == 2 * R && R % 2 == 0)
+          mpc::invert_spd_circ<GR, R, GC, C, NT == 32, false>(k, (int)threadIdx.x, false);
+        else
+#endif
         mpc::invert_spd_tiles<GR, R, GC, C>(k, (int)threadIdx.x);
       } else {
         mpc::invert_spd(cx, k);
       }
     }
     if (clk && threadIdx.x == 0) clk[2] = clock64();
+    if (P.debug_stop == 2) { __syncthreads(); continue; }
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
       mpc::active_set_init(cx, rec, gait, k);
       if constexpr (R > 0) {
         // shared-memory classes: the active-set loop is a chain of tiny steps, so one warp runs it with
         // __syncwarp / shuffles instead of CTA barriers; the other warps wait at the barrier below
-        if (P.warp_mode) { if (threadIdx.x < 32) mpc::active_set(mpc::Warp{(int)threadIdx.x, 32}, rec, gait, k, P.max_iter); } else mpc::active_set(cx, rec, gait, k, P.max_iter);
+        // which warp: rotated over CTAs and problems, so that the single-warp stages of the co-resident CTAs
+        // spread over the four SM sub-partitions (warp w of every CTA sits on sub-partition w % 4)
+        if (P.warp_mode) {
+#ifdef MPC_NO_ROTATE
+          const int aw = 0;
+#else
+          const int aw = (int)(blockIdx.x + it) & (NT / 32 - 1);
+#endif
+          if ((int)(threadIdx.x >> 5) == aw)
+            mpc::active_set(mpc::Warp{(int)(threadIdx.x & 31), 32}, rec, gait, k, P.max_iter);
+        } else {
+          mpc::active_set(cx, rec, gait, k, P.max_iter);
+        }
         __syncthreads();
       } else {
         mpc::active_set(cx, rec, gait, k, P.max_iter);
@@ -245,7 +264,12 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
       }
     }
     __syncthreads();
-    if (clk && threadIdx.x == 0) { clk[4] = clock64(); clk[5] = blockIdx.x; clk[6] = it; }
+    if (clk && threadIdx.x == 0) {
+      unsigned wid, sid;
+      asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sid));
+      clk[4] = clock64(); clk[5] = blockIdx.x; clk[6] = it; clk[7] = (long long)(sid << 8 | wid);
+    }
   }
 }
 
@@ -300,6 +324,7 @@ struct mpc_batch {
   unsigned** peer_flags_dev = nullptr;
   long long* phase_clk = nullptr;
   int ctas_per_sm_limit = 0;
+  int debug_stop = 0;
   void* peer_open[kMaxPeers] = {nullptr};
   std::string err;
 };
@@ -316,15 +341,26 @@ namespace {
   } while (0)
 
 // kernel variants: padded size -> (threads, thread grid, register tile)
+#ifndef MPC_MINB0
+#define MPC_MINB0 4  // resident CTAs per SM the smallest class is compiled for (register budget 65536 / (128 * MINB))
+#endif
+#ifndef MPC_V64_NT  // thread grid of the smallest class: NT = GR*GC threads, R x C register tiles (GR*R = GC*C = 64)
+#define MPC_V64_NT 128
+#define MPC_V64_GR 16
+#define MPC_V64_R 4
+#define MPC_V64_GC 8
+#define MPC_V64_C 8
+#endif
+#define MPC_V64_SHAPE MPC_V64_NT, MPC_V64_GR, MPC_V64_R, MPC_V64_GC, MPC_V64_C
 enum { V_64 = 0, V_96, V_128, V_GENERIC, V_COUNT };
 #define MPC_VARIANT_CALL(v, EXPR)                                                    \
   switch (v) {                                                                       \
-    case V_64: { auto kern = mpc_solve_kernel<128, 16, 4, 8, 8, 4>; EXPR; } break;    \
+    case V_64: { auto kern = mpc_solve_kernel<MPC_V64_SHAPE, MPC_MINB0>; EXPR; } break;    \
     case V_96: { auto kern = mpc_solve_kernel<256, 16, 6, 16, 6, 2>; EXPR; } break;   \
     case V_128: { auto kern = mpc_solve_kernel<256, 16, 8, 16, 8, 1>; EXPR; } break;  \
     default: { auto kern = mpc_solve_kernel<256, 0, 0, 0, 0, 1>; EXPR; } break;       \
   }
-const int kVariantThreads[V_COUNT] = {128, 256, 256, 256};
+const int kVariantThreads[V_COUNT] = {MPC_V64_NT, 256, 256, 256};
 const int kVariantPad[V_COUNT] = {64, 96, 128, 0};
 
 int configure_kernel(mpc_batch* eng, ClassCfg& c) {
@@ -411,6 +447,7 @@ void fill_params(const mpc_batch* eng, SolveParams& P, const void* records, int 
   P.max_iter = eng->max_iter;
   P.warp_mode = 1;
   P.phase_clk = eng->phase_clk;
+  P.debug_stop = eng->debug_stop;
   P.n_peers = eng->n_peers;
   P.rank_offset = eng->rank_offset;
   for (int q = 0; q < kMaxPeers; q++) P.peers[q] = eng->peers[q];
@@ -510,6 +547,7 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
       return fail(e_ == cudaErrorMemoryAllocation ? MPC_E_NOMEM : MPC_E_CUDA); \
     }                                                                   \
   } while (0)
+  if (const char* ds = getenv("MPC_DEBUG_STOP")) eng->debug_stop = atoi(ds);
   eng->device = device;
   eng->h = horizon;
   eng->max_batch = max_batch;

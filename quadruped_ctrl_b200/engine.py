@@ -14,7 +14,8 @@ import numpy as np
 from . import records as R
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libquadruped_mpc_b200.so")
+# MPC_LIB_PATH: development aid (A/B runs of experimental builds of the same library); never a CPU path
+LIB_PATH = os.environ.get("MPC_LIB_PATH") or os.path.join(_HERE, "libquadruped_mpc_b200.so")
 _LIB = None
 
 MPC_OK, MPC_E_ARG, MPC_E_CUDA, MPC_E_NOMEM, MPC_E_NODEVICE = 0, -1, -2, -3, -4

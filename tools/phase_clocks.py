@@ -47,3 +47,10 @@ print("  inter-problem gap median %.0f mean %.0f" % (np.median(gap), gap.mean())
 first = cs[np.r_[True, ~same]]
 print("  kernel span (max end - min start) %.0f cycles; first-problem start spread %.0f" %
       (c[:, 4].max() - c[:, 0].min(), first[:, 0].max() - first[:, 0].min()))
+
+# hardware warp slot of thread 0 (%warpid) per SM: which SM sub-partitions (slot % 4) the CTAs' first warps sit on
+wid = c[:, 7] & 0xff
+sm = c[:, 7] >> 8
+print("  %%warpid of warp 0, histogram of (slot %% 4): %s ; distinct slots %s" % (np.bincount(wid % 4, minlength=4), np.unique(wid)))
+one = sm == sm[0]
+print("  SM %d: slots used %s" % (sm[0], np.unique(wid[one])))
