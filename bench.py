@@ -183,14 +183,27 @@ def run_ours(args):
     n_sets = max(2, min(N_SETS, int(np.ceil(2.2 * L2_BYTES / (B * stride)))))
     host_sets = [W.config2(B, h, 1234 + 1000 * rank + i) for i in range(n_sets)]
     dev_sets = [torch.from_numpy(s).to(dev) for s in host_sets]
-    forces = torch.empty((B, 12), dtype=torch.float32, device=dev)
-    status = torch.empty((B,), dtype=torch.int32, device=dev)
-    gathered = torch.empty((world * B, 12), dtype=torch.float32, device=dev) if world > 1 else None
+    # Consecutive steps are independent batches, so they alternate between the engine's two scratch slots on two
+    # streams: the tail of step i (a few CTAs still solving) shares the GPU with the head of step i+1.
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    forces2 = [torch.empty((B, 12), dtype=torch.float32, device=dev) for _ in range(2)]
+    status2 = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(2)]
+    forces, status = forces2[0], status2[0]
+    gathered2 = [torch.empty((world * B, 12), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    gathered = gathered2[0] if world > 1 else None
     peer = world > 1 and args.gather == "peer"
     if peer:  # fused: the solve kernel stores every force straight into all ranks' gather buffers over NVLink
         gathered = eng.setup_peer_gather(world * B, rank * B)
+    overlap = not peer and not args.serial
 
     def step(i):
+        q = (i & 1) if overlap else 0
+        if overlap:
+            with torch.cuda.stream(streams[q]):
+                eng.solve_device(dev_sets[i % n_sets], forces=forces2[q], status=status2[q], stream=streams[q], slot=q)
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered2[q], forces2[q])
+            return
         eng.solve_device(dev_sets[i % n_sets], forces=forces, status=status)
         if world > 1:
             if peer:
@@ -198,17 +211,30 @@ def run_ours(args):
             else:
                 dist.all_gather_into_tensor(gathered, forces)
 
+    def fork():
+        cur = torch.cuda.current_stream(dev)
+        for st in streams:
+            st.wait_stream(cur)
+
+    def join():
+        cur = torch.cuda.current_stream(dev)
+        for st in streams:
+            cur.wait_stream(st)
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    fork()
     for i in range(args.warmup):
         step(i)
+    join()
     barrier()
     # all problems must have solved to optimality before anything is timed
-    codes = (status.cpu().numpy() & 0xff)
-    assert (codes == 0).all(), "non-optimal status in warm-up: %s" % np.bincount(codes)
+    for st_ in (status2 if overlap else status2[:1]):
+        codes = (st_.cpu().numpy() & 0xff)
+        assert (codes == 0).all(), "non-optimal status in warm-up: %s" % np.bincount(codes)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -220,14 +246,25 @@ def run_ours(args):
     barrier()
     eng.timing_mark()
     ev0.record()
+    fork()
     for i in range(args.steps):
         step(args.warmup + i)
+    join()
     ev1.record()
     barrier()
     total_ms = ev0.elapsed_time(ev1)
-    # mean duration of the dominant kernel over the timed steps (events recorded on the launching stream)
-    k_ms, k_n = eng.timing_collect(dominant)
     launches = eng.kernel_launches() - launches0
+    # mean duration of the dominant kernel over the timed steps (events recorded on the launching stream); with
+    # overlapping steps two launches share the GPU, so each one's duration is longer than its share of the step
+    k_ms_timed, k_n = eng.timing_collect(dominant)
+    # the same kernel timed alone: the same steps once more, one at a time on one stream (roofline figure)
+    k_ms = k_ms_timed
+    if overlap:
+        eng.timing_mark()
+        for i in range(min(args.steps, 32)):
+            eng.solve_device(dev_sets[(args.warmup + i) % n_sets], forces=forces, status=status)
+        torch.cuda.synchronize()
+        k_ms, _ = eng.timing_collect(dominant)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -282,6 +319,8 @@ def run_ours(args):
                                    "friction-cone rows per step, seed 1234+" % (B, h),
                        "l2": "inputs rotate over %d distinct record sets (%.0f MB > 126 MB L2), no flush needed"
                              % (n_sets, n_sets * B * stride / 1e6),
+                       "pipelining": ("steps alternate between the engine's two scratch slots / streams (independent batches)"
+                                      if overlap else "one stream, steps strictly one after another"),
                        "collective": ("none (N=1)" if world == 1 else
                                       "peer stores from the solve kernel + device-side flag barrier (no NCCL on the path)" if peer else
                                       "all_gather_into_tensor of [N*B,12] fp32 forces"),
@@ -293,6 +332,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(), "peak_source": peak_src,
                          "kernel": "mpc_solve_kernel<128> (size class nv<=60)", "kernel_ms": k_ms, "kernel_launches_timed": k_n,
+                         "kernel_ms_in_timed_region": k_ms_timed,
                          "algorithmic_bytes_per_solve": R.algorithmic_bytes(h),
                          "note": "on-chip fp64/latency bound by construction: H and g never leave shared memory, so "
                                  "the HBM fraction is tiny; see DESIGN.md for the fp64-pipe figures"},
@@ -317,6 +357,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--serial", action="store_true", help="one stream, no overlap between consecutive steps")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
                     help="N>1: NCCL all-gather of the forces (default) or the kernel's fused peer-store epilogue")
     args = ap.parse_args()

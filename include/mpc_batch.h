@@ -136,6 +136,13 @@ int mpc_batch_solve_device(mpc_batch_t* eng, const void* records_dev, int batch,
                            float* forces_dev, double* solution_dev,
                            int32_t* status_dev, void* cuda_stream);
 
+/* The same on scratch slot `slot` (0 or 1).  Two device-resident solves of one engine may overlap when they
+ * use different slots and different streams: the tail of one batch then shares the GPU with the head of the
+ * next (independent batches; nothing is exchanged between them). */
+int mpc_batch_solve_device_slot(mpc_batch_t* eng, int slot, const void* records_dev, int batch,
+                           float* forces_dev, double* solution_dev,
+                           int32_t* status_dev, void* cuda_stream);
+
 /* Host-resident solve: stages records through pinned memory, runs the device
  * solve, copies forces/solution/status back and synchronises. */
 int mpc_batch_solve_host(mpc_batch_t* eng, const void* records_host, int batch,

@@ -729,8 +729,11 @@ __device__ __forceinline__ double fast_rcp(double d) {
 template <int GR, int GC>
 __host__ __device__ constexpr bool sweep_block_kept(int i, int j2) { return 2 * GC * j2 <= GR * i + GR - 1; }
 
+// with_g: row nv of the padded matrix (free when nv < NVP; all of it lies in kept super-blocks) carries the
+// gradient g.  It is never pivoted, so the sweep turns it into H^{-1} g and the unconstrained optimum
+// x = -H^{-1} g comes out of the inversion for free (no matrix-vector product afterwards).
 template <int GR, int R, int GC, int C>
-__device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
+__device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid, bool with_g) {
   constexpr int NVP = GR * R;
   constexpr int BUF = NVP + 2;
   static_assert(GC * C == NVP && C % 2 == 0 && 32 % GC == 0, "tile grid must cover the padded matrix");
@@ -739,6 +742,7 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
   const int nv = sc->nv, ld = k.ld;
   double* Hm = k.Hm;
   const int tr = tid / GC, tc = tid % GC, lane = tid & 31;
+  const bool gaug = with_g && nv < NVP;
   double a[R][C];
 #pragma unroll
   for (int i = 0; i < R; i++) {
@@ -747,7 +751,10 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
     for (int j = 0; j < C; j++) {
       if (!sweep_block_kept<GR, GC>(i, j / 2)) continue;
       const int c = 2 * GC * (j / 2) + 2 * tc + (j & 1);
-      a[i][j] = (r < nv && c < nv) ? Hm[r * ld + c] : (r == c ? 1.0 : 0.0);
+      double v = (r < nv && c < nv) ? Hm[r * ld + c] : (r == c ? 1.0 : 0.0);
+      if (gaug && r == nv && c < nv) v = k.g[c];
+      if (gaug && c == nv && r < nv) v = k.g[r];
+      a[i][j] = v;
     }
   }
   // two broadcast buffers (even / odd pivot): slots 0..NVP-1 the pivot row, slot NVP = 1/d
@@ -834,10 +841,18 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid) {
     return;
   }
   // store H^{-1} = -(swept matrix), taking the 2 off every (swept) diagonal entry; entries whose transpose lies
-  // in a skipped super-block are written to both places
+  // in a skipped super-block are written to both places; row nv (the swept gradient) -> x = -H^{-1} g
 #pragma unroll
   for (int i = 0; i < R; i++) {
     const int r = tr + GR * i;
+    if (gaug && r == nv) {
+#pragma unroll
+      for (int j = 0; j < C; j++) {
+        if (!sweep_block_kept<GR, GC>(i, j / 2)) continue;
+        const int c = 2 * GC * (j / 2) + 2 * tc + (j & 1);
+        if (c < nv) k.x[c] = -a[i][j];
+      }
+    }
     if (r < nv) {
 #pragma unroll
       for (int j = 0; j < C; j++) {
@@ -1039,11 +1054,12 @@ __device__ __forceinline__ void invert_spd_circ(const Work& k, int tid, bool wit
 // ---------------------------------------------------------------------------
 // Start of stage 3 (all threads): unconstrained optimum x = -Minv g, empty working set.
 template <class Cx>
-MPC_HD void active_set_init(const Cx& cx, const float* rec, const unsigned char* gait, const Work& k) {
+MPC_HD void active_set_init(const Cx& cx, const float* rec, const unsigned char* gait, const Work& k,
+                            bool have_x = false) {
   Scalars* sc = k.sc;
   const int nv = sc->nv, ld = k.ld, ns = sc->ns;
   const double* Hm = k.Hm;
-  MPC_FOR(i, nv) {  // four independent partial sums: the chain is latency-, not throughput-bound
+  if (!have_x) MPC_FOR(i, nv) {  // four independent partial sums: the chain is latency-, not throughput-bound
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     int j = 0;
 #pragma unroll 1

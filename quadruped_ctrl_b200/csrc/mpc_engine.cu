@@ -210,10 +210,10 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
         static_assert(R == 0 || NT == GR * GC, "thread grid");
 #ifdef MPC_CIRC
         if constexpr (GR == 2 * GC && C == 2 * R && R % 2 == 0)
-          mpc::invert_spd_circ<GR, R, GC, C, NT == 32, false>(k, (int)threadIdx.x, false);
+          mpc::invert_spd_circ<GR, R, GC, C, NT == 32, false>(k, (int)threadIdx.x, true);
         else
 #endif
-        mpc::invert_spd_tiles<GR, R, GC, C>(k, (int)threadIdx.x);
+        mpc::invert_spd_tiles<GR, R, GC, C>(k, (int)threadIdx.x, true);
       } else {
         mpc::invert_spd(cx, k);
       }
@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
     if (clk && threadIdx.x == 0) clk[2] = clock64();
     if (P.debug_stop == 2) { __syncthreads(); continue; }
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
-      mpc::active_set_init(cx, rec, gait, k);
+      // register-resident classes: x = -H^{-1} g came out of the sweep (the gradient rode along as row nv)
+      mpc::active_set_init(cx, rec, gait, k, R > 0 && k.sc->nv < GR * R);
       if constexpr (R > 0) {
         // shared-memory classes: the active-set loop is a chain of tiny steps, so one warp runs it with
         // __syncwarp / shuffles instead of CTA barriers; the other warps wait at the barrier below
@@ -635,6 +636,19 @@ int mpc_batch_solve_device(mpc_batch_t* eng, const void* records_dev, int batch,
                          nullptr, nullptr, nullptr);
 }
 
+int mpc_batch_solve_device_slot(mpc_batch_t* eng, int slot, const void* records_dev, int batch, float* forces_dev,
+                                double* solution_dev, int32_t* status_dev, void* cuda_stream) {
+  if (!eng) return MPC_E_ARG;
+  if (slot < 0 || slot > 1 || !records_dev || !forces_dev || batch < 0 || batch > eng->max_batch ||
+      ((uintptr_t)records_dev & 15)) {
+    eng->err = "mpc_batch_solve_device_slot: bad argument";
+    return MPC_E_ARG;
+  }
+  CK(cudaSetDevice(eng->device));
+  return solve_on_stream(eng, slot, records_dev, batch, forces_dev, solution_dev, status_dev,
+                         (cudaStream_t)cuda_stream, nullptr, nullptr, nullptr);
+}
+
 int mpc_batch_submit_host(mpc_batch_t* eng, int slot, const void* records_host, int batch, int want_solution) {
   if (!eng) return MPC_E_ARG;
   if (slot < 0 || slot > 1 || !records_host || batch < 0 || batch > eng->max_batch) {
@@ -649,8 +663,23 @@ int mpc_batch_submit_host(mpc_batch_t* eng, int slot, const void* records_host, 
   const size_t NU = 12 * (size_t)eng->h;
   // pageable -> pinned staging on the host (skipped when the caller filled the slot's pinned buffer in place),
   // then H2D, kernels and D2H queued on the slot's stream; nothing here waits for the GPU
-  if (records_host != (const void*)S.rec_pin) memcpy(S.rec_pin, records_host, (size_t)batch * eng->stride);
-  CK(cudaMemcpyAsync(S.rec_dev, S.rec_pin, (size_t)batch * eng->stride, cudaMemcpyHostToDevice, S.stream));
+  const size_t bytes = (size_t)batch * eng->stride;
+  bool in_place = records_host == (const void*)S.rec_pin;
+  if (!in_place) {  // a page-locked caller buffer (cudaHostAlloc / cudaHostRegister) is read by the DMA in place
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, records_host) == cudaSuccess) in_place = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
+  if (in_place) {
+    CK(cudaMemcpyAsync(S.rec_dev, records_host, bytes, cudaMemcpyHostToDevice, S.stream));
+  } else {  // pageable: staged chunk by chunk, so that chunk c's DMA overlaps the host copy of chunk c+1
+    const size_t chunk = 512u << 10;
+    for (size_t off = 0; off < bytes; off += chunk) {
+      const size_t n = std::min(chunk, bytes - off);
+      memcpy(S.rec_pin + off, (const char*)records_host + off, n);
+      CK(cudaMemcpyAsync(S.rec_dev + off, S.rec_pin + off, n, cudaMemcpyHostToDevice, S.stream));
+    }
+  }
   int rc = solve_on_stream(eng, slot, S.rec_dev, batch, S.forces_dev, want_solution ? S.sol_dev : nullptr, S.status_dev,
                            S.stream, nullptr, nullptr, nullptr);
   if (rc) return rc;

@@ -23,7 +23,7 @@ STATUS_OPTIMAL, STATUS_MAX_ITER, STATUS_BAD_INPUT, STATUS_NOT_PD, STATUS_NO_STAN
 
 # every symbol include/mpc_batch.h and include/convexMPC_interface.h declare
 BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_create", "mpc_batch_destroy",
-                 "mpc_batch_solve_device", "mpc_batch_solve_host", "mpc_batch_submit_host", "mpc_batch_wait_host",
+                 "mpc_batch_solve_device", "mpc_batch_solve_device_slot", "mpc_batch_solve_host", "mpc_batch_submit_host", "mpc_batch_wait_host",
                  "mpc_batch_assemble_device", "mpc_batch_build_records_device", "mpc_batch_solve_ticks_device",
                  "mpc_batch_set_gather_peers", "mpc_batch_gather_alloc", "mpc_batch_gather_connect",
                  "mpc_batch_gather_buffer", "mpc_batch_gather_sync", "mpc_batch_set_max_iterations", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
@@ -69,6 +69,7 @@ def lib():
     L.mpc_batch_destroy.argtypes = [vp]
     L.mpc_batch_destroy.restype = None
     L.mpc_batch_solve_device.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.mpc_batch_solve_device_slot.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp]
     L.mpc_batch_solve_host.argtypes = [vp, vp, i32, vp, vp, vp]
     L.mpc_batch_submit_host.argtypes = [vp, i32, vp, i32, i32]
     L.mpc_batch_wait_host.argtypes = [vp, i32, vp, vp, vp]
@@ -260,9 +261,10 @@ class MpcBatch:
 
     # ---- solves ---------------------------------------------------------------------------
     def solve_device(self, records, forces=None, solution=None, status=None, want_solution=False,
-                     want_status=True, stream=None):
+                     want_status=True, stream=None, slot=0):
         """records: cuda uint8 tensor [B, stride] on this engine's device.  Asynchronous on `stream`
-        (default: torch's current stream).  Returns (forces [B,12] f32, solution [B,12h] f64 | None,
+        (default: torch's current stream).  `slot` (0/1) picks the engine's device scratch: two solves may
+        overlap when they use different slots on different streams.  Returns (forces [B,12] f32, solution [B,12h] f64 | None,
         status [B] int32 | None), all cuda tensors."""
         torch = _torch()
         assert records.is_cuda and records.dtype == torch.uint8 and records.is_contiguous()
@@ -276,10 +278,10 @@ class MpcBatch:
         if status is None and want_status:
             status = torch.empty((B,), dtype=torch.int32, device=dev)
         st = stream if stream is not None else torch.cuda.current_stream(dev)
-        rc = self._L.mpc_batch_solve_device(self._h, records.data_ptr(), B, forces.data_ptr(),
-                                            solution.data_ptr() if solution is not None else None,
-                                            status.data_ptr() if status is not None else None, st.cuda_stream)
-        self._check(rc, "mpc_batch_solve_device")
+        rc = self._L.mpc_batch_solve_device_slot(self._h, int(slot), records.data_ptr(), B, forces.data_ptr(),
+                                                 solution.data_ptr() if solution is not None else None,
+                                                 status.data_ptr() if status is not None else None, st.cuda_stream)
+        self._check(rc, "mpc_batch_solve_device_slot")
         return forces, solution, status
 
     def solve_host(self, records, want_solution=False, out_forces=None, out_status=None, out_solution=None):
