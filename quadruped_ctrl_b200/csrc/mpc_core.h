@@ -82,14 +82,17 @@ constexpr int kRedDoubles = 40;
 inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
 // The same function sizes the launch (host) and carves the pointers (device).
-inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npad = 0) {
+// packed: Hm as a packed lower triangle (the register-resident classes; the generic in-place sweep of the
+// catch-all class and of the host emulation needs full storage)
+inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npad = 0, int packed = -1) {
+  if (packed < 0) packed = 0;
   Layout L;
   L.h = h;
   L.nv_cap = nv_cap;
   // register-resident inversion: two (npad + 2)-long buffers (double-buffered pivot row + 1/pivot)
   L.ck_len = npad > 0 ? 2 * (npad + 2) : nv_cap;
   L.m_cap = m_cap;
-  L.ld = nv_cap | 1;
+  L.ld = packed ? -1 : (nv_cap | 1);  // packed lower triangle (see hix()) or full storage
   L.ldT = m_cap | 1;
   L.big_in_fast = big_in_fast;
   int o = 0;
@@ -107,7 +110,8 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
   int gi = L.ck_len + 1 + 4 * h + (m_cap + 1) * 6;  // ck (16-byte aligned), ub, Wca, Wcz, w, r, u, tcol
   int un = kAsmDoubles(h);
   int t_doubles = m_cap * L.ldT;
-  int hm_doubles = nv_cap * L.ld;
+  int hm_doubles = packed ? nv_cap * (nv_cap + 1) / 2 : nv_cap * L.ld;
+  if (hm_doubles < 3 * 12 * h) hm_doubles = 3 * 12 * h;  // the assembly parks its moment sums there
   if (big_in_fast) gi += t_doubles;
   if (gi > un) un = gi;
   o += 8 * un;
@@ -137,6 +141,7 @@ struct Work {
 };
 
 #if defined(__CUDA_ARCH__)
+// k.clk is null at compile time in the production instantiation of the kernel: the stamps then vanish
 #define MPC_STAMP(k, cx, slot) do { if ((k).clk && (cx).tid == 0) (k).clk[slot] = clock64(); } while (0)
 #else
 #define MPC_STAMP(k, cx, slot) do { } while (0)
@@ -191,25 +196,35 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
 // ---------------------------------------------------------------------------
 // Execution context.  Device: one CTA.  Host emulation: one thread.
 // ---------------------------------------------------------------------------
+// kPacked (compile time): Hm is a packed lower triangle (hix() below) instead of full row-major storage.
 #if defined(__CUDACC__)
-struct Cta {
+template <bool PK>
+struct CtaT {
   static constexpr bool kOneWarp = false;
+  static constexpr bool kPacked = PK;
   int tid, nt;
   __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 // One warp of the CTA working alone (the latency-bound active-set stage): barriers are __syncwarp and
 // reductions are shuffles only.
-struct Warp {
+template <bool PK>
+struct WarpT {
   static constexpr bool kOneWarp = true;
+  static constexpr bool kPacked = PK;
   int tid, nt;  // lane, 32
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
+using Cta = CtaT<false>;
+using Warp = WarpT<false>;
 #endif
-struct OneThread {
+template <bool PK>
+struct OneThreadT {
   static constexpr bool kOneWarp = false;
+  static constexpr bool kPacked = PK;
   int tid, nt;
   inline void sync() const {}
 };
+using OneThread = OneThreadT<false>;
 
 // Strided loops are deliberately NOT unrolled: the kernel is instruction-cache bound (32 KB L1.5 I-cache),
 // and these loops run a handful of iterations per thread.
@@ -289,6 +304,14 @@ MPC_HD double block_sum(const Cx& cx, double* red, double val) {
 //   type 4:  fz >= 0             type 5: -fz >= -gait*f_max
 // A row is (ia, ca, iz=3j+2, cz): n = ca*e_ia + cz*e_iz (ia == iz, ca = 0 for 4,5).
 // ---------------------------------------------------------------------------
+// Index of entry (i, j) of the symmetric matrix Hm: full row-major storage with leading dimension ld > 0, or
+// (ld < 0) a packed lower triangle, (i, j) and (j, i) being one element -- half the footprint for index arithmetic
+// on every access.  Hot code takes the choice at compile time (Cx::kPacked).
+MPC_HD int tri_index(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+template <bool PK>
+MPC_HD int hixT(int ld, int i, int j) { return PK ? tri_index(i, j) : i * ld + j; }
+MPC_HD int hix(int ld, int i, int j) { return ld > 0 ? i * ld + j : tri_index(i, j); }  // run-time form (cold paths)
+
 struct Row {
   int ia, iz;
   double ca, cz;
@@ -304,11 +327,12 @@ MPC_HD Row make_row(int c, double mu_inv) {
   return r;
 }
 // n_a' Minv n_b for two catalogue rows: at most four look-ups
+template <bool PK>
 MPC_HD double row_minv_row(const double* Hm, int ld, const Row& a, const Row& b) {
-  double s = a.cz * b.cz * Hm[a.iz * ld + b.iz];
-  if (a.ca != 0.0) s += a.ca * b.cz * Hm[a.ia * ld + b.iz];
-  if (b.ca != 0.0) s += a.cz * b.ca * Hm[a.iz * ld + b.ia];
-  if (a.ca != 0.0 && b.ca != 0.0) s += a.ca * b.ca * Hm[a.ia * ld + b.ia];
+  double s = a.cz * b.cz * Hm[hixT<PK>(ld, a.iz, b.iz)];
+  if (a.ca != 0.0) s += a.ca * b.cz * Hm[hixT<PK>(ld, a.ia, b.iz)];
+  if (b.ca != 0.0) s += a.cz * b.ca * Hm[hixT<PK>(ld, a.iz, b.ia)];
+  if (a.ca != 0.0 && b.ca != 0.0) s += a.ca * b.ca * Hm[hixT<PK>(ld, a.ia, b.ia)];
   return s;
 }
 
@@ -585,8 +609,8 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
           }
         double val = 2.0 * acc;
         if (a == b && ax == bx) val += 2.0 * alpha;
-        k.Hm[(3 * a + ax) * k.ld + 3 * b + bx] = val;
-        k.Hm[(3 * b + bx) * k.ld + 3 * a + ax] = val;
+        k.Hm[hixT<Cx::kPacked>(k.ld, 3 * a + ax, 3 * b + bx)] = val;
+        if (!Cx::kPacked) k.Hm[(3 * b + bx) * k.ld + 3 * a + ax] = val;
       }
   }
   cx.sync();
@@ -732,7 +756,7 @@ __host__ __device__ constexpr bool sweep_block_kept(int i, int j2) { return 2 * 
 // with_g: row nv of the padded matrix (free when nv < NVP; all of it lies in kept super-blocks) carries the
 // gradient g.  It is never pivoted, so the sweep turns it into H^{-1} g and the unconstrained optimum
 // x = -H^{-1} g comes out of the inversion for free (no matrix-vector product afterwards).
-template <int GR, int R, int GC, int C>
+template <int GR, int R, int GC, int C, bool kPacked>
 __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid, bool with_g) {
   constexpr int NVP = GR * R;
   constexpr int BUF = NVP + 2;
@@ -751,7 +775,7 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid, bool wi
     for (int j = 0; j < C; j++) {
       if (!sweep_block_kept<GR, GC>(i, j / 2)) continue;
       const int c = 2 * GC * (j / 2) + 2 * tc + (j & 1);
-      double v = (r < nv && c < nv) ? Hm[r * ld + c] : (r == c ? 1.0 : 0.0);
+      double v = (r < nv && c < nv) ? Hm[hixT<kPacked>(ld, r, c)] : (r == c ? 1.0 : 0.0);
       if (gaug && r == nv && c < nv) v = k.g[c];
       if (gaug && c == nv && r < nv) v = k.g[r];
       a[i][j] = v;
@@ -860,8 +884,14 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid, bool wi
         const int c = 2 * GC * (j / 2) + 2 * tc + (j & 1);
         if (c < nv) {
           const double val = (c == r) ? (2.0 - a[i][j]) : -a[i][j];
-          Hm[r * ld + c] = val;
-          if (!sweep_block_kept<GR, GC>(c / GR, r / (2 * GC))) Hm[c * ld + r] = val;
+          // packed storage: one writer per unordered pair -- the lower-triangular orientation, which always lies
+          // in a kept super-block (the diagonal super-blocks hold both orientations)
+          if (!kPacked) {
+            Hm[r * ld + c] = val;
+            if (!sweep_block_kept<GR, GC>(c / GR, r / (2 * GC))) Hm[c * ld + r] = val;
+          } else if (r >= c) {
+            Hm[tri_index(r, c)] = val;
+          }
         }
       }
     }
@@ -888,8 +918,6 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid, bool wi
 // kWarp: the NT = 32 threads are one warp working alone (__syncwarp instead of CTA barriers).
 // kPacked: H^{-1} is stored as a packed lower triangle, Hm[i*(i+1)/2 + j], j <= i.
 // ---------------------------------------------------------------------------
-MPC_HD int tri_index(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
-
 template <int GR, int R, int GC, int C, bool kWarp, bool kPacked>
 __device__ __forceinline__ void invert_spd_circ(const Work& k, int tid, bool with_g) {
   constexpr int S = GR, NB = R, D = NB / 2, NVP = S * NB, BUF = NVP + 2;
@@ -911,7 +939,7 @@ __device__ __forceinline__ void invert_spd_circ(const Work& k, int tid, bool wit
       for (int e = 0; e < 2; e++) {
         const int c = S * J + 2 * tc + e;
         double v;
-        if (r < nv && c < nv) v = kPacked ? Hm[tri_index(r, c)] : Hm[r * ld + c];
+        if (r < nv && c < nv) v = Hm[hixT<kPacked>(ld, r, c)];
         else if (gaug && r == nv && c < nv) v = k.g[c];
         else if (gaug && c == nv && r < nv) v = k.g[r];
         else v = (r == c) ? 1.0 : 0.0;
@@ -1064,13 +1092,13 @@ MPC_HD void active_set_init(const Cx& cx, const float* rec, const unsigned char*
     int j = 0;
 #pragma unroll 1
     for (; j + 3 < nv; j += 4) {
-      a0 += Hm[j * ld + i] * k.g[j];
-      a1 += Hm[(j + 1) * ld + i] * k.g[j + 1];
-      a2 += Hm[(j + 2) * ld + i] * k.g[j + 2];
-      a3 += Hm[(j + 3) * ld + i] * k.g[j + 3];
+      a0 += Hm[hixT<Cx::kPacked>(ld, j, i)] * k.g[j];
+      a1 += Hm[hixT<Cx::kPacked>(ld, (j + 1), i)] * k.g[j + 1];
+      a2 += Hm[hixT<Cx::kPacked>(ld, (j + 2), i)] * k.g[j + 2];
+      a3 += Hm[hixT<Cx::kPacked>(ld, (j + 3), i)] * k.g[j + 3];
     }
 #pragma unroll 1
-    for (; j < nv; j++) a0 += Hm[j * ld + i] * k.g[j];
+    for (; j < nv; j++) a0 += Hm[hixT<Cx::kPacked>(ld, j, i)] * k.g[j];
     k.x[i] = -((a0 + a1) + (a2 + a3));
   }
   MPC_FOR(j, ns) {
@@ -1128,9 +1156,9 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       MPC_FOR(a, m) {
         Row ra;
         ra.ia = k.Wia[a]; ra.iz = k.Wiz[a]; ra.ca = k.Wca[a]; ra.cz = k.Wcz[a];
-        k.w[a] = row_minv_row(Hm, ld, ra, rp);
+        k.w[a] = row_minv_row<Cx::kPacked>(Hm, ld, ra, rp);
       }
-      const double vnp = row_minv_row(Hm, ld, rp, rp);
+      const double vnp = row_minv_row<Cx::kPacked>(Hm, ld, rp, rp);
       cx.sync();
       // r = T w   (T symmetric: walk columns for contiguous reads)
       MPC_FOR(a, m) {
@@ -1168,12 +1196,12 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       // zero, and x and u must move with the same (r, t) for stationarity x = -Minv (g - N u) to survive.
       {
         MPC_FOR(i, nv) {
-          double acc0 = rp.cz * Hm[rp.iz * ld + i], acc1 = rp.ca * Hm[rp.ia * ld + i];
+          double acc0 = rp.cz * Hm[hixT<Cx::kPacked>(ld, rp.iz, i)], acc1 = rp.ca * Hm[hixT<Cx::kPacked>(ld, rp.ia, i)];
 #pragma unroll 1
           for (int a = 0; a < m; a++) {
             const double ra = k.r[a];
-            acc0 -= ra * k.Wcz[a] * Hm[k.Wiz[a] * ld + i];
-            acc1 -= ra * k.Wca[a] * Hm[k.Wia[a] * ld + i];
+            acc0 -= ra * k.Wcz[a] * Hm[hixT<Cx::kPacked>(ld, k.Wiz[a], i)];
+            acc1 -= ra * k.Wca[a] * Hm[hixT<Cx::kPacked>(ld, k.Wia[a], i)];
           }
           k.x[i] += t * (acc0 + acc1);
         }
@@ -1274,8 +1302,8 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
 #pragma unroll 1
         for (int a = 0; a < m; a++) {
           const double ra = k.r[a];
-          acc0 += ra * k.Wcz[a] * Hm[k.Wiz[a] * ld + i];
-          acc1 += ra * k.Wca[a] * Hm[k.Wia[a] * ld + i];
+          acc0 += ra * k.Wcz[a] * Hm[hixT<Cx::kPacked>(ld, k.Wiz[a], i)];
+          acc1 += ra * k.Wca[a] * Hm[hixT<Cx::kPacked>(ld, k.Wia[a], i)];
         }
         k.x[i] += acc0 + acc1;
       }

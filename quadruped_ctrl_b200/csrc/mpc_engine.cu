@@ -149,7 +149,9 @@ __global__ void mpc_gather_wait_kernel(const unsigned* my_flags, int world, unsi
 // NT threads per CTA.  R > 0: register-resident inversion with R x C tiles on a GR x GC thread grid (NT == GR*GC,
 // padded size GR*R == GC*C).  R == 0: the generic shared/global-memory sweep, used by the catch-all class whose
 // matrix does not fit in the register file of one SM.
-template <int NT, int GR, int R, int GC, int C, int MINB>
+// PROF: the instantiation that serves the profiling / debugging entries (phase clocks, assemble-only output, stage
+// stop).  The production instantiation carries none of that code (2% faster: the kernel is instruction-fetch heavy).
+template <int NT, int GR, int R, int GC, int C, int MINB, bool PK, bool PROF>
 __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) char smem[];
   const int count = P.count ? *P.count : P.batch;
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
   uint64_t* bar = (uint64_t*)smem;
   char* recbuf = smem + 16;
   char* fast = recbuf + 2 * P.stride;
-  const mpc::Cta cx{(int)threadIdx.x, NT};
+  const mpc::CtaT<PK> cx{(int)threadIdx.x, NT};  // PK: H / H^{-1} as a packed lower triangle (see build_classes)
   const mpc::Work k = mpc::carve(P.L, fast, P.slab ? P.slab + (size_t)blockIdx.x * P.L.slab_bytes : nullptr);
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
@@ -185,11 +187,13 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
     const float* rec = (const float*)(recbuf + (size_t)cur * P.stride);
     const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
 
-    long long* clk = P.phase_clk ? P.phase_clk + (size_t)24 * b : nullptr;
-    const_cast<mpc::Work&>(k).clk = clk;
+    long long* clk = nullptr;
+    if constexpr (PROF) clk = P.phase_clk ? P.phase_clk + (size_t)24 * b : nullptr;
+    if constexpr (PROF) const_cast<mpc::Work&>(k).clk = clk;
     if (clk && threadIdx.x == 0) clk[0] = clock64();
     mpc::assemble(cx, rec, gait, k);
     if (clk && threadIdx.x == 0) clk[1] = clock64();
+    if constexpr (PROF) {
     if (P.H_out) {  // debug / parity entry: write the reduced QP out and stop
       const int nv = (k.sc->status == MPC_STATUS_OPTIMAL) ? k.sc->nv : 0;
       const int NU = 12 * P.h;
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
       double* Ho = P.H_out + (size_t)b * NU * NU;
       for (int e = threadIdx.x; e < nv * nv; e += NT) {
         const int i = e / nv, j = e - i * nv;
-        Ho[(size_t)i * NU + j] = k.Hm[i * k.ld + j];
+        Ho[(size_t)i * NU + j] = k.Hm[mpc::hixT<PK>(k.ld, i, j)];
       }
       if (P.g_out)
         for (int i = threadIdx.x; i < nv; i += NT) P.g_out[(size_t)b * NU + i] = k.g[i];
@@ -205,37 +209,38 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
       continue;
     }
     if (P.debug_stop == 1) { __syncthreads(); continue; }
+    }
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
       if constexpr (R > 0) {
         static_assert(R == 0 || NT == GR * GC, "thread grid");
 #ifdef MPC_CIRC
         if constexpr (GR == 2 * GC && C == 2 * R && R % 2 == 0)
-          mpc::invert_spd_circ<GR, R, GC, C, NT == 32, false>(k, (int)threadIdx.x, true);
+          mpc::invert_spd_circ<GR, R, GC, C, NT == 32, PK>(k, (int)threadIdx.x, true);
         else
 #endif
-        mpc::invert_spd_tiles<GR, R, GC, C>(k, (int)threadIdx.x, true);
+        mpc::invert_spd_tiles<GR, R, GC, C, PK>(k, (int)threadIdx.x, true);
       } else {
         mpc::invert_spd(cx, k);
       }
     }
     if (clk && threadIdx.x == 0) clk[2] = clock64();
-    if (P.debug_stop == 2) { __syncthreads(); continue; }
+    if constexpr (PROF) {
+      if (P.debug_stop == 2) { __syncthreads(); continue; }
+    }
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
       // register-resident classes: x = -H^{-1} g came out of the sweep (the gradient rode along as row nv)
       mpc::active_set_init(cx, rec, gait, k, R > 0 && k.sc->nv < GR * R);
       if constexpr (R > 0) {
         // shared-memory classes: the active-set loop is a chain of tiny steps, so one warp runs it with
         // __syncwarp / shuffles instead of CTA barriers; the other warps wait at the barrier below
-        // which warp: rotated over CTAs and problems, so that the single-warp stages of the co-resident CTAs
-        // spread over the four SM sub-partitions (warp w of every CTA sits on sub-partition w % 4)
         if (P.warp_mode) {
-#ifdef MPC_NO_ROTATE
-          const int aw = 0;
-#else
+#ifdef MPC_ROTATE_GI  // measured: rotating the warp over CTAs / problems is 1% slower than always using warp 0
           const int aw = (int)(blockIdx.x + it) & (NT / 32 - 1);
+#else
+          const int aw = 0;
 #endif
           if ((int)(threadIdx.x >> 5) == aw)
-            mpc::active_set(mpc::Warp{(int)(threadIdx.x & 31), 32}, rec, gait, k, P.max_iter);
+            mpc::active_set(mpc::WarpT<PK>{(int)(threadIdx.x & 31), 32}, rec, gait, k, P.max_iter);
         } else {
           mpc::active_set(cx, rec, gait, k, P.max_iter);
         }
@@ -345,6 +350,12 @@ namespace {
 #ifndef MPC_MINB0
 #define MPC_MINB0 4  // resident CTAs per SM the smallest class is compiled for (register budget 65536 / (128 * MINB))
 #endif
+#ifndef MPC_MINB96
+#define MPC_MINB96 2
+#endif
+#ifndef MPC_MINB128
+#define MPC_MINB128 2
+#endif
 #ifndef MPC_V64_NT  // thread grid of the smallest class: NT = GR*GC threads, R x C register tiles (GR*R = GC*C = 64)
 #define MPC_V64_NT 128
 #define MPC_V64_GR 16
@@ -354,13 +365,15 @@ namespace {
 #endif
 #define MPC_V64_SHAPE MPC_V64_NT, MPC_V64_GR, MPC_V64_R, MPC_V64_GC, MPC_V64_C
 enum { V_64 = 0, V_96, V_128, V_GENERIC, V_COUNT };
-#define MPC_VARIANT_CALL(v, EXPR)                                                    \
-  switch (v) {                                                                       \
-    case V_64: { auto kern = mpc_solve_kernel<MPC_V64_SHAPE, MPC_MINB0>; EXPR; } break;    \
-    case V_96: { auto kern = mpc_solve_kernel<256, 16, 6, 16, 6, 2>; EXPR; } break;   \
-    case V_128: { auto kern = mpc_solve_kernel<256, 16, 8, 16, 8, 1>; EXPR; } break;  \
-    default: { auto kern = mpc_solve_kernel<256, 0, 0, 0, 0, 1>; EXPR; } break;       \
+#define MPC_VARIANT_CALL1(v, PROF, EXPR)                                                                     \
+  switch (v) {                                                                                               \
+    case V_64: { auto kern = mpc_solve_kernel<MPC_V64_SHAPE, MPC_MINB0, false, PROF>; EXPR; } break;          \
+    case V_96: { auto kern = mpc_solve_kernel<256, 16, 6, 16, 6, MPC_MINB96, false, PROF>; EXPR; } break;     \
+    case V_128: { auto kern = mpc_solve_kernel<256, 16, 8, 16, 8, MPC_MINB128, true, PROF>; EXPR; } break;    \
+    default: { auto kern = mpc_solve_kernel<256, 0, 0, 0, 0, 1, false, PROF>; EXPR; } break;                  \
   }
+#define MPC_VARIANT_CALL(v, prof, EXPR)                       \
+  if (prof) { MPC_VARIANT_CALL1(v, true, EXPR) } else { MPC_VARIANT_CALL1(v, false, EXPR) }
 const int kVariantThreads[V_COUNT] = {MPC_V64_NT, 256, 256, 256};
 const int kVariantPad[V_COUNT] = {64, 96, 128, 0};
 
@@ -369,10 +382,12 @@ int configure_kernel(mpc_batch* eng, ClassCfg& c) {
   int max_smem = 0;
   CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, eng->device));
   int occ = 0;
-  MPC_VARIANT_CALL(c.variant, {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c.threads, c.smem));
-  });
+  for (int prof = 1; prof >= 0; prof--) {  // the production instantiation last: its occupancy sizes the grid
+    MPC_VARIANT_CALL(c.variant, prof, {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c.threads, c.smem));
+    });
+  }
   if (occ < 1) {
     eng->err = "solve kernel does not fit on an SM";
     return MPC_E_CUDA;
@@ -408,7 +423,11 @@ int build_classes(mpc_batch* eng) {
     c.threads = kVariantThreads[c.variant];
     c.m_cap = free_m_cap(h, cap, kVariantPad[c.variant]);
     c.in_fast = 1;
-    c.L = mpc::make_layout(h, c.nv_cap, c.m_cap, 1, kVariantPad[c.variant]);
+    // Packed (lower-triangular) storage of H / H^{-1} halves the tile but costs index arithmetic on every access
+    // (measured, same box: -11% at nv <= 60, -7% at nv <= 96 with unchanged occupancy).  It pays where it buys
+    // residency: the nv <= 128 class goes from one to two CTAs per SM (+33% on four-stance horizon-10 problems).
+    const int packed = c.variant == V_128 ? 1 : 0;  // must match the PK argument of the variant's kernel
+    c.L = mpc::make_layout(h, c.nv_cap, c.m_cap, 1, kVariantPad[c.variant], packed);
     c.smem = 16 + 2 * eng->stride + c.L.fast_bytes;
     if ((int)c.smem > max_smem) continue;
     int rc = configure_kernel(eng, c);
@@ -455,7 +474,8 @@ void fill_params(const mpc_batch* eng, SolveParams& P, const void* records, int 
 }
 
 int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int grid, cudaStream_t st) {
-  MPC_VARIANT_CALL(c.variant, (kern<<<grid, c.threads, c.smem, st>>>(P)));
+  const bool prof = P.phase_clk != nullptr || P.H_out != nullptr || P.debug_stop != 0;
+  MPC_VARIANT_CALL(c.variant, prof, (kern<<<grid, c.threads, c.smem, st>>>(P)));
   eng->launches++;
   CK(cudaGetLastError());
   return MPC_OK;

@@ -16,29 +16,21 @@ static std::vector<double> g_dbg_u, g_dbg_minv;
 static std::vector<int> g_dbg_W;
 static int g_dbg_nv = 0, g_dbg_m = 0;
 
-extern "C" {
-
-// debugging aid: working set, duals and inverse of the LAST problem solved
-int emu_debug_last(int* W, double* u, double* minv, int* nv) {
-  for (int i = 0; i < g_dbg_m; i++) { W[i] = g_dbg_W[i]; u[i] = g_dbg_u[i]; }
-  for (size_t i = 0; i < g_dbg_minv.size(); i++) minv[i] = g_dbg_minv[i];
-  *nv = g_dbg_nv;
-  return g_dbg_m;
-}
-
 // Runs `batch` records through the kernel body with one emulated thread.
 //   nv_cap / m_cap <= 0 -> worst case (12h).  H_out/g_out (optional): the reduced QP
 //   before inversion, [batch*(12h)^2] / [batch*12h] with leading dimension 12h.
 //   info [batch*4]: nv, active-set size at exit, iterations, status code.
-int emu_solve_batch(const void* records, int batch, int h, int nv_cap, int m_cap, int max_iter, float* forces,
-                    double* solution, int* info, double* H_out, double* g_out) {
+template <bool PK>
+static int emu_solve_batch_t(const void* records, int batch, int h, int nv_cap, int m_cap, int max_iter, float* forces,
+                             double* solution, int* info, double* H_out, double* g_out) {
   using namespace mpc;
   if (nv_cap <= 0) nv_cap = 12 * h;
   if (m_cap <= 0) m_cap = nv_cap;
-  const Layout L = make_layout(h, nv_cap, m_cap, 1);
+  const int packed = PK ? 1 : 0;
+  const Layout L = make_layout(h, nv_cap, m_cap, 1, 0, packed);
   std::vector<char> fast(L.fast_bytes + 64);
   const size_t stride = ((size_t)(4 * (MPC_REC_TRAJ + 12 * h) + 4 * h) + 15) / 16 * 16;
-  OneThread cx{0, 1};
+  OneThreadT<PK> cx{0, 1};
   const int NU = 12 * h;
   for (int b = 0; b < batch; b++) {
     memset(fast.data(), 0xCD, fast.size());  // poison: nothing may rely on zeroed workspace
@@ -50,10 +42,29 @@ int emu_solve_batch(const void* records, int batch, int h, int nv_cap, int m_cap
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
       if (H_out)
         for (int i = 0; i < k.sc->nv; i++)
-          for (int j = 0; j < k.sc->nv; j++) H_out[(size_t)b * NU * NU + (size_t)i * NU + j] = k.Hm[i * k.ld + j];
+          for (int j = 0; j < k.sc->nv; j++) H_out[(size_t)b * NU * NU + (size_t)i * NU + j] = k.Hm[hix(k.ld, i, j)];
       if (g_out)
         for (int i = 0; i < k.sc->nv; i++) g_out[(size_t)b * NU + i] = k.g[i];
-      invert_spd(cx, k);
+      if (k.ld > 0) {
+        invert_spd(cx, k);
+      } else {
+        // packed layout: the device inverts in registers (invert_spd_tiles); here the same symmetric sweep runs on
+        // a dense copy, so that the packed stores of the assembly and the packed reads of the active set are tested
+        const int n = k.sc->nv;
+        std::vector<double> D((size_t)n * n);
+        for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) D[(size_t)i * n + j] = k.Hm[hix(k.ld, i, j)];
+        for (int p = 0; p < n && k.sc->status == MPC_STATUS_OPTIMAL; p++) {
+          const double d = D[(size_t)p * n + p];
+          if (!(d > 0.0)) { k.sc->status = MPC_STATUS_NOT_PD; break; }
+          std::vector<double> c(n);
+          for (int i = 0; i < n; i++) c[i] = D[(size_t)p * n + i];
+          for (int i = 0; i < n; i++) for (int j = 0; j < n; j++)
+            if (i != p && j != p) D[(size_t)i * n + j] -= c[i] * c[j] / d;
+          for (int i = 0; i < n; i++) { D[(size_t)p * n + i] = c[i] / d; D[(size_t)i * n + p] = c[i] / d; }
+          D[(size_t)p * n + p] = -1.0 / d;
+        }
+        for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) k.Hm[hix(k.ld, i, j)] = -D[(size_t)i * n + j];
+      }
       if (k.sc->status == MPC_STATUS_OPTIMAL) {
         active_set_init(cx, rec, gait, k);
         active_set(cx, rec, gait, k, max_iter);
@@ -62,7 +73,7 @@ int emu_solve_batch(const void* records, int batch, int h, int nv_cap, int m_cap
     g_dbg_m = k.sc->m; g_dbg_nv = k.sc->nv;
     g_dbg_W.assign(k.W, k.W + g_dbg_m); g_dbg_u.assign(k.u, k.u + g_dbg_m);
     g_dbg_minv.resize((size_t)g_dbg_nv * g_dbg_nv);
-    for (int i = 0; i < g_dbg_nv; i++) for (int j = 0; j < g_dbg_nv; j++) g_dbg_minv[(size_t)i * g_dbg_nv + j] = k.Hm[i * k.ld + j];
+    for (int i = 0; i < g_dbg_nv; i++) for (int j = 0; j < g_dbg_nv; j++) g_dbg_minv[(size_t)i * g_dbg_nv + j] = k.Hm[hix(k.ld, i, j)];
     int32_t st = 0;
     scatter(cx, k, forces + 12 * b, solution ? solution + (size_t)NU * b : nullptr, &st);
     if (info) {
@@ -73,6 +84,24 @@ int emu_solve_batch(const void* records, int batch, int h, int nv_cap, int m_cap
     }
   }
   return 0;
+}
+
+extern "C" {
+
+// debugging aid: working set, duals and inverse of the LAST problem solved
+int emu_debug_last(int* W, double* u, double* minv, int* nv) {
+  for (int i = 0; i < g_dbg_m; i++) { W[i] = g_dbg_W[i]; u[i] = g_dbg_u[i]; }
+  for (size_t i = 0; i < g_dbg_minv.size(); i++) minv[i] = g_dbg_minv[i];
+  *nv = g_dbg_nv;
+  return g_dbg_m;
+}
+
+int emu_solve_batch(const void* records, int batch, int h, int nv_cap, int m_cap, int max_iter, float* forces,
+                    double* solution, int* info, double* H_out, double* g_out) {
+  // MPC_EMU_PACKED=1: the packed-triangle layout of the nv <= 128 register class
+  const bool packed = getenv("MPC_EMU_PACKED") && atoi(getenv("MPC_EMU_PACKED")) != 0;
+  return packed ? emu_solve_batch_t<true>(records, batch, h, nv_cap, m_cap, max_iter, forces, solution, info, H_out, g_out)
+                : emu_solve_batch_t<false>(records, batch, h, nv_cap, m_cap, max_iter, forces, solution, info, H_out, g_out);
 }
 
 // Host build of the device-side record builder (csrc/mpc_ticks.h), one robot at a time.

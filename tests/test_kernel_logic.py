@@ -151,3 +151,20 @@ def test_gait_values_above_one_scale_the_force_limit():
     hi = emu_solve(rec2, h)
     assert lo["sol"].max() <= 10.0 + 1e-9
     assert hi["sol"].max() > 10.0 + 1e-3 and hi["sol"].max() <= 20.0 + 1e-9
+
+
+def test_packed_layout_gives_the_same_answers(monkeypatch):
+    """The register-resident classes keep H / H^{-1} as a packed lower triangle (hix() with ld < 0).  The host
+    emulation of that layout (assembly stores and active-set reads go through the packed index) must agree with
+    the full-storage layout to round-off."""
+    rec = W.CONFIGS["config2"](48, seed=77)
+    rec4 = W.CONFIGS["four_stance"](16, seed=78)
+    for r, h in ((rec, 10), (rec4, 10)):
+        monkeypatch.setenv("MPC_EMU_PACKED", "0")
+        full = emu_solve(r, h, want_qp=True)
+        monkeypatch.setenv("MPC_EMU_PACKED", "1")
+        packed = emu_solve(r, h, want_qp=True)
+        assert (packed["status"] == ST_OPT).all() and (full["status"] == ST_OPT).all()
+        assert np.array_equal(packed["H"], full["H"]) and np.array_equal(packed["g"], full["g"])
+        assert rel(packed["sol"], full["sol"]).max() < 1e-10
+        assert (packed["iters"] == full["iters"]).all()

@@ -54,3 +54,22 @@ sm = c[:, 7] >> 8
 print("  %%warpid of warp 0, histogram of (slot %% 4): %s ; distinct slots %s" % (np.bincount(wid % 4, minlength=4), np.unique(wid)))
 one = sm == sm[0]
 print("  SM %d: slots used %s" % (sm[0], np.unique(wid[one])))
+
+# Are the co-resident CTAs phase-locked?  For every SM: at the start of each sweep, how many OTHER CTAs of that SM are
+# inside their sweep (clk[1]..clk[2]) at that instant, against the expectation if the CTAs ran independently.
+starts, ends, sms = c[:, 1], c[:, 2], sm
+frac_in = ((ends - starts).sum() / max(1, (c[:, 4] - c[:, 0]).sum()))
+cnt = []
+for s_id in np.unique(sms)[:40]:
+    sel = sms == s_id
+    a, b_, t0, t1 = starts[sel], ends[sel], c[sel, 0], c[sel, 4]
+    lo, hi = np.percentile(t0, 20), np.percentile(t1, 80)   # steady part of the launch
+    for t in a[(a > lo) & (a < hi)]:
+        others = ((a < t) & (b_ > t)).sum()
+        alive = ((t0 < t) & (t1 > t)).sum() - 1
+        cnt.append((others, alive))
+cnt = np.array(cnt)
+if len(cnt):
+    print("  sweep overlap: at a sweep start %.2f other CTAs of the SM are sweeping (mean; %.2f other CTAs mid-problem; "
+          "independent phases would give %.2f); histogram %s"
+          % (cnt[:, 0].mean(), cnt[:, 1].mean(), cnt[:, 1].mean() * frac_in, np.bincount(cnt[:, 0])))
