@@ -76,6 +76,7 @@ struct Scalars {
   double sp, t1, t2, t, up, vnp, znp, dreg;
 };
 
+constexpr int kSweepGroup = 8;  // pivots per pass of the generic sweep (see invert_spd)
 constexpr int kAsmDoubles(int h) { return 3 * 156 + 6 * 144 + 39 + 12 * h + 5 * h; }
 constexpr int kRedDoubles = 40;
 
@@ -90,7 +91,7 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
   L.h = h;
   L.nv_cap = nv_cap;
   // register-resident inversion: two (npad + 2)-long buffers (double-buffered pivot row + 1/pivot)
-  L.ck_len = npad > 0 ? 2 * (npad + 2) : nv_cap;
+  L.ck_len = npad > 0 ? 2 * (npad + 2) : 2 * kSweepGroup * nv_cap;  // generic sweep: K snapshots + K scaled copies
   L.m_cap = m_cap;
   L.ld = packed ? -1 : (nv_cap | 1);  // packed lower triangle (see hix()) or full storage
   L.ldT = m_cap | 1;
@@ -198,10 +199,15 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
 // ---------------------------------------------------------------------------
 // kPacked (compile time): Hm is a packed lower triangle (hix() below) instead of full row-major storage.
 #if defined(__CUDACC__)
-template <bool PK>
+// UNR: unroll factor of the active set's inner loops over the working set.  1 where H^{-1} and T sit in shared memory
+// (the kernel is instruction-fetch heavy); 4 for the catch-all class, whose H^{-1} / T live in an L2-resident slab and
+// whose loops are chains of dependent-latency loads -- unrolling issues the loads of four steps before the first
+// FMA (same summation order, so the same bits).
+template <bool PK, int UNR = 1>
 struct CtaT {
   static constexpr bool kOneWarp = false;
   static constexpr bool kPacked = PK;
+  static constexpr int kUnroll = UNR;
   int tid, nt;
   __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
@@ -211,6 +217,7 @@ template <bool PK>
 struct WarpT {
   static constexpr bool kOneWarp = true;
   static constexpr bool kPacked = PK;
+  static constexpr int kUnroll = 1;
   int tid, nt;  // lane, 32
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
@@ -221,6 +228,7 @@ template <bool PK>
 struct OneThreadT {
   static constexpr bool kOneWarp = false;
   static constexpr bool kPacked = PK;
+  static constexpr int kUnroll = 1;
   int tid, nt;
   inline void sync() const {}
 };
@@ -631,28 +639,62 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
 // (i > p); the result is mirrored, negated and the 2 taken off the diagonal in one final pass.
 template <class Cx>
 MPC_HD void invert_spd(const Cx& cx, const Work& k) {
+  // Pivots are taken in groups of K = kSweepGroup so that the matrix (L2-resident in the catch-all class) is read
+  // and written once per GROUP instead of once per pivot.  This is NOT the block sweep ruled out above: nothing is
+  // inverted blockwise.  (A) the K pivot rows are gathered into fast memory; (B) they are swept against each other
+  // one pivot at a time, and each row is frozen ("snapshot") the moment it becomes the pivot row -- exactly the row
+  // the one-pivot-per-pass algorithm would broadcast, with slot p holding d-1 -- together with its scaled copy
+  // u = -row/d; (C) one pass over the lower triangle applies the K rank-1 updates in pivot order to every tile,
+  // a_ij = fma(u_p[i], row_p[j], a_ij).  Every element sees the same operations in the same order as with one pass
+  // per pivot, so the result is bit-identical to it; only the traffic drops by K.
+  constexpr int K = kSweepGroup;
   Scalars* sc = k.sc;
   const int nv = sc->nv, ld = k.ld;
   double* Hm = k.Hm;
-  double* ck = k.ck;
+  double* S = k.ck;                       // [K][nv_cap] snapshots of the pivot rows
+  double* U = k.ck + K * k.nv_cap;        // [K][nv_cap] -snapshot/d
+  const int lds = k.nv_cap;
   const int nt4 = (nv + 3) / 4;
   const int ntiles = nt4 * (nt4 + 1) / 2;
-  for (int p = 0; p < nv; p++) {
-    MPC_FOR(i, nv) {
-      const double v = (i <= p) ? Hm[p * ld + i] : Hm[i * ld + p];
-      ck[i] = (i == p) ? v - 1.0 : v;
+  for (int p0 = 0; p0 < nv; p0 += K) {
+    const int kk = (nv - p0 < K) ? nv - p0 : K;
+    // (A) gather rows p0..p0+kk-1 (row p = row p for j <= p, column p for i > p)
+    MPC_FOR(e, kk * nv) {
+      const int g = e / nv, i = e - g * nv, p = p0 + g;
+      S[g * lds + i] = (i <= p) ? Hm[p * ld + i] : Hm[i * ld + p];
     }
     cx.sync();
-    const double d = ck[p] + 1.0;
-    if (!(d > 0.0)) {  // uniform: every thread reads the same pivot
+    // (B) sweep the group's rows against each other, freezing each at its pivot time
+    bool bad = false;
+    for (int g = 0; g < kk; g++) {
+      const int p = p0 + g;
+      const double d = S[g * lds + p];
+      if (!(d > 0.0)) { bad = true; break; }  // uniform: every thread reads the same pivot
+      const double dinv = 1.0 / d;
+      cx.sync();  // everybody has read d before the diagonal slot is rewritten
+      MPC_FOR(i, nv) {
+        const double c = (i == p) ? d - 1.0 : S[g * lds + i];
+        if (i == p) S[g * lds + i] = c;
+        U[g * lds + i] = -c * dinv;
+      }
+      cx.sync();
+      // later rows r of the group: entry (r, j) sees what pass (C) applies to the stored element -- (r, j) itself
+      // for j <= r, its mirror (j, r) for j > r: u taken at the row index, the pivot-row value at the column index
+      MPC_FOR(e, (kk - 1 - g) * nv) {
+        const int g2 = g + 1 + e / nv, j = e - (e / nv) * nv, r = p0 + g2;
+        const double uv = (j <= r) ? U[g * lds + r] * S[g * lds + j] : U[g * lds + j] * S[g * lds + r];
+        S[g2 * lds + j] = S[g2 * lds + j] + uv;
+      }
+      cx.sync();
+    }
+    if (bad) {
       cx.sync();
       MPC_ONE sc->status = MPC_STATUS_NOT_PD;
       cx.sync();
       return;
     }
-    const double dinv = 1.0 / d;
-    // two tiles per iteration with all loads issued before the arithmetic: the matrix sits in L2 (catch-all
-    // class), so the pass is bound by outstanding loads per thread
+    // (C) one pass over the lower triangle: two tiles per iteration with all loads issued before the arithmetic
+    // (the matrix sits in L2, so the pass is bound by outstanding loads per thread)
     for (int t0 = cx.tid; t0 < ntiles; t0 += 2 * cx.nt) {
       double acc[2][4][4];
       int ti0[2], tj0[2];
@@ -678,18 +720,26 @@ MPC_HD void invert_spd(const Cx& cx, const Work& k) {
       }
 #pragma unroll
       for (int s2 = 0; s2 < 2; s2++) {
-        double u[4], v[4];
+        if (ti0[s2] >= nv) continue;
+#pragma unroll 1
+        for (int g = 0; g < kk; g++) {
+          double u[4], v[4];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          u[e] = (ti0[s2] + e < nv) ? -ck[ti0[s2] + e] * dinv : 0.0;
-          v[e] = (tj0[s2] + e < nv) ? ck[tj0[s2] + e] : 0.0;
+          for (int e = 0; e < 4; e++) {
+            u[e] = (ti0[s2] + e < nv) ? U[g * lds + ti0[s2] + e] : 0.0;
+            v[e] = (tj0[s2] + e < nv) ? S[g * lds + tj0[s2] + e] : 0.0;
+          }
+#pragma unroll
+          for (int di = 0; di < 4; di++)
+#pragma unroll
+            for (int dj = 0; dj < 4; dj++) acc[s2][di][dj] = acc[s2][di][dj] + u[di] * v[dj];
         }
 #pragma unroll
         for (int di = 0; di < 4; di++)
 #pragma unroll
           for (int dj = 0; dj < 4; dj++) {
             const int i = ti0[s2] + di, j = tj0[s2] + dj;
-            if (i < nv && j <= i) Hm[i * ld + j] = acc[s2][di][dj] + u[di] * v[dj];
+            if (i < nv && j <= i) Hm[i * ld + j] = acc[s2][di][dj];
           }
       }
     }
@@ -834,7 +884,9 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid, bool wi
         }
         __syncthreads();
         const double dinv = cur[NVP];
-        bad = bad || !(dinv > 0.0 && dinv < 1e300);
+        // positive, normal and < 1e300, tested on the high word (two integer instructions instead of two DSETPs
+        // on the fp64 pipe): NaN, inf, zero, subnormal and negative values all fall outside the window
+        bad = bad || (unsigned)(__double2hiint(dinv) - 0x00100000) >= (unsigned)(0x7E37E43C - 0x00100000);
         double u[R];
 #pragma unroll
         for (int ii = 0; ii < R; ii++) {
@@ -1163,7 +1215,7 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       // r = T w   (T symmetric: walk columns for contiguous reads)
       MPC_FOR(a, m) {
         double acc = 0;
-#pragma unroll 1
+#pragma unroll(Cx::kUnroll)
         for (int b = 0; b < m; b++) acc += T[b * ldT + a] * k.w[b];
         k.r[a] = acc;
       }
@@ -1197,7 +1249,7 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       {
         MPC_FOR(i, nv) {
           double acc0 = rp.cz * Hm[hixT<Cx::kPacked>(ld, rp.iz, i)], acc1 = rp.ca * Hm[hixT<Cx::kPacked>(ld, rp.ia, i)];
-#pragma unroll 1
+#pragma unroll(Cx::kUnroll)
           for (int a = 0; a < m; a++) {
             const double ra = k.r[a];
             acc0 -= ra * k.Wcz[a] * Hm[hixT<Cx::kPacked>(ld, k.Wiz[a], i)];
@@ -1292,14 +1344,14 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       cx.sync();
       MPC_FOR(a, m) {
         double acc = 0;
-#pragma unroll 1
+#pragma unroll(Cx::kUnroll)
         for (int b = 0; b < m; b++) acc += T[b * ldT + a] * k.w[b];
         k.r[a] = acc;
       }
       cx.sync();
       MPC_FOR(i, nv) {
         double acc0 = 0, acc1 = 0;
-#pragma unroll 1
+#pragma unroll(Cx::kUnroll)
         for (int a = 0; a < m; a++) {
           const double ra = k.r[a];
           acc0 += ra * k.Wcz[a] * Hm[hixT<Cx::kPacked>(ld, k.Wiz[a], i)];

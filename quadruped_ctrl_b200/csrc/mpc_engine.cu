@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
   uint64_t* bar = (uint64_t*)smem;
   char* recbuf = smem + 16;
   char* fast = recbuf + 2 * P.stride;
-  const mpc::CtaT<PK> cx{(int)threadIdx.x, NT};  // PK: H / H^{-1} as a packed lower triangle (see build_classes)
+  const mpc::CtaT<PK, (R == 0 ? 4 : 1)> cx{(int)threadIdx.x, NT};  // PK: H / H^{-1} as a packed lower triangle (see build_classes)
   const mpc::Work k = mpc::carve(P.L, fast, P.slab ? P.slab + (size_t)blockIdx.x * P.L.slab_bytes : nullptr);
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
@@ -353,6 +353,9 @@ namespace {
 #ifndef MPC_MINB96
 #define MPC_MINB96 2
 #endif
+#ifndef MPC_MINBG  // catch-all class: CTAs per SM it is compiled for
+#define MPC_MINBG 2
+#endif
 #ifndef MPC_MINB128
 #define MPC_MINB128 2
 #endif
@@ -370,7 +373,7 @@ enum { V_64 = 0, V_96, V_128, V_GENERIC, V_COUNT };
     case V_64: { auto kern = mpc_solve_kernel<MPC_V64_SHAPE, MPC_MINB0, false, PROF>; EXPR; } break;          \
     case V_96: { auto kern = mpc_solve_kernel<256, 16, 6, 16, 6, MPC_MINB96, false, PROF>; EXPR; } break;     \
     case V_128: { auto kern = mpc_solve_kernel<256, 16, 8, 16, 8, MPC_MINB128, true, PROF>; EXPR; } break;    \
-    default: { auto kern = mpc_solve_kernel<256, 0, 0, 0, 0, 1, false, PROF>; EXPR; } break;                  \
+    default: { auto kern = mpc_solve_kernel<256, 0, 0, 0, 0, MPC_MINBG, false, PROF>; EXPR; } break;                  \
   }
 #define MPC_VARIANT_CALL(v, prof, EXPR)                       \
   if (prof) { MPC_VARIANT_CALL1(v, true, EXPR) } else { MPC_VARIANT_CALL1(v, false, EXPR) }
@@ -445,6 +448,7 @@ int build_classes(mpc_batch* eng) {
   big.threads = kVariantThreads[V_GENERIC];
   int rc = configure_kernel(eng, big);
   if (rc) return rc;
+  if (const char* e = getenv("MPC_BIG_CTAS")) big.grid = std::min(big.grid, atoi(e) * eng->sms); else
   big.grid = std::min(big.grid, 2 * eng->sms);  // two slabs per SM: more loads in flight, slabs still mostly L2-resident
   eng->classes.push_back(big);
   if ((int)eng->classes.size() > kMaxClasses) {
