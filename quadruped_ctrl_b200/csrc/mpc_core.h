@@ -76,7 +76,7 @@ struct Scalars {
   double sp, t1, t2, t, up, vnp, znp, dreg;
 };
 
-constexpr int kSweepGroup = 8;  // pivots per pass of the generic sweep (see invert_spd)
+constexpr int kSweepGroup = 16;  // pivots per pass of the generic sweep (see invert_spd)
 constexpr int kAsmDoubles(int h) { return 3 * 156 + 6 * 144 + 39 + 12 * h + 5 * h; }
 constexpr int kRedDoubles = 40;
 
@@ -659,7 +659,8 @@ MPC_HD void invert_spd(const Cx& cx, const Work& k) {
   for (int p0 = 0; p0 < nv; p0 += K) {
     const int kk = (nv - p0 < K) ? nv - p0 : K;
     // (A) gather rows p0..p0+kk-1 (row p = row p for j <= p, column p for i > p)
-    MPC_FOR(e, kk * nv) {
+#pragma unroll 4
+    for (int e = cx.tid; e < kk * nv; e += cx.nt) {  // unrolled: independent L2 loads in flight
       const int g = e / nv, i = e - g * nv, p = p0 + g;
       S[g * lds + i] = (i <= p) ? Hm[p * ld + i] : Hm[i * ld + p];
     }
@@ -746,7 +747,8 @@ MPC_HD void invert_spd(const Cx& cx, const Work& k) {
     cx.sync();
   }
   // mirror the lower triangle, negate, take the 2 off the (swept) diagonal
-  MPC_FOR(e, nv * nv) {
+#pragma unroll 4
+  for (int e = cx.tid; e < nv * nv; e += cx.nt) {  // unrolled: independent L2 loads in flight
     const int i = e / nv, j = e - i * nv;
     if (j < i) {
       const double v = -Hm[i * ld + j];

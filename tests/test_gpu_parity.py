@@ -232,6 +232,48 @@ def test_pipelined_host_entry_matches_synchronous(cuda_engine_factory):
         assert np.array_equal(rf, gf) and np.array_equal(rs, gs) and np.array_equal(rst, gst)
 
 
+def test_two_device_slots_overlap_without_interference(cuda_engine_factory):
+    """Device-resident solves on the engine's two scratch slots / two streams (the bench's pipelined steps):
+    interleaved, overlapping launches give bit for bit what one-at-a-time solves give, for mixed size classes."""
+    B = 1024
+    eng = cuda_engine_factory(10, B)
+    batches = [torch.from_numpy(np.concatenate([W.config2(B // 2, 10, 300 + i), W.CONFIGS["four_stance"](B // 2, seed=400 + i)]))
+               .cuda() for i in range(6)]
+    ref = []
+    for b in batches:
+        f, s, st = eng.solve_device(b, want_solution=True)
+        torch.cuda.synchronize()
+        ref.append((f.cpu().numpy(), s.cpu().numpy(), st.cpu().numpy()))
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for i, b in enumerate(batches):
+        with torch.cuda.stream(streams[i & 1]):
+            outs.append(eng.solve_device(b, want_solution=True, stream=streams[i & 1], slot=i & 1))
+    torch.cuda.synchronize()
+    for (rf, rs, rst), (f, s, st) in zip(ref, outs):
+        assert np.array_equal(rf, f.cpu().numpy())
+        assert np.array_equal(rs, s.cpu().numpy())
+        assert np.array_equal(rst, st.cpu().numpy())
+    assert (E.status_code(ref[0][2]) == E.STATUS_OPTIMAL).all()
+
+
+def test_host_entry_reads_page_locked_buffers_in_place(cuda_engine_factory):
+    """submit_host: a page-locked caller buffer goes to the DMA engine in place, a pageable one is staged in
+    chunks (the batch here spans several 512 KB chunks); both give the same bytes back."""
+    B = 2048
+    eng = cuda_engine_factory(10, B)
+    rec = W.config2(B, 10, 555)
+    assert rec.nbytes > 2 * (512 << 10)
+    pinned = torch.from_numpy(rec.copy()).pin_memory()
+    f1, s1, st1 = eng.solve_host(rec, want_solution=True)             # pageable numpy array
+    f2, s2, st2 = eng.solve_host(pinned.numpy(), want_solution=True)  # page-locked memory
+    assert np.array_equal(f1, f2) and np.array_equal(s1, s2) and np.array_equal(st1, st2)
+    fd, sd, std = eng.solve_device(torch.from_numpy(rec).cuda(), want_solution=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(f1, fd.cpu().numpy()) and np.array_equal(s1, sd.cpu().numpy())
+    assert (E.status_code(st1) == E.STATUS_OPTIMAL).all()
+
+
 def test_device_record_builder_is_byte_exact(oracle, cuda_engine_factory):
     """SURVEY 8f N1 + N2: records built on the device from tick records equal the oracle's restatement of the
     reference's host code (ConvexMPCLocomotion.cpp:498-640, Gait.cpp:142-166) byte for byte, and solving the

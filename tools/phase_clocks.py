@@ -24,6 +24,16 @@ torch.cuda.synchronize()
 c = buf.cpu().numpy()
 d = np.diff(c[:, :5], axis=1)
 names = ["assemble", "invert", "active_set", "scatter+sync"]
+# optional 4th argument: only problems with more than that many reduced variables (e.g. the catch-all class)
+if len(sys.argv) > 4:
+    from quadruped_ctrl_b200 import records as R
+    rec_h = W.CONFIGS[name](B)
+    go = R.gait_offset(h)
+    nvv = 3 * (rec_h[:, go:go + 4 * h] > 0).sum(1)
+    keep = nvv > int(sys.argv[4])
+    c = c[keep]
+    d = d[keep]
+    print("filtered to %d problems with nv > %s" % (keep.sum(), sys.argv[4]))
 print("%s B=%d: cycles per problem per CTA (median / mean / p95)" % (name, B))
 for i, n in enumerate(names):
     print("  %-14s %8.0f %8.0f %8.0f" % (n, np.median(d[:, i]), d[:, i].mean(), np.percentile(d[:, i], 95)))
