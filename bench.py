@@ -47,12 +47,16 @@ def load_peaks():
 
 
 def load_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    """(dram bytes per launch, on-chip pipe figures) of the dominant kernel from the committed ncu capture
+    (profiles/roofline_traffic.json), or (None, None)."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f).get("dram_bytes_per_launch")
-    return None
+            d = json.load(f)
+        return d.get("dram_bytes_per_launch"), {"fp64_pipe_pct_of_peak": d.get("fp64_pipe_pct_of_peak"),
+                                                "issue_slots_pct_of_peak": d.get("issue_slots_pct_of_peak"),
+                                                "source": d.get("source")}
+    return None, None
 
 
 class ClockSampler:
@@ -309,6 +313,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = load_peaks()
+        traffic, on_chip = load_traffic()
         alg_bytes = R.algorithmic_bytes(h) * B
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         line = {
@@ -330,7 +335,7 @@ def run_ours(args):
                     "api": "mpc_batch_submit_host / mpc_batch_wait_host (two slots, pinned host buffers)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(), "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src, "on_chip": on_chip,
                          "kernel": "mpc_solve_kernel<128> (size class nv<=60)", "kernel_ms": k_ms, "kernel_launches_timed": k_n,
                          "kernel_ms_in_timed_region": k_ms_timed,
                          "algorithmic_bytes_per_solve": R.algorithmic_bytes(h),

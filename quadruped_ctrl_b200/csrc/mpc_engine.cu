@@ -85,37 +85,49 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 // One thread per problem: counts the stance (step,leg) pairs of its gait table (16-byte loads: the table starts
-// 16-byte aligned inside the record), picks the size class and appends the problem to that class's list.  Also
-// zeroes the OTHER parity's counters for the next solve, so no memset sits between solves.
+// 16-byte aligned inside the record), picks the size class and appends the problem to that class's list (one
+// atomic per warp and class).  Also zeroes the OTHER parity's counters for the next solve, so no memset sits
+// between solves.
 __global__ void mpc_classify_kernel(const char* records, unsigned long long stride, int h, int batch, int n_classes,
                                     const int* __restrict__ class_cap, int* lists, int* counts, int* counts_next,
                                     int max_batch) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < kMaxClasses) counts_next[b] = 0;
-  if (b >= batch) return;
-  const float* rec = (const float*)(records + stride * b);
-  const float fmax = rec[MPC_REC_FMAX];
-  const uint4* g4 = (const uint4*)((const char*)rec + 4 * (MPC_REC_TRAJ + 12 * h));
-  const int nbytes = 4 * h;
-  int ns = 0;
-  for (int q = 0; q * 16 < nbytes; q++) {
-    const uint4 v = g4[q];  // bytes past 4h are the record's zero padding (stride is rounded up to 16)
-    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+  int c = -1;  // -1: no problem behind this thread
+  if (b < batch) {
+    const float* rec = (const float*)(records + stride * b);
+    const float fmax = rec[MPC_REC_FMAX];
+    const uint4* g4 = (const uint4*)((const char*)rec + 4 * (MPC_REC_TRAJ + 12 * h));
+    const int nbytes = 4 * h;
+    int ns = 0;
+    for (int q = 0; q * 16 < nbytes; q++) {
+      const uint4 v = g4[q];  // bytes past 4h are the record's zero padding (stride is rounded up to 16)
+      const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+      for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        if (q * 16 + i * 4 + e < nbytes) {
-          const float ub = (float)((w[i] >> (8 * e)) & 0xffu) * fmax;
-          ns += !((double)ub < 0.01 && (double)ub > -0.01);
+        for (int e = 0; e < 4; e++) {
+          if (q * 16 + i * 4 + e < nbytes) {
+            const float ub = (float)((w[i] >> (8 * e)) & 0xffu) * fmax;
+            ns += !((double)ub < 0.01 && (double)ub > -0.01);
+          }
         }
-      }
+    }
+    const int nv = 3 * ns;
+    c = 0;
+    while (c < n_classes - 1 && nv > class_cap[c]) c++;
   }
-  const int nv = 3 * ns;
-  int c = 0;
-  while (c < n_classes - 1 && nv > class_cap[c]) c++;
-  const int slot = atomicAdd(&counts[c], 1);
-  lists[c * max_batch + slot] = b;
+  // one atomic per warp and class instead of one per problem (4096 atomics on one counter were most of this kernel)
+  const unsigned lane = threadIdx.x & 31u;
+  for (int cc = 0; cc < n_classes; cc++) {
+    const unsigned m = __ballot_sync(0xffffffffu, c == cc);
+    if (m == 0) continue;  // uniform
+    int base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(&counts[cc], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (c == cc) lists[cc * max_batch + base + __popc(m & ((1u << lane) - 1u))] = b;
+  }
 }
 
 // Tick records -> problem records, one robot per thread (SURVEY 8f N1 + N2; body in mpc_ticks.h).
