@@ -198,7 +198,8 @@ def run_ours(args):
     peer = world > 1 and args.gather == "peer"
     if peer:  # fused: the solve kernel stores every force straight into all ranks' gather buffers over NVLink
         gathered = eng.setup_peer_gather(world * B, rank * B)
-    overlap = not peer and not args.serial
+        gathered2 = eng.gather_views   # one region per scratch slot
+    overlap = not args.serial
 
     def step(i):
         q = (i & 1) if overlap else 0
@@ -206,7 +207,10 @@ def run_ours(args):
             with torch.cuda.stream(streams[q]):
                 eng.solve_device(dev_sets[i % n_sets], forces=forces2[q], status=status2[q], stream=streams[q], slot=q)
                 if world > 1:
-                    dist.all_gather_into_tensor(gathered2[q], forces2[q])
+                    if peer:
+                        eng.gather_sync(stream=streams[q], slot=q)  # device-side flag exchange over NVLink
+                    else:
+                        dist.all_gather_into_tensor(gathered2[q], forces2[q])
             return
         eng.solve_device(dev_sets[i % n_sets], forces=forces, status=status)
         if world > 1:

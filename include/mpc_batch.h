@@ -201,11 +201,19 @@ int mpc_batch_gather_alloc(mpc_batch_t* eng, int world_batch, void* ipc_handle_o
 int mpc_batch_gather_connect(mpc_batch_t* eng, const void* ipc_handles, int world, int rank,
                              int rank_offset);
 void* mpc_batch_gather_buffer(mpc_batch_t* eng);
+/* The gather buffer exists once per scratch slot (mpc_batch_solve_device_slot): a solve on slot q stores into
+ * every rank's slot-q region and is followed by mpc_batch_gather_sync_slot(q), so two batches can be in flight. */
+void* mpc_batch_gather_buffer_slot(mpc_batch_t* eng, int slot);
 /* The cross-rank barrier of the fused gather, on the device: queued on `cuda_stream` after a solve,
  * it tells every peer (a release store into its flag word over NVLink) that this rank's rows have
  * landed and waits until every peer has said the same here.  Work queued behind it on the stream
- * sees the complete gather buffer.  Every rank must call it once per solve. */
+ * sees the complete gather buffer.  Every rank must call it once per solve.
+ * The hand-shake orders the stores BEFORE the reads.  The other direction is the caller's: a rank must not start
+ * its next solve on a slot while some rank still reads that slot's region -- any cross-rank barrier after the reads
+ * does (one more gather_sync on the slot is such a barrier), or alternate the two slots and consume a region before
+ * the solve after next is queued. */
 int mpc_batch_gather_sync(mpc_batch_t* eng, void* cuda_stream);
+int mpc_batch_gather_sync_slot(mpc_batch_t* eng, int slot, void* cuda_stream);
 
 /* Iteration cap of the active-set loop (working-set additions); default 4000.
  * The reference caps qpOASES at nWSR = 100 (SolverMPC.cpp:435) and returns stale

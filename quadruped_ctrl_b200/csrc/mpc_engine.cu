@@ -140,17 +140,16 @@ __global__ void mpc_build_records_kernel(const float* ticks, int batch, int h, c
 }
 
 // Device-side barrier of the fused gather: after this rank's solve kernels have completed (stream order), tell every
-// peer "my rows of epoch E have landed" through its flag word, then wait until every peer has said the same here.
-__global__ void mpc_gather_signal_kernel(unsigned* const* peer_flags, int world, int rank, unsigned epoch) {
-  const int q = threadIdx.x;
-  if (q < world && peer_flags[q]) {
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[q] + rank), "r"(epoch) : "memory");
-  }
-}
-__global__ void mpc_gather_wait_kernel(const unsigned* my_flags, int world, unsigned epoch) {
+// peer "my rows of epoch E have landed" through its flag word, then wait until every peer has said the same here
+// (each lane signals before it waits, so the ranks cannot dead-lock each other).
+__global__ void mpc_gather_barrier_kernel(unsigned* const* peer_flags, const unsigned* my_flags, int world, int rank,
+                                          unsigned epoch) {
   const int q = threadIdx.x;
   if (q < world) {
+    if (peer_flags[q]) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[q] + rank), "r"(epoch) : "memory");
+    }
     unsigned v;
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + q) : "memory");
@@ -335,11 +334,14 @@ struct mpc_batch {
   int max_iter = 4000;
   float* peers[kMaxPeers] = {nullptr};
   int n_peers = 0, rank_offset = 0;
-  float* gather_buf = nullptr;   // [gather_rows*12] fp32 forces, then kMaxPeers flag words (one per rank)
+  // fused gather: one region per scratch slot, each [gather_rows*12] fp32 forces followed by kMaxPeers flag words
+  // (one per rank); slot q's region starts gather_slot_bytes * q into every rank's buffer
+  float* gather_buf = nullptr;
+  size_t gather_slot_bytes = 0;
   int gather_rows = 0;
   int gather_world = 0, gather_rank = 0;
-  unsigned gather_epoch = 0;
-  unsigned** peer_flags_dev = nullptr;
+  unsigned gather_epoch[2] = {0, 0};
+  unsigned** peer_flags_dev = nullptr;  // [2][kMaxPeers]
   long long* phase_clk = nullptr;
   int ctas_per_sm_limit = 0;
   int debug_stop = 0;
@@ -470,8 +472,8 @@ int build_classes(mpc_batch* eng) {
   return MPC_OK;
 }
 
-void fill_params(const mpc_batch* eng, SolveParams& P, const void* records, int batch, float* forces, double* solution,
-                 int32_t* status) {
+void fill_params(const mpc_batch* eng, int slot, SolveParams& P, const void* records, int batch, float* forces,
+                 double* solution, int32_t* status) {
   memset(&P, 0, sizeof(P));
   P.records = (const char*)records;
   P.stride = eng->stride;
@@ -486,7 +488,8 @@ void fill_params(const mpc_batch* eng, SolveParams& P, const void* records, int 
   P.debug_stop = eng->debug_stop;
   P.n_peers = eng->n_peers;
   P.rank_offset = eng->rank_offset;
-  for (int q = 0; q < kMaxPeers; q++) P.peers[q] = eng->peers[q];
+  for (int q = 0; q < kMaxPeers; q++)
+    P.peers[q] = eng->peers[q] ? (float*)((char*)eng->peers[q] + eng->gather_slot_bytes * (size_t)slot) : nullptr;
 }
 
 int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int grid, cudaStream_t st) {
@@ -515,7 +518,7 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
   for (int ci = 0; ci < nc; ci++) {
     const ClassCfg& c = eng->classes[ci];
     SolveParams P;
-    fill_params(eng, P, records, batch, forces, solution, status);
+    fill_params(eng, slot, P, records, batch, forces, solution, status);
     P.list = S.lists + (size_t)ci * eng->max_batch;
     P.count = counts + ci;
     P.L = c.L;
@@ -531,14 +534,14 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
     P.nvar_out = nvar_out;
     P.H_out = H_out;
     P.g_out = g_out;
-    const size_t slot = (size_t)(eng->ring_pos % kRing) * kMaxClasses + ci;
+    const size_t ring = (size_t)(eng->ring_pos % kRing) * kMaxClasses + ci;
     const bool time_this = eng->timed && (eng->timed_class < 0 || eng->timed_class == ci);
-    if (time_this) CK(cudaEventRecord(eng->ring0[slot], st));
+    if (time_this) CK(cudaEventRecord(eng->ring0[ring], st));
     int grid = std::min(c.grid, batch);
     if (eng->ctas_per_sm_limit > 0) grid = std::min(grid, eng->ctas_per_sm_limit * eng->sms);
     int rc = launch_solve(eng, c, P, grid, st);
     if (rc) return rc;
-    if (time_this) CK(cudaEventRecord(eng->ring1[slot], st));
+    if (time_this) CK(cudaEventRecord(eng->ring1[ring], st));
   }
   if (time_all) CK(cudaEventRecord(eng->ev1, st));
   if (eng->timed) eng->ring_pos++;
@@ -810,7 +813,8 @@ int mpc_batch_gather_alloc(mpc_batch_t* eng, int world_batch, void* ipc_handle_o
   CK(cudaSetDevice(eng->device));
   if (eng->gather_buf) CK(cudaFree(eng->gather_buf));
   eng->gather_buf = nullptr;
-  const size_t bytes = (size_t)world_batch * 12 * sizeof(float) + kMaxPeers * sizeof(unsigned);
+  eng->gather_slot_bytes = ((size_t)world_batch * 12 * sizeof(float) + kMaxPeers * sizeof(unsigned) + 255) / 256 * 256;
+  const size_t bytes = 2 * eng->gather_slot_bytes;  // one region per scratch slot
   CK(cudaMalloc(&eng->gather_buf, bytes));
   CK(cudaMemset(eng->gather_buf, 0, bytes));
   eng->gather_rows = world_batch;
@@ -838,30 +842,40 @@ int mpc_batch_gather_connect(mpc_batch_t* eng, const void* ipc_handles, int worl
     eng->peer_open[q] = ptr;
     peers[q] = (float*)ptr;
   }
-  unsigned* flags[kMaxPeers] = {nullptr};
-  for (int q = 0; q < world; q++) flags[q] = (unsigned*)(peers[q] + (size_t)eng->gather_rows * 12);
+  unsigned* flags[2][kMaxPeers] = {{nullptr}};
+  for (int sl = 0; sl < 2; sl++)
+    for (int q = 0; q < world; q++)
+      flags[sl][q] = (unsigned*)((char*)peers[q] + eng->gather_slot_bytes * sl) + (size_t)eng->gather_rows * 12;
   if (!eng->peer_flags_dev) CK(cudaMalloc(&eng->peer_flags_dev, sizeof(flags)));
   CK(cudaMemcpy(eng->peer_flags_dev, flags, sizeof(flags), cudaMemcpyHostToDevice));
   eng->gather_world = world;
   eng->gather_rank = rank;
-  eng->gather_epoch = 0;
+  eng->gather_epoch[0] = eng->gather_epoch[1] = 0;
   return mpc_batch_set_gather_peers(eng, peers, world, rank_offset);
 }
 
-int mpc_batch_gather_sync(mpc_batch_t* eng, void* cuda_stream) {
-  if (!eng || !eng->peer_flags_dev || eng->gather_world < 1) return MPC_E_ARG;
+int mpc_batch_gather_sync_slot(mpc_batch_t* eng, int slot, void* cuda_stream) {
+  if (!eng || slot < 0 || slot > 1 || !eng->peer_flags_dev || eng->gather_world < 1) return MPC_E_ARG;
   CK(cudaSetDevice(eng->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  const unsigned epoch = ++eng->gather_epoch;
-  mpc_gather_signal_kernel<<<1, 32, 0, st>>>(eng->peer_flags_dev, eng->gather_world, eng->gather_rank, epoch);
-  mpc_gather_wait_kernel<<<1, 32, 0, st>>>((const unsigned*)(eng->gather_buf + (size_t)eng->gather_rows * 12),
-                                           eng->gather_world, epoch);
-  eng->launches += 2;
+  const unsigned epoch = ++eng->gather_epoch[slot];
+  const unsigned* my_flags =
+      (const unsigned*)((const char*)eng->gather_buf + eng->gather_slot_bytes * slot) + (size_t)eng->gather_rows * 12;
+  // one launch: lane q tells rank q "my rows of this epoch have landed", then waits for rank q's word here
+  mpc_gather_barrier_kernel<<<1, 32, 0, st>>>(eng->peer_flags_dev + (size_t)slot * kMaxPeers, my_flags,
+                                              eng->gather_world, eng->gather_rank, epoch);
+  eng->launches += 1;
   CK(cudaGetLastError());
   return MPC_OK;
 }
 
+int mpc_batch_gather_sync(mpc_batch_t* eng, void* cuda_stream) { return mpc_batch_gather_sync_slot(eng, 0, cuda_stream); }
+
 void* mpc_batch_gather_buffer(mpc_batch_t* eng) { return eng ? eng->gather_buf : nullptr; }
+void* mpc_batch_gather_buffer_slot(mpc_batch_t* eng, int slot) {
+  if (!eng || !eng->gather_buf || slot < 0 || slot > 1) return nullptr;
+  return (char*)eng->gather_buf + eng->gather_slot_bytes * slot;
+}
 
 int mpc_batch_set_max_iterations(mpc_batch_t* eng, int max_iter) {
   if (!eng || max_iter < 1) return MPC_E_ARG;

@@ -26,7 +26,7 @@ BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_creat
                  "mpc_batch_solve_device", "mpc_batch_solve_device_slot", "mpc_batch_solve_host", "mpc_batch_submit_host", "mpc_batch_wait_host",
                  "mpc_batch_assemble_device", "mpc_batch_build_records_device", "mpc_batch_solve_ticks_device",
                  "mpc_batch_set_gather_peers", "mpc_batch_gather_alloc", "mpc_batch_gather_connect",
-                 "mpc_batch_gather_buffer", "mpc_batch_gather_sync", "mpc_batch_set_max_iterations", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
+                 "mpc_batch_gather_buffer", "mpc_batch_gather_buffer_slot", "mpc_batch_gather_sync", "mpc_batch_gather_sync_slot", "mpc_batch_set_max_iterations", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
                  "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
                  "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_class_kernel_ms", "mpc_batch_timing_mark",
                  "mpc_batch_timing_collect", "mpc_batch_host_buffers",
@@ -70,6 +70,9 @@ def lib():
     L.mpc_batch_destroy.restype = None
     L.mpc_batch_solve_device.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.mpc_batch_solve_device_slot.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp]
+    L.mpc_batch_gather_buffer_slot.argtypes = [vp, i32]
+    L.mpc_batch_gather_buffer_slot.restype = vp
+    L.mpc_batch_gather_sync_slot.argtypes = [vp, i32, vp]
     L.mpc_batch_solve_host.argtypes = [vp, vp, i32, vp, vp, vp]
     L.mpc_batch_submit_host.argtypes = [vp, i32, vp, i32, i32]
     L.mpc_batch_wait_host.argtypes = [vp, i32, vp, vp, vp]
@@ -245,19 +248,26 @@ class MpcBatch:
         blob = allh.cpu().numpy().tobytes()
         self._check(self._L.mpc_batch_gather_connect(self._h, blob, world, rank, int(rank_offset)),
                     "mpc_batch_gather_connect")
-        ptr = self._L.mpc_batch_gather_buffer(self._h)
+        self._gather_keepalive = []
+        views = []
+        for slot in (0, 1):
+            ptr = self._L.mpc_batch_gather_buffer_slot(self._h, slot)
 
-        class _Buf:
-            __cuda_array_interface__ = {"shape": (int(world_batch), 12), "typestr": "<f4", "data": (int(ptr), False),
-                                        "version": 2, "strides": None}
-        self._gather_keepalive = _Buf()
-        return torch.as_tensor(self._gather_keepalive, device=torch.device("cuda", self.device))
+            class _Buf:
+                __cuda_array_interface__ = {"shape": (int(world_batch), 12), "typestr": "<f4",
+                                            "data": (int(ptr), False), "version": 2, "strides": None}
+            self._gather_keepalive.append(_Buf())
+            views.append(torch.as_tensor(self._gather_keepalive[-1], device=torch.device("cuda", self.device)))
+        self.gather_views = views   # one [world_batch, 12] view per scratch slot
+        return views[0]
 
-    def gather_sync(self, stream=None):
-        """Device-side cross-rank barrier of the fused gather, queued on `stream` (default: current)."""
+    def gather_sync(self, stream=None, slot=0):
+        """Device-side cross-rank barrier of the fused gather for scratch slot `slot`, queued on `stream`
+        (default: current)."""
         torch = _torch()
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
-        self._check(self._L.mpc_batch_gather_sync(self._h, st.cuda_stream), "mpc_batch_gather_sync")
+        self._check(self._L.mpc_batch_gather_sync_slot(self._h, int(slot), st.cuda_stream),
+                    "mpc_batch_gather_sync_slot")
 
     # ---- solves ---------------------------------------------------------------------------
     def solve_device(self, records, forces=None, solution=None, status=None, want_solution=False,

@@ -32,7 +32,27 @@ for rep in range(5):  # several epochs: the device-side barrier must order every
     torch.cuda.synchronize()
     ok = ok and bool(torch.equal(snap, ref_r))
     dist.barrier()              # nobody starts the next epoch's stores before everyone has snapshotted
-print("rank %d: peer-store gather %s NCCL all-gather (%d rows)" % (rank, "==" if ok else "!=", world * B), flush=True)
+# both scratch slots, two batches in flight: slot q's solve stores into every rank's slot-q region
+streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+for pair in range(3):
+    snaps, refs = [], []
+    for q in (0, 1):
+        rec_r = torch.from_numpy(W.config2(B, h, 900 + rank + 10 * (2 * pair + q))).to(dev)
+        torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(streams[q]):
+            f_r, _, _ = eng.solve_device(rec_r, stream=streams[q], slot=q)
+            eng.gather_sync(stream=streams[q], slot=q)
+            snaps.append(eng.gather_views[q].clone())
+        refs.append(f_r)
+    torch.cuda.synchronize()
+    for q in (0, 1):
+        ref_r = torch.empty_like(ref)
+        dist.all_gather_into_tensor(ref_r, refs[q])
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(snaps[q], ref_r))
+    dist.barrier()
+print("rank %d: peer-store gather %s NCCL all-gather (%d rows, both slots)" % (rank, "==" if ok else "!=", world * B),
+      flush=True)
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 eng.close()
