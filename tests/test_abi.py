@@ -147,3 +147,32 @@ def test_legacy_calls_pack_the_same_record_as_the_batch_packer(lib):
                                          f["gait"][b].astype(np.int32))
             assert (I.legacy_record(h) == rec[b]).all(), (h, b)
     I.set_robot([0.07, 0.26, 0.242], 9.0)
+
+
+def _build_caller_stub():
+    """g++-compiles tests/caller/solve_dense_mpc_stub.cpp against include/ and links it to the product library."""
+    src = os.path.join(ROOT, "tests", "caller", "solve_dense_mpc_stub.cpp")
+    exe = os.path.join(tempfile.gettempdir(), "solve_dense_mpc_stub_%d" % os.getpid())
+    libdir = os.path.dirname(E.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-I", INC, src, "-o", exe,
+                           "-L", libdir, "-l:" + os.path.basename(E.LIB_PATH), "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_caller_with_the_reference_call_sequence_links_and_runs(lib):
+    """SURVEY 8b link test: a C++14 caller (the reference's flags: -Wall -Wextra -Werror) issuing the call sequence
+    of ConvexMPCLocomotion::solveDenseMPC compiles against our header, links against the library -- including the
+    C++-linkage update_x_drag -- and runs.  Without a GPU every solve must fail loudly (status < 0, forces 0)."""
+    import torch
+    exe = _build_caller_stub()
+    try:
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    finally:
+        os.unlink(exe)
+    assert r.returncode == 0, r.stderr
+    lines = [l.split() for l in r.stdout.splitlines() if l.startswith("h ")]
+    assert [int(l[1]) for l in lines] == [10, 14, 10]
+    if not torch.cuda.is_available():
+        for l in lines:
+            assert int(l[3]) < 0 and all(float(x) == 0.0 for x in l[5:17])
+        assert "no" in r.stderr.lower() or "cuda" in r.stderr.lower()

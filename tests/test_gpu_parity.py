@@ -140,6 +140,42 @@ def test_legacy_interface_matches_oracle(oracle):
     I.shutdown()
 
 
+def test_cpp_caller_stub_matches_oracle(oracle):
+    """SURVEY 8b link test on the GPU: the C++ caller with the reference's call sequence
+    (tests/caller/solve_dense_mpc_stub.cpp, linked against the library) gets the oracle's forces."""
+    import subprocess
+    from quadruped_ctrl_b200 import records as R
+    from test_abi import _build_caller_stub
+    exe = _build_caller_stub()
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    finally:
+        os.unlink(exe)
+    assert out.returncode == 0, out.stderr
+    lines = [l.split() for l in out.stdout.splitlines() if l.startswith("h ")]
+    assert len(lines) == 3
+    foot = np.array([[0.19, -0.111, 0], [0.19, 0.111, 0], [-0.19, -0.111, 0], [-0.19, 0.111, 0]], np.float32)
+    for l, (h, vx) in zip(lines, ((10, 0.5), (14, 0.5), (10, 0.3))):
+        assert int(l[1]) == h and int(l[3]) == 0
+        got = np.array([float(x) for x in l[5:17]])
+        p = np.array([0, 0, 0.29], np.float32)
+        traj = np.zeros((h, 12), np.float32)
+        dt = np.float32(0.002) * np.float32(13)
+        for i in range(h):
+            traj[i, 3] = p[0] + dt * np.float32(i) * np.float32(vx)
+            traj[i, 5], traj[i, 9] = 0.25, vx
+        gait = np.zeros((h, 4), np.uint8)
+        for i in range(h):
+            a = 1 if i < h // 2 else 0
+            gait[i] = (a, 1 - a, 1 - a, a)
+        r = (foot - p[None, :]).T.reshape(-1)   # r[axis*4+leg]
+        rec = R.pack_records(h, p=p[None], v=np.array([[vx, 0, 0]], np.float32), q=np.array([[1, 0, 0, 0]], np.float32),
+                             w=np.zeros((1, 3), np.float32), r=r[None].astype(np.float32), yaw=np.zeros(1, np.float32),
+                             traj=traj.reshape(1, -1), gait=gait.reshape(1, -1), dt=np.array([dt], np.float32))
+        ref = oracle.solve_batch(rec, h, 64)
+        assert rel(got[None], ref["forces"][:1].astype(np.float64))[0] < 1e-6
+
+
 def test_status_codes_and_failure_outputs(cuda_engine_factory):
     from quadruped_ctrl_b200 import records as R
     h = 10
