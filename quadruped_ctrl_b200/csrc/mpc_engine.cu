@@ -308,6 +308,9 @@ struct mpc_batch {
   struct Slot {
     cudaStream_t stream = nullptr;
     char* rec_dev = nullptr;
+    char* out_dev = nullptr;   // forces_dev | status_dev | sol_dev (one allocation)
+    char* out_pin = nullptr;   // the same layout in page-locked host memory
+    size_t out_bytes = 0;
     float* forces_dev = nullptr;
     double* sol_dev = nullptr;
     int32_t* status_dev = nullptr;
@@ -321,6 +324,7 @@ struct mpc_batch {
     char* slab = nullptr;   // per-CTA global workspace of the catch-all class
     int pending_batch = 0;
     bool pending_solution = false;
+    int pending_single_class = -1;  // >= 0: the pending solve was host-classified (batch of one)
   } s[2];
   int* caps_dev = nullptr;
   std::vector<ClassCfg> classes;
@@ -345,6 +349,7 @@ struct mpc_batch {
   long long* phase_clk = nullptr;
   int ctas_per_sm_limit = 0;
   int debug_stop = 0;
+  bool no_host_classify = false;  // env MPC_NO_HOST_CLASSIFY: batches of one take the general path too
   void* peer_open[kMaxPeers] = {nullptr};
   std::string err;
 };
@@ -500,11 +505,26 @@ int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int gr
   return MPC_OK;
 }
 
+// single_class >= 0: the caller has classified the batch on the host (every problem belongs to that class): no
+// classify kernel, no empty-class launches, identity list.  Used by the host entry for a batch of one -- the legacy
+// single-robot tick -- where launch overhead, not the solve, is most of the latency.  A working set that outgrows the
+// class's tile cannot be re-queued on this path; it comes back as MAX_ITER with few iterations and the host entry
+// repeats the solve on the general path.
 int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, float* forces, double* solution,
-                    int32_t* status, cudaStream_t st, int32_t* nvar_out, double* H_out, double* g_out) {
+                    int32_t* status, cudaStream_t st, int32_t* nvar_out, double* H_out, double* g_out,
+                    int single_class = -1) {
   if (batch == 0) return MPC_OK;
   const int nc = (int)eng->classes.size();
   mpc_batch::Slot& S = eng->s[slot];
+  if (single_class >= 0) {
+    const ClassCfg& c = eng->classes[single_class];
+    SolveParams P;
+    fill_params(eng, slot, P, records, batch, forces, solution, status);
+    P.L = c.L;
+    P.warp_mode = c.variant == V_64 ? 1 : 0;
+    P.slab = c.in_fast ? nullptr : S.slab;
+    return launch_solve(eng, c, P, std::min(c.grid, batch), st);
+  }
   // class counters are double-buffered by solve parity: this solve's classify kernel zeroes the other set
   int* counts = S.counts + (S.parity ? kMaxClasses : 0);
   int* counts_next = S.counts + (S.parity ? 0 : kMaxClasses);
@@ -588,6 +608,7 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
     }                                                                   \
   } while (0)
   if (const char* ds = getenv("MPC_DEBUG_STOP")) eng->debug_stop = atoi(ds);
+  eng->no_host_classify = getenv("MPC_NO_HOST_CLASSIFY") != nullptr;
   eng->device = device;
   eng->h = horizon;
   eng->max_batch = max_batch;
@@ -610,13 +631,19 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
     mpc_batch::Slot& S = eng->s[q];
     CKC(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
     CKC(cudaMalloc(&S.rec_dev, B * eng->stride));
-    CKC(cudaMalloc(&S.forces_dev, B * 12 * sizeof(float)));
-    CKC(cudaMalloc(&S.sol_dev, B * NU * sizeof(double)));
-    CKC(cudaMalloc(&S.status_dev, B * sizeof(int32_t)));
+    // forces | status | solution in ONE block per side, so that a small batch's results come back in one copy
+    const size_t off_st = (B * 12 * sizeof(float) + 15) / 16 * 16;
+    const size_t off_sol = (off_st + B * sizeof(int32_t) + 15) / 16 * 16;
+    S.out_bytes = off_sol + B * NU * sizeof(double);
+    CKC(cudaMalloc(&S.out_dev, S.out_bytes));
+    S.forces_dev = (float*)S.out_dev;
+    S.status_dev = (int32_t*)(S.out_dev + off_st);
+    S.sol_dev = (double*)(S.out_dev + off_sol);
     CKC(cudaMallocHost(&S.rec_pin, B * eng->stride));
-    CKC(cudaMallocHost(&S.forces_pin, B * 12 * sizeof(float)));
-    CKC(cudaMallocHost(&S.sol_pin, B * NU * sizeof(double)));
-    CKC(cudaMallocHost(&S.status_pin, B * sizeof(int32_t)));
+    CKC(cudaMallocHost(&S.out_pin, S.out_bytes));
+    S.forces_pin = (float*)S.out_pin;
+    S.status_pin = (int32_t*)(S.out_pin + off_st);
+    S.sol_pin = (double*)(S.out_pin + off_sol);
     CKC(cudaMalloc(&S.lists, sizeof(int) * kMaxClasses * B));
     CKC(cudaMalloc(&S.counts, sizeof(int) * 2 * kMaxClasses));
     CKC(cudaMemset(S.counts, 0, sizeof(int) * 2 * kMaxClasses));
@@ -641,13 +668,9 @@ void mpc_batch_destroy(mpc_batch_t* eng) {
   for (int q = 0; q < 2; q++) {
     mpc_batch::Slot& S = eng->s[q];
     cudaFree(S.rec_dev);
-    cudaFree(S.forces_dev);
-    cudaFree(S.sol_dev);
-    cudaFree(S.status_dev);
+    cudaFree(S.out_dev);
     cudaFreeHost(S.rec_pin);
-    cudaFreeHost(S.forces_pin);
-    cudaFreeHost(S.sol_pin);
-    cudaFreeHost(S.status_pin);
+    cudaFreeHost(S.out_pin);
     cudaFree(S.lists);
     cudaFree(S.counts);
     cudaFree(S.slab);
@@ -719,9 +742,27 @@ int mpc_batch_submit_host(mpc_batch_t* eng, int slot, const void* records_host, 
       CK(cudaMemcpyAsync(S.rec_dev + off, S.rec_pin + off, n, cudaMemcpyHostToDevice, S.stream));
     }
   }
+  int single = -1;
+  if (batch == 1 && !eng->no_host_classify && !eng->phase_clk && !eng->debug_stop) {
+    // the reference's near-zero test on gait * f_max (SolverMPC.cpp:441-469), as in mpc_classify_kernel
+    const float* rec = (const float*)records_host;
+    const unsigned char* gait = (const unsigned char*)records_host + mpc_record_gait_offset(eng->h);
+    int ns = 0;
+    for (int q = 0; q < 4 * eng->h; q++) {
+      const float ub = (float)gait[q] * rec[MPC_REC_FMAX];
+      ns += !((double)ub < 0.01 && (double)ub > -0.01);
+    }
+    single = 0;
+    while (single < (int)eng->classes.size() - 1 && 3 * ns > eng->classes[single].nv_cap) single++;
+  }
+  S.pending_single_class = single;
   int rc = solve_on_stream(eng, slot, S.rec_dev, batch, S.forces_dev, want_solution ? S.sol_dev : nullptr, S.status_dev,
-                           S.stream, nullptr, nullptr, nullptr);
+                           S.stream, nullptr, nullptr, nullptr, single);
   if (rc) return rc;
+  if (S.out_bytes <= 8192) {  // small engine (the legacy single-robot one): one copy brings everything back
+    CK(cudaMemcpyAsync(S.out_pin, S.out_dev, S.out_bytes, cudaMemcpyDeviceToHost, S.stream));
+    return MPC_OK;
+  }
   CK(cudaMemcpyAsync(S.forces_pin, S.forces_dev, (size_t)batch * 12 * sizeof(float), cudaMemcpyDeviceToHost, S.stream));
   if (want_solution)
     CK(cudaMemcpyAsync(S.sol_pin, S.sol_dev, (size_t)batch * NU * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
@@ -744,6 +785,19 @@ int mpc_batch_wait_host(mpc_batch_t* eng, int slot, float* forces_host, double* 
   CK(cudaSetDevice(eng->device));
   CK(cudaStreamSynchronize(S.stream));
   const size_t NU = 12 * (size_t)eng->h;
+  if (S.pending_single_class >= 0 && S.pending_single_class < (int)eng->classes.size() - 1 && batch == 1 &&
+      (S.status_pin[0] & 0xff) == MPC_STATUS_MAX_ITER && (S.status_pin[0] >> 8) < eng->max_iter) {
+    // host-classified solve whose working set outgrew its class's tile: once more on the general path (re-queue)
+    S.pending_single_class = -1;
+    int rc = solve_on_stream(eng, slot, S.rec_dev, 1, S.forces_dev, S.pending_solution ? S.sol_dev : nullptr,
+                             S.status_dev, S.stream, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(S.forces_pin, S.forces_dev, 12 * sizeof(float), cudaMemcpyDeviceToHost, S.stream));
+    if (S.pending_solution)
+      CK(cudaMemcpyAsync(S.sol_pin, S.sol_dev, NU * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaMemcpyAsync(S.status_pin, S.status_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaStreamSynchronize(S.stream));
+  }
   if (forces_host && forces_host != S.forces_pin) memcpy(forces_host, S.forces_pin, (size_t)batch * 12 * sizeof(float));
   if (solution_host && solution_host != S.sol_pin)
     memcpy(solution_host, S.sol_pin, (size_t)batch * NU * sizeof(double));

@@ -243,6 +243,12 @@ def test_working_set_overflow_is_requeued_not_dropped(oracle, cuda_engine_factor
     o = oracle.solve_batch(rec, h, 64, "port")
     assert rel(sol, o["sol"]).max() < 1e-6
     assert E.status_iterations(status).max() > m_cap   # at least one problem really did overflow the tile
+    # batches of one are classified on the host and launch their class's kernel alone (the legacy single-robot
+    # tick); an overflow there is repeated on the general path: same bits as inside the batch
+    worst = int(np.argmax(E.status_iterations(status)))
+    for b in (worst, 0, 1):
+        f1, s1, st1 = eng.solve_host(rec[b:b + 1], want_solution=True)
+        assert np.array_equal(f1[0], forces[b]) and np.array_equal(s1[0], sol[b]) and st1[0] == status[b]
 
 
 def test_pipelined_host_entry_matches_synchronous(cuda_engine_factory):
