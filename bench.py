@@ -280,12 +280,14 @@ def run_ours(args):
     value = world * B * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the host entry: pinned host records -> H2D -> kernels -> D2H, every step.
-    # The two-slot host API is used the way a caller with a stream of batches uses it: submit step i, then
-    # collect step i-1, so one step's transfers overlap the other's kernels.  Every step's inputs come from
+    # The slotted host API is used the way a caller with a stream of batches uses it: submit step i, then
+    # collect step i-2, so one step's transfers and the host's work overlap the other steps' kernels.  Every step's inputs come from
     # pinned host memory and every step's forces + status are read back to the host inside the timed region.
     pinned_sets = [torch.from_numpy(s).pin_memory() for s in host_sets[:8]]
-    out_f = [eng.host_buffers(q)[1] for q in (0, 1)]
-    out_s = [eng.host_buffers(q)[3] for q in (0, 1)]
+    nslots = E.SLOTS
+    depth = nslots - 1          # batches submitted ahead of the one being collected
+    out_f = [eng.host_buffers(q)[1] for q in range(nslots)]
+    out_s = [eng.host_buffers(q)[3] for q in range(nslots)]
     checksum = [0.0]
 
     def collect(slot):
@@ -297,10 +299,11 @@ def run_ours(args):
 
     def e2e_run(n):
         for i in range(n):
-            eng.submit_host(i & 1, pinned_sets[i % len(pinned_sets)].numpy())
-            if i > 0:
-                collect((i - 1) & 1)
-        collect((n - 1) & 1)
+            eng.submit_host(i % nslots, pinned_sets[i % len(pinned_sets)].numpy())
+            if i >= depth:
+                collect((i - depth) % nslots)
+        for j in range(max(0, n - depth), n):
+            collect(j % nslots)
         torch.cuda.synchronize()
 
     e2e_run(max(args.warmup, 2 * len(pinned_sets) + 4))   # every pinned set has been through the DMA path once
@@ -320,6 +323,12 @@ def run_ours(args):
         traffic, on_chip = load_traffic()
         alg_bytes = R.algorithmic_bytes(h) * B
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        if on_chip is not None:
+            # secondary figure: fp64 rate of the dominant kernel against the fp64 peak measured on this pool's B200s
+            # with tools/microbench/dfma.cu (36.8 TFLOP/s); every problem of this workload has nv = 60
+            flops = R.algorithmic_flops(h, 60) * B
+            on_chip.update(fp64_tflops_achieved=flops / (k_ms * 1e-3) / 1e12, fp64_tflops_peak_measured=36.8,
+                           algorithmic_fp64_flops_per_solve=R.algorithmic_flops(h, 60))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -336,7 +345,7 @@ def run_ours(args):
                        "classes": classes},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * stride,
                     "d2h_bytes_per_step": B * 48 + B * 4,
-                    "api": "mpc_batch_submit_host / mpc_batch_wait_host (two slots, pinned host buffers)"},
+                    "api": "mpc_batch_submit_host / mpc_batch_wait_host (%d slots, %d batches submitted ahead; page-locked host buffers read in place)" % (nslots, depth)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "on_chip": on_chip,

@@ -136,7 +136,8 @@ int mpc_batch_solve_device(mpc_batch_t* eng, const void* records_dev, int batch,
                            float* forces_dev, double* solution_dev,
                            int32_t* status_dev, void* cuda_stream);
 
-/* The same on scratch slot `slot` (0 or 1).  Two device-resident solves of one engine may overlap when they
+#define MPC_BATCH_SLOTS 3
+/* The same on scratch slot `slot` (0 .. MPC_BATCH_SLOTS-1).  Device-resident solves of one engine may overlap when they
  * use different slots and different streams: the tail of one batch then shares the GPU with the head of the
  * next (independent batches; nothing is exchanged between them). */
 int mpc_batch_solve_device_slot(mpc_batch_t* eng, int slot, const void* records_dev, int batch,
@@ -149,7 +150,7 @@ int mpc_batch_solve_host(mpc_batch_t* eng, const void* records_host, int batch,
                          float* forces_host, double* solution_host,
                          int32_t* status_host);
 
-/* Pipelined host-resident solve.  The engine has two slots (0, 1), each with its own stream, pinned
+/* Pipelined host-resident solve.  The engine has MPC_BATCH_SLOTS slots, each with its own stream, pinned
  * staging and device buffers.  submit stages `records_host` into the slot and queues H2D, kernels and
  * D2H on the slot's stream without waiting for the GPU; wait blocks until that slot is done and copies
  * the results out (pass the slot's own pinned pointers from mpc_batch_host_buffers to skip the copies).
@@ -210,7 +211,7 @@ void* mpc_batch_gather_buffer_slot(mpc_batch_t* eng, int slot);
  * sees the complete gather buffer.  Every rank must call it once per solve.
  * The hand-shake orders the stores BEFORE the reads.  The other direction is the caller's: a rank must not start
  * its next solve on a slot while some rank still reads that slot's region -- any cross-rank barrier after the reads
- * does (one more gather_sync on the slot is such a barrier), or alternate the two slots and consume a region before
+ * does (one more gather_sync on the slot is such a barrier), or rotate over the slots and consume a region before
  * the solve after next is queued. */
 int mpc_batch_gather_sync(mpc_batch_t* eng, void* cuda_stream);
 int mpc_batch_gather_sync_slot(mpc_batch_t* eng, int slot, void* cuda_stream);

@@ -29,6 +29,7 @@
 namespace {
 
 constexpr int kMaxPeers = 8;
+constexpr int kSlots = MPC_BATCH_SLOTS;  // scratch slots per engine: that many batches can be in flight
 constexpr int kMaxClasses = 6;
 constexpr int kRing = 256;
 
@@ -325,7 +326,7 @@ struct mpc_batch {
     int pending_batch = 0;
     bool pending_solution = false;
     int pending_single_class = -1;  // >= 0: the pending solve was host-classified (batch of one)
-  } s[2];
+  } s[kSlots];
   int* caps_dev = nullptr;
   std::vector<ClassCfg> classes;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -344,8 +345,8 @@ struct mpc_batch {
   size_t gather_slot_bytes = 0;
   int gather_rows = 0;
   int gather_world = 0, gather_rank = 0;
-  unsigned gather_epoch[2] = {0, 0};
-  unsigned** peer_flags_dev = nullptr;  // [2][kMaxPeers]
+  unsigned gather_epoch[kSlots] = {0};
+  unsigned** peer_flags_dev = nullptr;  // [kSlots][kMaxPeers]
   long long* phase_clk = nullptr;
   int ctas_per_sm_limit = 0;
   int debug_stop = 0;
@@ -627,7 +628,7 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
   if (rc) return fail(rc);
   const size_t B = (size_t)max_batch, NU = 12 * (size_t)horizon;
   const ClassCfg& big = eng->classes.back();
-  for (int q = 0; q < 2; q++) {
+  for (int q = 0; q < kSlots; q++) {
     mpc_batch::Slot& S = eng->s[q];
     CKC(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
     CKC(cudaMalloc(&S.rec_dev, B * eng->stride));
@@ -665,7 +666,7 @@ void mpc_batch_destroy(mpc_batch_t* eng) {
     if (eng->peer_open[q]) cudaIpcCloseMemHandle(eng->peer_open[q]);
   cudaFree(eng->gather_buf);
   cudaFree(eng->peer_flags_dev);
-  for (int q = 0; q < 2; q++) {
+  for (int q = 0; q < kSlots; q++) {
     mpc_batch::Slot& S = eng->s[q];
     cudaFree(S.rec_dev);
     cudaFree(S.out_dev);
@@ -701,7 +702,7 @@ int mpc_batch_solve_device(mpc_batch_t* eng, const void* records_dev, int batch,
 int mpc_batch_solve_device_slot(mpc_batch_t* eng, int slot, const void* records_dev, int batch, float* forces_dev,
                                 double* solution_dev, int32_t* status_dev, void* cuda_stream) {
   if (!eng) return MPC_E_ARG;
-  if (slot < 0 || slot > 1 || !records_dev || !forces_dev || batch < 0 || batch > eng->max_batch ||
+  if (slot < 0 || slot >= kSlots || !records_dev || !forces_dev || batch < 0 || batch > eng->max_batch ||
       ((uintptr_t)records_dev & 15)) {
     eng->err = "mpc_batch_solve_device_slot: bad argument";
     return MPC_E_ARG;
@@ -713,7 +714,7 @@ int mpc_batch_solve_device_slot(mpc_batch_t* eng, int slot, const void* records_
 
 int mpc_batch_submit_host(mpc_batch_t* eng, int slot, const void* records_host, int batch, int want_solution) {
   if (!eng) return MPC_E_ARG;
-  if (slot < 0 || slot > 1 || !records_host || batch < 0 || batch > eng->max_batch) {
+  if (slot < 0 || slot >= kSlots || !records_host || batch < 0 || batch > eng->max_batch) {
     eng->err = "mpc_batch_submit_host: bad argument";
     return MPC_E_ARG;
   }
@@ -772,7 +773,7 @@ int mpc_batch_submit_host(mpc_batch_t* eng, int slot, const void* records_host, 
 
 int mpc_batch_wait_host(mpc_batch_t* eng, int slot, float* forces_host, double* solution_host, int32_t* status_host) {
   if (!eng) return MPC_E_ARG;
-  if (slot < 0 || slot > 1) {
+  if (slot < 0 || slot >= kSlots) {
     eng->err = "mpc_batch_wait_host: bad slot";
     return MPC_E_ARG;
   }
@@ -868,7 +869,7 @@ int mpc_batch_gather_alloc(mpc_batch_t* eng, int world_batch, void* ipc_handle_o
   if (eng->gather_buf) CK(cudaFree(eng->gather_buf));
   eng->gather_buf = nullptr;
   eng->gather_slot_bytes = ((size_t)world_batch * 12 * sizeof(float) + kMaxPeers * sizeof(unsigned) + 255) / 256 * 256;
-  const size_t bytes = 2 * eng->gather_slot_bytes;  // one region per scratch slot
+  const size_t bytes = kSlots * eng->gather_slot_bytes;  // one region per scratch slot
   CK(cudaMalloc(&eng->gather_buf, bytes));
   CK(cudaMemset(eng->gather_buf, 0, bytes));
   eng->gather_rows = world_batch;
@@ -896,20 +897,20 @@ int mpc_batch_gather_connect(mpc_batch_t* eng, const void* ipc_handles, int worl
     eng->peer_open[q] = ptr;
     peers[q] = (float*)ptr;
   }
-  unsigned* flags[2][kMaxPeers] = {{nullptr}};
-  for (int sl = 0; sl < 2; sl++)
+  unsigned* flags[kSlots][kMaxPeers] = {{nullptr}};
+  for (int sl = 0; sl < kSlots; sl++)
     for (int q = 0; q < world; q++)
       flags[sl][q] = (unsigned*)((char*)peers[q] + eng->gather_slot_bytes * sl) + (size_t)eng->gather_rows * 12;
   if (!eng->peer_flags_dev) CK(cudaMalloc(&eng->peer_flags_dev, sizeof(flags)));
   CK(cudaMemcpy(eng->peer_flags_dev, flags, sizeof(flags), cudaMemcpyHostToDevice));
   eng->gather_world = world;
   eng->gather_rank = rank;
-  eng->gather_epoch[0] = eng->gather_epoch[1] = 0;
+  for (int sl = 0; sl < kSlots; sl++) eng->gather_epoch[sl] = 0;
   return mpc_batch_set_gather_peers(eng, peers, world, rank_offset);
 }
 
 int mpc_batch_gather_sync_slot(mpc_batch_t* eng, int slot, void* cuda_stream) {
-  if (!eng || slot < 0 || slot > 1 || !eng->peer_flags_dev || eng->gather_world < 1) return MPC_E_ARG;
+  if (!eng || slot < 0 || slot >= kSlots || !eng->peer_flags_dev || eng->gather_world < 1) return MPC_E_ARG;
   CK(cudaSetDevice(eng->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const unsigned epoch = ++eng->gather_epoch[slot];
@@ -927,7 +928,7 @@ int mpc_batch_gather_sync(mpc_batch_t* eng, void* cuda_stream) { return mpc_batc
 
 void* mpc_batch_gather_buffer(mpc_batch_t* eng) { return eng ? eng->gather_buf : nullptr; }
 void* mpc_batch_gather_buffer_slot(mpc_batch_t* eng, int slot) {
-  if (!eng || !eng->gather_buf || slot < 0 || slot > 1) return nullptr;
+  if (!eng || !eng->gather_buf || slot < 0 || slot >= kSlots) return nullptr;
   return (char*)eng->gather_buf + eng->gather_slot_bytes * slot;
 }
 
@@ -1006,7 +1007,7 @@ int mpc_batch_timing_collect(mpc_batch_t* eng, int idx, float* mean_ms, int* n_s
 
 int mpc_batch_host_buffers(mpc_batch_t* eng, int slot, void** records, float** forces, double** solution,
                            int32_t** status) {
-  if (!eng || slot < 0 || slot > 1) return MPC_E_ARG;
+  if (!eng || slot < 0 || slot >= kSlots) return MPC_E_ARG;
   mpc_batch::Slot& S = eng->s[slot];
   if (records) *records = S.rec_pin;
   if (forces) *forces = S.forces_pin;

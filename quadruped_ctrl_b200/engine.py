@@ -19,6 +19,7 @@ LIB_PATH = os.environ.get("MPC_LIB_PATH") or os.path.join(_HERE, "libquadruped_m
 _LIB = None
 
 MPC_OK, MPC_E_ARG, MPC_E_CUDA, MPC_E_NOMEM, MPC_E_NODEVICE = 0, -1, -2, -3, -4
+SLOTS = 3  # MPC_BATCH_SLOTS of include/mpc_batch.h: scratch slots per engine (batches that can be in flight)
 STATUS_OPTIMAL, STATUS_MAX_ITER, STATUS_BAD_INPUT, STATUS_NOT_PD, STATUS_NO_STANCE = 0, 1, 2, 3, 4
 
 # every symbol include/mpc_batch.h and include/convexMPC_interface.h declare
@@ -250,7 +251,7 @@ class MpcBatch:
                     "mpc_batch_gather_connect")
         self._gather_keepalive = []
         views = []
-        for slot in (0, 1):
+        for slot in range(SLOTS):
             ptr = self._L.mpc_batch_gather_buffer_slot(self._h, slot)
 
             class _Buf:
@@ -273,7 +274,7 @@ class MpcBatch:
     def solve_device(self, records, forces=None, solution=None, status=None, want_solution=False,
                      want_status=True, stream=None, slot=0):
         """records: cuda uint8 tensor [B, stride] on this engine's device.  Asynchronous on `stream`
-        (default: torch's current stream).  `slot` (0/1) picks the engine's device scratch: two solves may
+        (default: torch's current stream).  `slot` (0..SLOTS-1) picks the engine's device scratch: solves may
         overlap when they use different slots on different streams.  Returns (forces [B,12] f32, solution [B,12h] f64 | None,
         status [B] int32 | None), all cuda tensors."""
         torch = _torch()
@@ -311,7 +312,7 @@ class MpcBatch:
         return forces, sol, status
 
     def submit_host(self, slot, records, want_solution=False):
-        """Queues H2D + kernels + D2H for `records` (numpy uint8 [B, stride]) on slot 0 or 1; returns at once."""
+        """Queues H2D + kernels + D2H for `records` (numpy uint8 [B, stride]) on slot 0..SLOTS-1; returns at once."""
         records = np.ascontiguousarray(records, np.uint8)
         assert records.shape[1] == self.stride
         rc = self._L.mpc_batch_submit_host(self._h, int(slot), records.ctypes.data, records.shape[0],

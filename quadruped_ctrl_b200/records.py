@@ -87,3 +87,15 @@ def unpack_records(rec, horizon):
 def algorithmic_bytes(horizon):
     """Compulsory HBM bytes per solve: inputs 4*(47+12h)+4h, output 48."""
     return 4 * (47 + 12 * horizon) + 4 * horizon + 48
+
+
+def algorithmic_flops(horizon, nv):
+    """fp64 operations per solve of the algorithm the engine runs, for the secondary on-chip
+    figure of the bench line: symmetric sweep inversion nv^3 (nv^3/2 FMAs), closed-form assembly (9 FMAs per entry of
+    the lower triangle + the six 12x12 tables + gradient moments), x = -H^{-1} g riding along (nv^2).  The active-set
+    iterations are data dependent and left out.  The reference's dense route (SolverMPC.cpp:395) would be
+    2*(12h)^2*(13h) = 3744 h^3 for the Hessian alone."""
+    sweep = nv ** 3 + 2 * nv * nv
+    assembly = 18 * (nv * (nv + 1) // 2) + 6 * 2 * 12 * 12 * 12 + 2 * 3 * 12 * horizon * horizon
+    return sweep + assembly
+

@@ -16,20 +16,20 @@ arrs = [s.numpy() for s in sets]
 n = 200
 
 
-def run(depth):
+def run(depth, nslots=E.SLOTS):
     t_sub = t_wait = 0.0
     t0 = time.perf_counter()
     for i in range(n):
         a = time.perf_counter()
-        eng.submit_host(i & 1, arrs[i % 8])
+        eng.submit_host(i % nslots, arrs[i % 8])
         b = time.perf_counter()
         if i >= depth:
-            eng.wait_host((i - depth) & 1)
+            eng.wait_host((i - depth) % nslots)
         c = time.perf_counter()
         t_sub += b - a
         t_wait += c - b
     for j in range(max(0, n - depth), n):
-        eng.wait_host(j & 1)
+        eng.wait_host(j % nslots)
     torch.cuda.synchronize()
     tot = time.perf_counter() - t0
     print("depth %d: %.1f us/step (%.2f M solves/s); host time in submit %.1f us, in wait %.1f us per step"
@@ -38,6 +38,8 @@ def run(depth):
 
 run(1)
 run(1)
+run(2)
+run(2)
 # raw copies for scale
 dev = torch.empty((B, eng.stride), dtype=torch.uint8, device="cuda")
 torch.cuda.synchronize()
