@@ -420,8 +420,7 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
     const int lanes = cx.nt >= 128 ? 32 : 0;  // task t runs on thread 32*t (one per warp); single thread: all on 0
     if (cx.tid == 0 * lanes) {
       const double yaw = (double)rec[MPC_REC_YAW];
-      scr[0] = cos(yaw);
-      scr[1] = sin(yaw);
+      sincos(yaw, &scr[1], &scr[0]);  // one range reduction for both
     }
     if (cx.tid == 1 * lanes) x0[2] = MPC_ATAN2(2. * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
     if (cx.tid == 2 * lanes) {
@@ -516,7 +515,10 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
   // ---- P8: moments mom[a][j][row] = sum_{r>=j} (r-j)^a q_e[r][row] ----
   const int na = (xd != 0.0) ? 3 : 2;  // without drag C2 == 0 and every k^2 term drops out
   MPC_FOR(e, na * 12 * h) {
-    const int a = e / (12 * h), jr = e - a * 12 * h, j = jr / 12, row = jr - 12 * j;
+    int a = 0, jr = e;  // e = a*12h + jr without a division by the run-time 12h
+    if (jr >= 12 * h) { jr -= 12 * h; a = 1; }
+    if (jr >= 12 * h) { jr -= 12 * h; a = 2; }
+    const int j = jr / 12, row = jr - 12 * j;
     double acc = 0;
 #pragma unroll 2
     for (int r = j; r < h; r++) {
@@ -558,27 +560,28 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
     }
     k.g[v] = 2.0 * (acc0 + acc1);
   }
-  // six tables M_ab, a <= b (M_ba = M_ab'); one thread per (table, row): 12 independent accumulators, each
-  // weighted C_a entry loaded once
-  MPC_FOR(e, 6 * 12) {
-    const int tb = e / 12, i = e - 12 * tb;
-    const int a = tb < 3 ? 0 : (tb < 5 ? 1 : 2), b = tb < 3 ? tb : (tb < 5 ? tb - 2 : 2);
-    if (b < na) {  // a <= b
+  // six tables M_ab, a <= b (M_ba = M_ab'), of which only those with b < na are needed (three without drag); one
+  // thread per ENTRY (table, i, j), rows q ascending -- 432 entries over the CTA instead of 36 threads doing a row
+  // of twelve each
+  {
+    const int ntab = na == 2 ? 3 : 6;
+    MPC_FOR(e, ntab * 144) {
+      const int t = e / 144, ij = e - 144 * t, i = ij / 12, j = ij - 12 * i;
+      // na == 2: tables 0 (0,0), 1 (0,1), 3 (1,1);  na == 3: all six in order
+      const int tb = na == 2 ? (t == 2 ? 3 : t) : t;
+      const int a = tb < 3 ? 0 : (tb < 5 ? 1 : 2), b = tb < 3 ? tb : (tb < 5 ? tb - 2 : 2);
       const double* Ca = C0 + 156 * a;
       const double* Cb = C0 + 156 * b;
       const unsigned mask = rowmask[a] & rowmask[b];
-      double acc[12];
-#pragma unroll
-      for (int j = 0; j < 12; j++) acc[j] = 0.0;
+      double acc = 0.0;
+#pragma unroll 4
       for (int q = 0; q < 12; q++) {
         if ((mask >> q) & 1u) {
           const double wa = (double)rec[MPC_REC_WEIGHTS + q] * Ca[q * 12 + i];
-#pragma unroll
-          for (int j = 0; j < 12; j++) acc[j] += wa * Cb[q * 12 + j];
+          acc += wa * Cb[q * 12 + j];
         }
       }
-#pragma unroll
-      for (int j = 0; j < 12; j++) k.M[tb * 144 + i * 12 + j] = acc[j];
+      k.M[tb * 144 + ij] = acc;
     }
   }
   cx.sync();
@@ -600,21 +603,32 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
     const double d = (double)(i - j);
     const double* P = k.psum + 5 * (h - 1 - i);
     const double P0 = P[0], P1 = P[1], P2 = P[2], P3 = P[3], P4 = P[4];
-    double s[3][3];
-    s[0][0] = P0;  s[0][1] = P1 + d * P0;  s[0][2] = P2 + 2.0 * d * P1 + d * d * P0;
-    s[1][0] = P1;  s[1][1] = P2 + d * P1;  s[1][2] = P3 + 2.0 * d * P2 + d * d * P1;
-    s[2][0] = P2;  s[2][1] = P3 + d * P2;  s[2][2] = P4 + 2.0 * d * P3 + d * d * P2;
+    // s_{pa,pb}: scalars for the no-drag case (the usual one: four terms, everything in registers); the general
+    // case indexes a 3x3 array at run time
+    const double s00 = P0, s01 = P1 + d * P0, s10 = P1, s11 = P2 + d * P1;
     for (int ax = 0; ax < 3; ax++)
       for (int bx = 0; bx < 3; bx++) {
         const int ci = la * 3 + ax, cj = lb * 3 + bx;
         double acc = 0;
-        for (int pa = 0; pa < na; pa++)
-          for (int pb = 0; pb < na; pb++) {
-            // table of (min, max): 00 01 02 11 12 22 -> 0..5; the lower-index pair is stored, the other is its transpose
-            const int lo = pa < pb ? pa : pb, hi = pa < pb ? pb : pa;
-            const int tb = lo * 3 - (lo * (lo - 1)) / 2 + (hi - lo);
-            acc += s[pa][pb] * k.M[tb * 144 + (pa <= pb ? ci * 12 + cj : cj * 12 + ci)];
-          }
+        if (na == 2) {
+          acc += s00 * k.M[0 * 144 + ci * 12 + cj];
+          acc += s01 * k.M[1 * 144 + ci * 12 + cj];
+          acc += s10 * k.M[1 * 144 + cj * 12 + ci];
+          acc += s11 * k.M[3 * 144 + ci * 12 + cj];
+        } else {
+          double s[3][3];
+          s[0][0] = P0;  s[0][1] = P1 + d * P0;  s[0][2] = P2 + 2.0 * d * P1 + d * d * P0;
+          s[1][0] = P1;  s[1][1] = P2 + d * P1;  s[1][2] = P3 + 2.0 * d * P2 + d * d * P1;
+          s[2][0] = P2;  s[2][1] = P3 + d * P2;  s[2][2] = P4 + 2.0 * d * P3 + d * d * P2;
+          for (int pa = 0; pa < na; pa++)
+            for (int pb = 0; pb < na; pb++) {
+              // table of (min, max): 00 01 02 11 12 22 -> 0..5; the lower-index pair is stored, the other is its
+              // transpose
+              const int lo = pa < pb ? pa : pb, hi = pa < pb ? pb : pa;
+              const int tb = lo * 3 - (lo * (lo - 1)) / 2 + (hi - lo);
+              acc += s[pa][pb] * k.M[tb * 144 + (pa <= pb ? ci * 12 + cj : cj * 12 + ci)];
+            }
+        }
         double val = 2.0 * acc;
         if (a == b && ax == bx) val += 2.0 * alpha;
         k.Hm[hixT<Cx::kPacked>(k.ld, 3 * a + ax, 3 * b + bx)] = val;
@@ -953,175 +967,6 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid, bool wi
   __syncthreads();
 }
 
-// ---------------------------------------------------------------------------
-// Stage 2, register-resident, CIRCULANT symmetric storage: the same sweep, but with a kept-block pattern that is
-// invariant under a cyclic relabelling of the indices, so that ONE copy of the pivot body serves every pivot
-// (the triangular pattern above needs R copies with different register indices: at R = 8 that is 33 KB of SASS,
-// more than the 32 KB L1.5 instruction cache, and the kernel stalls on instruction fetch).
-//
-// Requires square super-blocks: S := GR = 2*GC, NB := R = C/2 blocks per side, NVP = S*NB.  Thread (tr, tc) holds,
-// for its row slot i (row tr + S*i of the CURRENT frame) the column blocks J = (i - dl) mod NB for dl = 0..D,
-// D = NB/2, columns S*J + 2*tc + e:  a[i][dl][e].  Every unordered block pair {I, J} has a representative
-// ((I - J) mod NB <= D or (J - I) mod NB <= D); pairs at distance 0 and D are held twice, which is harmless.
-// After the S pivots of block 0 the frame is rotated by one block (index k -> k - S mod NVP): a[i] <- a[i+1],
-// dl unchanged.  NB rotations bring the frame back to the original labelling.
-//
-// Row nv of the padded matrix (free when nv < NVP) optionally carries the gradient g: the sweep turns it into
-// H^{-1} g, so the unconstrained optimum x = -H^{-1} g needs no matrix-vector product afterwards.
-//
-// kWarp: the NT = 32 threads are one warp working alone (__syncwarp instead of CTA barriers).
-// kPacked: H^{-1} is stored as a packed lower triangle, Hm[i*(i+1)/2 + j], j <= i.
-// ---------------------------------------------------------------------------
-template <int GR, int R, int GC, int C, bool kWarp, bool kPacked>
-__device__ __forceinline__ void invert_spd_circ(const Work& k, int tid, bool with_g) {
-  constexpr int S = GR, NB = R, D = NB / 2, NVP = S * NB, BUF = NVP + 2;
-  static_assert(GR == 2 * GC && C == 2 * R && NB % 2 == 0 && NB >= 2, "square super-blocks, even block count");
-  Scalars* sc = k.sc;
-  const int nv = sc->nv, ld = k.ld;
-  double* Hm = k.Hm;
-  const int tr = tid / GC, tc = tid % GC;
-  auto sync = [&]() { if (kWarp) __syncwarp(); else __syncthreads(); };
-  double a[R][D + 1][2];
-  const bool gaug = with_g && nv < NVP;
-#pragma unroll
-  for (int i = 0; i < R; i++) {
-    const int r = tr + S * i;
-#pragma unroll
-    for (int dl = 0; dl <= D; dl++) {
-      const int J = (i - dl + NB) % NB;
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int c = S * J + 2 * tc + e;
-        double v;
-        if (r < nv && c < nv) v = Hm[hixT<kPacked>(ld, r, c)];
-        else if (gaug && r == nv && c < nv) v = k.g[c];
-        else if (gaug && c == nv && r < nv) v = k.g[r];
-        else v = (r == c) ? 1.0 : 0.0;
-        a[i][dl][e] = v;
-      }
-    }
-  }
-  double* const buf0 = k.ck;
-  double* const buf1 = k.ck + BUF;
-  bool bad = false;
-  sync();  // everybody has read Hm / g before the buffers (which may overlay nothing) and Hm are rewritten
-  // publish pivot row q of the current frame into `dst` (all threads call it; compile-time register indices)
-  auto publish = [&](double* dst, int q, int e) {  // e == q & 1
-    if (tr == q) {
-#pragma unroll
-      for (int dl = 0; dl <= D; dl++) {
-        const int J = (NB - dl) % NB;
-        *reinterpret_cast<double2*>(dst + S * J + 2 * tc) = make_double2(a[0][dl][0], a[0][dl][1]);
-      }
-    }
-    if (tc == (q >> 1)) {
-#pragma unroll
-      for (int J = 1; J < D; J++) dst[tr + S * J] = a[J][J][e];
-    }
-    // slot q was just written (with d) by this same thread as part of its column pair: program order
-    const double rd = fast_rcp(a[0][0][e]);  // every thread (branch-free, overlaps with the bulk update); owner stores
-    if (tr == q && tc == (q >> 1)) {
-      dst[q] = a[0][0][e] - 1.0;
-      dst[NVP] = rd;
-    }
-  };
-  int p0 = 0;
-#pragma unroll 1
-  for (int b = 0; b < NB; b++, p0 += S) {
-    if (p0 < nv) {  // uniform
-      publish(buf0, 0, 0);
-#pragma unroll 1
-      for (int q0 = 0; q0 < S; q0 += 2) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int q = q0 + e;
-          if (p0 + q >= nv) break;  // uniform
-          double* const cur = e ? buf1 : buf0;
-          double* const nxt = e ? buf0 : buf1;
-          sync();
-          const double dinv = cur[NVP];
-          bad = bad || !(dinv > 0.0 && dinv < 1e300);
-          double u[R];
-#pragma unroll
-          for (int i = 0; i < R; i++) u[i] = -cur[tr + S * i] * dinv;
-          double2 v[NB];
-#pragma unroll
-          for (int J = 0; J < NB; J++) v[J] = *reinterpret_cast<const double2*>(cur + S * J + 2 * tc);
-          // look-ahead: first the entries the NEXT pivot's publication reads (row slot 0 and the column entries
-          // a[J][J][.]), then that publication, then the rest of the update -- the stores and the reciprocal overlap
-          // with the bulk of the DFMAs
-#pragma unroll
-          for (int dl = 0; dl <= D; dl++) {
-            const int J = (NB - dl) % NB;
-            a[0][dl][0] = fma(u[0], v[J].x, a[0][dl][0]);
-            a[0][dl][1] = fma(u[0], v[J].y, a[0][dl][1]);
-          }
-#pragma unroll
-          for (int J = 1; J < D; J++) {
-            a[J][J][0] = fma(u[J], v[0].x, a[J][J][0]);
-            a[J][J][1] = fma(u[J], v[0].y, a[J][J][1]);
-          }
-          if (q + 1 < S && p0 + q + 1 < nv) publish(nxt, q + 1, e ^ 1);  // uniform condition
-#pragma unroll
-          for (int i = 1; i < R; i++) {
-#pragma unroll
-            for (int dl = 0; dl <= D; dl++) {
-              if (i < D && dl == i) continue;  // done above
-              const int J = (i - dl + NB) % NB;
-              a[i][dl][0] = fma(u[i], v[J].x, a[i][dl][0]);
-              a[i][dl][1] = fma(u[i], v[J].y, a[i][dl][1]);
-            }
-          }
-        }
-      }
-      sync();  // the last pivot's buffer has been read by everybody before the next block publishes into buf0
-    }
-    // rotate the frame by one block
-#pragma unroll
-    for (int dl = 0; dl <= D; dl++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const double t0 = a[0][dl][e];
-#pragma unroll
-        for (int i = 0; i + 1 < R; i++) a[i][dl][e] = a[i + 1][dl][e];
-        a[R - 1][dl][e] = t0;
-      }
-  }
-  const bool any_bad = kWarp ? (__any_sync(0xffffffffu, bad) != 0) : (__syncthreads_or(bad) != 0);
-  if (any_bad) {
-    if (tid == 0) sc->status = MPC_STATUS_NOT_PD;
-    sync();
-    return;
-  }
-  // store H^{-1} = -(swept matrix) with the 2 taken off the diagonal; one writer per unordered pair (block pairs at
-  // distance 0 and D are held in both orientations: the lower-triangular one writes); row nv -> x = -H^{-1} g
-#pragma unroll
-  for (int i = 0; i < R; i++) {
-    const int r = tr + S * i;
-#pragma unroll
-    for (int dl = 0; dl <= D; dl++) {
-      const int J = (i - dl + NB) % NB;
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int c = S * J + 2 * tc + e;
-        const double raw = a[i][dl][e];
-        if (r < nv && c < nv) {
-          const bool twice = (dl == 0) || (dl == D);
-          if (!twice || r >= c) {
-            const double val = (c == r) ? (2.0 - raw) : -raw;
-            if (kPacked) Hm[tri_index(r, c)] = val;
-            else { Hm[r * ld + c] = val; if (r != c) Hm[c * ld + r] = val; }
-          }
-        } else if (gaug && r == nv && c < nv) {
-          k.x[c] = -raw;
-        } else if (gaug && c == nv && r < nv && !(dl == 0 || dl == D)) {
-          k.x[r] = -raw;
-        }
-      }
-    }
-  }
-  sync();
-}
 #endif
 
 // ---------------------------------------------------------------------------

@@ -225,11 +225,6 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
       if constexpr (R > 0) {
         static_assert(R == 0 || NT == GR * GC, "thread grid");
-#ifdef MPC_CIRC
-        if constexpr (GR == 2 * GC && C == 2 * R && R % 2 == 0)
-          mpc::invert_spd_circ<GR, R, GC, C, NT == 32, PK>(k, (int)threadIdx.x, true);
-        else
-#endif
         mpc::invert_spd_tiles<GR, R, GC, C, PK>(k, (int)threadIdx.x, true);
       } else {
         mpc::invert_spd(cx, k);

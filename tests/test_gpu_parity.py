@@ -176,6 +176,23 @@ def test_cpp_caller_stub_matches_oracle(oracle):
         assert rel(got[None], ref["forces"][:1].astype(np.float64))[0] < 1e-6
 
 
+@pytest.mark.parametrize("h", [1, 2, 9, 36])
+def test_extreme_horizons(h, oracle, cuda_engine_factory):
+    """Horizon 1 and 2 (smallest problems), 9 (the last horizon whose gait table fits update_data_t.gait without
+    running on into hack_pad) and 36 (K_MAX_GAIT_SEGMENTS, the largest the reference's structs can carry: trot
+    nv = 216, four-stance nv = 432 -- the catch-all class with its grouped sweep)."""
+    rec = np.concatenate([W.config2(6, h, 70 + h), W.four_stance(3, h, 80 + h)])
+    eng = cuda_engine_factory(h, rec.shape[0])
+    f, s, st = eng.solve_device(torch.from_numpy(rec).cuda(), want_solution=True)
+    torch.cuda.synchronize()
+    o = oracle.solve_batch(rec, h, 64)
+    ok = o["rc"] == 0
+    code = E.status_code(st.cpu().numpy())
+    assert ((code == E.STATUS_OPTIMAL) | (code == E.STATUS_NO_STANCE)).all()
+    assert rel(s.cpu().numpy(), o["sol"])[ok].max() < 1e-9
+    assert ok.sum() >= 3
+
+
 def test_status_codes_and_failure_outputs(cuda_engine_factory):
     from quadruped_ctrl_b200 import records as R
     h = 10
