@@ -64,6 +64,8 @@ struct Layout {
   int ld;       // leading dimension of Hm (odd -> conflict-free column walks)
   int ldT;      // leading dimension of T
   int big_in_fast;  // 1: Hm and T are carved from `fast`; 0: from the global slab
+  int pipe;         // 1: two problems in flight per CTA (see make_layout): disjoint assembly / active-set regions
+  int off_scal2, off_ints2, off_gi, off_mom;  // pipe: second per-problem set, active-set region, moment sums
   // byte offsets into `fast`
   int off_scal, off_g, off_x, off_ints, off_union, off_red, off_Hm, off_T;
   int fast_bytes;
@@ -85,9 +87,15 @@ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 // The same function sizes the launch (host) and carves the pointers (device).
 // packed: Hm as a packed lower triangle (the register-resident classes; the generic in-place sweep of the
 // catch-all class and of the host emulation needs full storage)
-inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npad = 0, int packed = -1) {
+// pipe: the smallest class keeps two problems in flight per CTA -- one warp runs the active set of problem n while
+// the other warps assemble problem n+1 (phases P0..P9) -- so the assembly scratch and the active-set scratch are
+// disjoint instead of a union, the moment sums get their own place (H^{-1} of problem n is still being read) and the
+// small per-problem state (scalars, stance lists) exists twice.
+inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npad = 0, int packed = -1, int pipe = 0) {
   if (packed < 0) packed = 0;
   Layout L;
+  L.pipe = pipe;
+  L.off_scal2 = L.off_ints2 = L.off_gi = L.off_mom = 0;
   L.h = h;
   L.nv_cap = nv_cap;
   // register-resident inversion: two (npad + 2)-long buffers (double-buffered pivot row + 1/pivot)
@@ -114,12 +122,25 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
   int hm_doubles = packed ? nv_cap * (nv_cap + 1) / 2 : nv_cap * L.ld;
   if (hm_doubles < 3 * 12 * h) hm_doubles = 3 * 12 * h;  // the assembly parks its moment sums there
   if (big_in_fast) gi += t_doubles;
-  if (gi > un) un = gi;
-  o += 8 * un;
+  if (pipe) {
+    o += 8 * un;                 // assembly scratch
+    L.off_mom = o;
+    o += 8 * 3 * 12 * h;
+    L.off_gi = o;
+    o += 8 * (gi + 1);           // active-set scratch (T first)
+    L.off_scal2 = o;
+    o += (int)((sizeof(Scalars) + 15) / 16 * 16);
+    L.off_ints2 = o;
+    o += 4 * 3 * 4 * h;
+    o = (o + 15) / 16 * 16;
+  } else {
+    if (gi > un) un = gi;
+    o += 8 * un;
+  }
   L.off_red = o;
   o += 8 * kRedDoubles;
   L.off_Hm = o;
-  L.off_T = L.off_union;  // T sits at the start of the GI part of the union
+  L.off_T = pipe ? L.off_gi : L.off_union;  // T sits at the start of the active-set scratch
   if (big_in_fast) o += 8 * hm_doubles;
   L.fast_bytes = (o + 15) / 16 * 16;
   L.slab_Hm = 0;
@@ -133,7 +154,7 @@ struct Work {
   double *g, *x, *Hm, *T;
   int *stance, *posk, *amask, *W, *Wia, *Wiz;
   // assembly view of the union
-  double *C, *M, *xs, *qe, *psum;
+  double *C, *M, *xs, *qe, *psum, *mom;  // mom: [3][h][12] moment sums (parked in Hm unless the layout is piped)
   // active-set view of the union
   double *ck, *ub, *Wca, *Wcz, *w, *r, *u, *tcol;
   double* red;
@@ -148,15 +169,17 @@ struct Work {
 #define MPC_STAMP(k, cx, slot) do { } while (0)
 #endif
 
-MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
+// set: which of the two per-problem sets (scalars, stance / posk / amask) of a piped layout; 0 otherwise
+MPC_HD Work carve(const Layout& L, char* fast, char* slab, int set = 0) {
   Work k;
-  k.sc = (Scalars*)(fast + L.off_scal);
+  k.sc = (Scalars*)(fast + (set ? L.off_scal2 : L.off_scal));
   k.g = (double*)(fast + L.off_g);
   k.x = (double*)(fast + L.off_x);
   int* ip = (int*)(fast + L.off_ints);
-  k.stance = ip;
-  k.posk = ip + 4 * L.h;
-  k.amask = ip + 8 * L.h;
+  int* ips = set ? (int*)(fast + L.off_ints2) : ip;
+  k.stance = ips;
+  k.posk = ips + 4 * L.h;
+  k.amask = ips + 8 * L.h;
   k.W = ip + 12 * L.h;
   k.Wia = k.W + (L.m_cap + 1);
   k.Wiz = k.Wia + (L.m_cap + 1);
@@ -166,7 +189,7 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
   k.xs = k.M + 6 * 144;
   k.qe = k.xs + 39;
   k.psum = k.qe + 12 * L.h;
-  double* gi = un;
+  double* gi = L.pipe ? (double*)(fast + L.off_gi) : un;
   if (L.big_in_fast) {
     k.T = gi;
     gi += L.m_cap * L.ldT;
@@ -185,6 +208,7 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab) {
   k.u = k.r + (L.m_cap + 1);
   k.tcol = k.u + (L.m_cap + 1);
   k.red = (double*)(fast + L.off_red);
+  k.mom = L.pipe ? (double*)(fast + L.off_mom) : k.Hm;
   k.ld = L.ld;
   k.ldT = L.ldT;
   k.nv_cap = L.nv_cap;
@@ -220,6 +244,16 @@ struct WarpT {
   static constexpr int kUnroll = 1;
   int tid, nt;  // lane, 32
   __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+// NTP threads of the CTA (a whole number of warps) working as a group with hardware barrier BAR (not 0, which is
+// __syncthreads): the assembly of the next problem while warp 0 runs the active set of the current one.
+template <int BAR, int NTP>
+struct PartT {
+  static constexpr bool kOneWarp = false;
+  static constexpr bool kPacked = false;
+  static constexpr int kUnroll = 1;
+  int tid, nt;  // 0..NTP-1, NTP
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NTP) : "memory"); }
 };
 using Cta = CtaT<false>;
 using Warp = WarpT<false>;
@@ -369,8 +403,10 @@ MPC_HD double apply_A2(const double* X, int ldx, int i, int j, double xd) {
   return i == 5 ? xd * X[9 * ldx + j] + X[12 * ldx + j] : 0.0;
 }
 
+// assemble = assemble_front (P0..P9: everything up to the gradient and the M tables; touches neither Hm -- when the
+// moment sums have a place of their own -- nor anything the active set uses) + assemble_H (P11: the H blocks).
 template <class Cx>
-MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, const Work& k) {
+MPC_HD void assemble_front(const Cx& cx, const float* rec, const unsigned char* gait, const Work& k) {
   const int h = k.h;
   Scalars* sc = k.sc;
   double* B = k.M;          // 13x12   (the M region is free until the C_a are final)
@@ -381,7 +417,8 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
   double* x0 = k.xs;        // 13
   double* Ax0 = x0 + 13;
   double* A2x0 = Ax0 + 13;
-  double* mom = k.Hm;       // [3][h][12] moments of the tracking error; Hm is free until the H blocks are written
+  double* mom = k.mom;      // [3][h][12] moments of the tracking error (in Hm, free until the H blocks are written,
+                            // or in a place of its own when two problems are in flight)
   int* flag = k.amask;      // 0/1 stance flags while the stance list is built (amask[] proper is set up later)
   const float fmax = rec[MPC_REC_FMAX];
 
@@ -417,18 +454,21 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
   {
     // quat_to_rpy (SolverMPC.cpp:257-267), q = (w,x,y,z); x_0 = [rpy(2), rpy(1), rpy(0), ...] (:318)
     const double qw = rec[MPC_REC_Q], qx = rec[MPC_REC_Q + 1], qy = rec[MPC_REC_Q + 2], qz = rec[MPC_REC_Q + 3];
-    const int lanes = cx.nt >= 128 ? 32 : 0;  // task t runs on thread 32*t (one per warp); single thread: all on 0
-    if (cx.tid == 0 * lanes) {
+    // the transcendental groups on different warps: sincos on thread 0, the two atan2 on neighbouring lanes of the
+    // second warp (one instruction stream), asin on the third (three warps suffice: the piped kernel assembles on 96
+    // threads); a single thread runs them all
+    const int w1 = cx.nt >= 96 ? 32 : 0, w2 = cx.nt >= 96 ? 64 : 0, l1 = cx.nt >= 96 ? 1 : 0;
+    if (cx.tid == 0) {
       const double yaw = (double)rec[MPC_REC_YAW];
       sincos(yaw, &scr[1], &scr[0]);  // one range reduction for both
     }
-    if (cx.tid == 1 * lanes) x0[2] = MPC_ATAN2(2. * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
-    if (cx.tid == 2 * lanes) {
+    if (cx.tid == w1) x0[2] = MPC_ATAN2(2. * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
+    if (cx.tid == w2) {
       double as = -2. * (qx * qz - qw * qy);
       if (!(as < .99999)) as = .99999;
       x0[1] = asin(as);
     }
-    if (cx.tid == 3 * lanes) x0[0] = MPC_ATAN2(2. * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
+    if (cx.tid == w1 + l1) x0[0] = MPC_ATAN2(2. * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
   }
   cx.sync();
   MPC_STAMP(k, cx, 8);
@@ -544,7 +584,7 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
   // ---- P9: reduced gradient g_v = 2 sum_a C_a[:,c]' mom[a][j] (SolverMPC.cpp:399), and the tables
   //          M_ab = C_a' Q C_b (12x12).  Row supports: C0 rows 0..11, C1 rows {0..5,11}, C2 row {5}.
   //          M overlays B,t1,t2,scr, which are dead: the barrier above is the last point anything reads them. ----
-  const int nv = sc->nv, ns = sc->ns;
+  const int nv = sc->nv;
   const unsigned rowmask[3] = {0xFFFu, 0x83Fu, 0x020u};
   MPC_FOR(v, nv) {
     const int sidx = v / 3, ax = v - 3 * sidx;
@@ -586,6 +626,14 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
   }
   cx.sync();
   MPC_STAMP(k, cx, 11);
+}
+
+template <class Cx>
+MPC_HD void assemble_H(const Cx& cx, const float* rec, const Work& k) {
+  const int h = k.h;
+  const Scalars* sc = k.sc;
+  const int ns = sc->ns;
+  const int na = ((double)rec[MPC_REC_XDRAG] != 0.0) ? 3 : 2;  // as in assemble_front
   // ---- P11: reduced Hessian, one 3x3 block per stance pair (a >= b) (SolverMPC.cpp:395):
   //   H[(i,la),(j,lb)] = 2 sum_{pa,pb} s_{pa,pb} M_{pa,pb}[la,lb] + 2 alpha I,
   //   s_{pa,pb} = sum_{q=0..n} q^pa (q+d)^pb, d = i-j >= 0, n = h-1-i, from the power sums P_e(n) = sum q^e
@@ -636,6 +684,13 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
       }
   }
   cx.sync();
+}
+
+template <class Cx>
+MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, const Work& k) {
+  assemble_front(cx, rec, gait, k);
+  if (k.sc->status != MPC_STATUS_OPTIMAL) return;
+  assemble_H(cx, rec, k);
 }
 
 // ---------------------------------------------------------------------------

@@ -286,10 +286,121 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
   }
 }
 
+// ---- two problems in flight per CTA (the smallest class, production instantiation) --------------------------------
+// In mpc_solve_kernel the active set of a problem runs on one warp while the CTA's other warps wait at a barrier (18 %
+// of all warp samples of the round-1 capture).  Here the CTA works in rounds: in phase X warp 0 runs the active set and
+// the scatter of problem n-1 while warps 1..3 assemble problem n up to the gradient and the M tables (assemble_front,
+// on its own hardware barrier); in phase Y all four warps write the H blocks, invert them in registers and set the
+// active set up.  The two roles share no shared memory (piped layout, mpc_core.h: disjoint assembly / active-set
+// scratch, moment sums outside the H^{-1} tile, scalars and stance lists twice), the record of problem n-1 stays in
+// its buffer until its active set is done, and the arithmetic per problem is exactly that of mpc_solve_kernel.
+template <int NT, int GR, int R, int GC, int C, int MINB>
+__global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_constant__ SolveParams P) {
+  extern __shared__ __align__(128) char smem[];
+  const int count = P.count ? *P.count : P.batch;
+  if ((int)blockIdx.x >= count) return;
+  uint64_t* bar = (uint64_t*)smem;
+  char* recbuf = smem + 16;
+  char* fast = recbuf + 2 * P.stride;
+  const int tid = (int)threadIdx.x;
+  const mpc::CtaT<false> cx{tid, NT};
+  const mpc::PartT<1, NT - 32> px{tid - 32, NT - 32};
+  const mpc::WarpT<false> wx{tid & 31, 32};
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t rec_bytes = (uint32_t)P.stride;
+  int item = blockIdx.x;
+  if (tid == 0) {
+    const int b0 = P.list ? P.list[item] : item;
+    mbar_expect_tx(&bar[0], rec_bytes);
+    tma_bulk_g2s(recbuf, P.records + P.stride * b0, rec_bytes, &bar[0]);
+  }
+  int prev_b = -1;  // problem whose active set is still to run (its state sits in set (it-1)&1, its record in buffer (it-1)&1)
+  for (int it = 0;; it++) {
+    const int cur = it & 1;
+    const bool have = item < count;
+    const float* rec = (const float*)(recbuf + (size_t)cur * P.stride);
+    const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
+    if (have) mbar_wait(&bar[cur], (uint32_t)((it >> 1) & 1));
+    // ---- phase X: active set + scatter of the previous problem (warp 0) || front half of this problem's assembly ----
+    if (tid < 32) {
+      if (prev_b >= 0) {
+        const mpc::Work kg = mpc::carve(P.L, fast, nullptr, cur ^ 1);
+        const float* recp = (const float*)(recbuf + (size_t)(cur ^ 1) * P.stride);
+        const unsigned char* gaitp = (const unsigned char*)recp + 4 * (MPC_REC_TRAJ + 12 * P.h);
+        mpc::active_set(wx, recp, gaitp, kg, P.max_iter);
+        __syncwarp();
+        const int code = kg.sc->status;
+        if (code == mpc::STATUS_RETRY_BIG && P.retry_list) {
+          if (tid == 0) {
+            const int slot = atomicAdd(P.retry_count, 1);
+            P.retry_list[slot] = prev_b;
+          }
+        } else {
+          __syncwarp();
+          if (code == mpc::STATUS_RETRY_BIG && tid == 0) kg.sc->status = MPC_STATUS_MAX_ITER;
+          __syncwarp();
+          mpc::scatter(wx, kg, P.forces + (size_t)12 * prev_b,
+                       P.solution ? P.solution + (size_t)12 * P.h * prev_b : nullptr, P.status ? P.status + prev_b : nullptr);
+          if (P.n_peers > 0 && tid < 12) {
+            const float f = P.forces[(size_t)12 * prev_b + tid];
+#pragma unroll
+            for (int q = 0; q < kMaxPeers; q++)
+              if (q < P.n_peers && P.peers[q]) P.peers[q][(size_t)12 * (P.rank_offset + prev_b) + tid] = f;
+          }
+        }
+      }
+    } else if (have) {
+      const mpc::Work ka = mpc::carve(P.L, fast, nullptr, cur);
+      mpc::assemble_front(px, rec, gait, ka);
+    }
+    __syncthreads();
+    if (!have) break;
+    const int b = P.list ? P.list[item] : item;
+    const int next = item + gridDim.x;
+    if (tid == 0 && next < count) {  // buffer cur^1 is free now: the previous problem's active set is done with it
+      const int bn = P.list ? P.list[next] : next;
+      mbar_expect_tx(&bar[cur ^ 1], rec_bytes);
+      tma_bulk_g2s(recbuf + (size_t)(cur ^ 1) * P.stride, P.records + P.stride * bn, rec_bytes, &bar[cur ^ 1]);
+    }
+    // ---- phase Y: H blocks, inversion, active-set set-up (all warps) ----
+    const mpc::Work k = mpc::carve(P.L, fast, nullptr, cur);
+    if (k.sc->status == MPC_STATUS_OPTIMAL) mpc::assemble_H(cx, rec, k);
+    if (k.sc->status == MPC_STATUS_OPTIMAL) mpc::invert_spd_tiles<GR, R, GC, C, false>(k, tid, true);
+    if (k.sc->status == MPC_STATUS_OPTIMAL) {
+      mpc::active_set_init(cx, rec, gait, k, true);  // nv <= 60 < 64: x = -H^{-1} g always comes out of the sweep
+      prev_b = b;
+    } else {  // bad input / no stance leg / not positive definite: report now, nothing to iterate on
+      __syncthreads();
+      mpc::scatter(cx, k, P.forces + (size_t)12 * b, P.solution ? P.solution + (size_t)12 * P.h * b : nullptr,
+                   P.status ? P.status + b : nullptr);
+      if (P.n_peers > 0 && tid < 12) {
+        const float f = P.forces[(size_t)12 * b + tid];
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; q++)
+          if (q < P.n_peers && P.peers[q]) P.peers[q][(size_t)12 * (P.rank_offset + b) + tid] = f;
+      }
+      prev_b = -1;
+      __syncthreads();
+    }
+    item = next;
+  }
+}
+
 struct ClassCfg {
   int nv_cap, m_cap, in_fast, threads, grid, variant;
   size_t smem;
   mpc::Layout L;
+  // two problems in flight per CTA (mpc_solve_pipe_kernel; the smallest class when its piped layout fits four CTAs per
+  // SM with a useful working-set tile): the production launches use these, the profiling entries the ones above
+  bool pipe = false;
+  int pipe_m_cap = 0, pipe_grid = 0;
+  size_t pipe_smem = 0;
+  mpc::Layout pipe_L;
 };
 
 thread_local std::string g_err;
@@ -450,6 +561,29 @@ int build_classes(mpc_batch* eng) {
     if ((int)c.smem > max_smem) continue;
     int rc = configure_kernel(eng, c);
     if (rc) return rc;
+    if (c.variant == V_64 && MPC_V64_NT == 128 && !getenv("MPC_NO_PIPE")) {
+      // piped layout: the largest working-set tile that still lets four CTAs share an SM; not worth it below 16 rows
+      int sm_smem = 0;
+      CK(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, eng->device));
+      const size_t budget = (size_t)sm_smem / 4 - 1024;  // 1 KB per CTA is reserved by the system
+      for (int m = c.m_cap; m >= 16; m--) {
+        const mpc::Layout Lp = mpc::make_layout(h, c.nv_cap, m, 1, kVariantPad[c.variant], 0, 1);
+        const size_t need = 16 + 2 * eng->stride + Lp.fast_bytes;
+        if (need > budget) continue;
+        auto kern = mpc_solve_pipe_kernel<MPC_V64_SHAPE, 4>;
+        int occ = 0;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c.threads, need));
+        if (occ >= 4) {
+          c.pipe = true;
+          c.pipe_m_cap = m;
+          c.pipe_L = Lp;
+          c.pipe_smem = need;
+          c.pipe_grid = occ * eng->sms;
+        }
+        break;
+      }
+    }
     eng->classes.push_back(c);
   }
   // catch-all: full-size problem and working set in a per-CTA global slab (L2 resident)
@@ -495,6 +629,14 @@ void fill_params(const mpc_batch* eng, int slot, SolveParams& P, const void* rec
 
 int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int grid, cudaStream_t st) {
   const bool prof = P.phase_clk != nullptr || P.H_out != nullptr || P.debug_stop != 0;
+  if (c.pipe && !prof) {
+    SolveParams Pp = P;
+    Pp.L = c.pipe_L;
+    mpc_solve_pipe_kernel<MPC_V64_SHAPE, 4><<<grid, c.threads, c.pipe_smem, st>>>(Pp);
+    eng->launches++;
+    CK(cudaGetLastError());
+    return MPC_OK;
+  }
   MPC_VARIANT_CALL(c.variant, prof, (kern<<<grid, c.threads, c.smem, st>>>(P)));
   eng->launches++;
   CK(cudaGetLastError());
@@ -553,7 +695,8 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
     const size_t ring = (size_t)(eng->ring_pos % kRing) * kMaxClasses + ci;
     const bool time_this = eng->timed && (eng->timed_class < 0 || eng->timed_class == ci);
     if (time_this) CK(cudaEventRecord(eng->ring0[ring], st));
-    int grid = std::min(c.grid, batch);
+    const bool piped = c.pipe && !eng->phase_clk && !H_out && !eng->debug_stop;
+    int grid = std::min(piped ? c.pipe_grid : c.grid, batch);
     if (eng->ctas_per_sm_limit > 0) grid = std::min(grid, eng->ctas_per_sm_limit * eng->sms);
     int rc = launch_solve(eng, c, P, grid, st);
     if (rc) return rc;
@@ -1019,7 +1162,8 @@ int mpc_batch_num_classes(const mpc_batch_t* eng) { return eng ? (int)eng->class
 int mpc_batch_class_info(const mpc_batch_t* eng, int idx, int* info) {
   if (!eng || idx < 0 || idx >= (int)eng->classes.size() || !info) return MPC_E_ARG;
   const ClassCfg& c = eng->classes[idx];
-  info[0] = c.nv_cap; info[1] = c.m_cap; info[2] = c.threads; info[3] = c.grid; info[4] = (int)c.smem; info[5] = c.in_fast;
+  info[0] = c.nv_cap; info[1] = c.pipe ? c.pipe_m_cap : c.m_cap; info[2] = c.threads;
+  info[3] = c.pipe ? c.pipe_grid : c.grid; info[4] = (int)(c.pipe ? c.pipe_smem : c.smem); info[5] = c.in_fast;
   return MPC_OK;
 }
 
