@@ -349,7 +349,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "on_chip": on_chip,
-                         "kernel": "mpc_solve_kernel<128> (size class nv<=60)", "kernel_ms": k_ms, "kernel_launches_timed": k_n,
+                         "kernel": "mpc_solve_pipe_kernel<128,...> (size class nv<=60, two problems in flight per CTA)", "kernel_ms": k_ms, "kernel_launches_timed": k_n,
                          "kernel_ms_in_timed_region": k_ms_timed,
                          "algorithmic_bytes_per_solve": R.algorithmic_bytes(h),
                          "note": "on-chip fp64/latency bound by construction: H and g never leave shared memory, so "

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
 // active set up.  The two roles share no shared memory (piped layout, mpc_core.h: disjoint assembly / active-set
 // scratch, moment sums outside the H^{-1} tile, scalars and stance lists twice), the record of problem n-1 stays in
 // its buffer until its active set is done, and the arithmetic per problem is exactly that of mpc_solve_kernel.
-template <int NT, int GR, int R, int GC, int C, int MINB>
+template <int NT, int GR, int R, int GC, int C, int MINB, bool PK>
 __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) char smem[];
   const int count = P.count ? *P.count : P.batch;
@@ -303,9 +303,9 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
   char* recbuf = smem + 16;
   char* fast = recbuf + 2 * P.stride;
   const int tid = (int)threadIdx.x;
-  const mpc::CtaT<false> cx{tid, NT};
+  const mpc::CtaT<PK> cx{tid, NT};
   const mpc::PartT<1, NT - 32> px{tid - 32, NT - 32};
-  const mpc::WarpT<false> wx{tid & 31, 32};
+  const mpc::WarpT<PK> wx{tid & 31, 32};
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -370,9 +370,9 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
     // ---- phase Y: H blocks, inversion, active-set set-up (all warps) ----
     const mpc::Work k = mpc::carve(P.L, fast, nullptr, cur);
     if (k.sc->status == MPC_STATUS_OPTIMAL) mpc::assemble_H(cx, rec, k);
-    if (k.sc->status == MPC_STATUS_OPTIMAL) mpc::invert_spd_tiles<GR, R, GC, C, false>(k, tid, true);
+    if (k.sc->status == MPC_STATUS_OPTIMAL) mpc::invert_spd_tiles<GR, R, GC, C, PK>(k, tid, true);
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
-      mpc::active_set_init(cx, rec, gait, k, true);  // nv <= 60 < 64: x = -H^{-1} g always comes out of the sweep
+      mpc::active_set_init(cx, rec, gait, k, k.sc->nv < GR * R);  // x = -H^{-1} g came out of the sweep if it had room
       prev_b = b;
     } else {  // bad input / no stance leg / not positive definite: report now, nothing to iterate on
       __syncthreads();
@@ -503,6 +503,11 @@ enum { V_64 = 0, V_96, V_128, V_GENERIC, V_COUNT };
   }
 #define MPC_VARIANT_CALL(v, prof, EXPR)                       \
   if (prof) { MPC_VARIANT_CALL1(v, true, EXPR) } else { MPC_VARIANT_CALL1(v, false, EXPR) }
+#define MPC_PIPE_CALL(v, EXPR)                                                                                \
+  switch (v) {                                                                                               \
+    case V_64: { auto kern = mpc_solve_pipe_kernel<MPC_V64_SHAPE, MPC_MINB0, false>; EXPR; } break;          \
+    default: { auto kern = mpc_solve_pipe_kernel<256, 16, 6, 16, 6, MPC_MINB96, false>; EXPR; } break;       \
+  }
 const int kVariantThreads[V_COUNT] = {MPC_V64_NT, 256, 256, 256};
 const int kVariantPad[V_COUNT] = {64, 96, 128, 0};
 
@@ -561,20 +566,26 @@ int build_classes(mpc_batch* eng) {
     if ((int)c.smem > max_smem) continue;
     int rc = configure_kernel(eng, c);
     if (rc) return rc;
-    if (c.variant == V_64 && MPC_V64_NT == 128 && !getenv("MPC_NO_PIPE")) {
-      // piped layout: the largest working-set tile that still lets four CTAs share an SM; not worth it below 16 rows
+    // Piped for nv <= 60 (+12 % on trot horizon 10) and nv <= 96 (+6 % on gallop horizon 16).  Not for nv <= 128:
+    // with nine working-set changes per problem on average the active set is better off on the whole CTA than on one
+    // warp beside the next assembly (measured -9 % on four-stance horizon 10).  MPC_NO_PIPE: development switch.
+    const bool try_pipe = !getenv("MPC_NO_PIPE") && c.variant != V_128;
+    if (try_pipe && (c.variant != V_64 || MPC_V64_NT == 128)) {
+      // piped layout: the largest working-set tile that keeps the class's CTAs per SM; not worth it below 16 rows
       int sm_smem = 0;
       CK(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, eng->device));
-      const size_t budget = (size_t)sm_smem / 4 - 1024;  // 1 KB per CTA is reserved by the system
+      const int per_sm = c.grid / eng->sms;                     // resident CTAs of the un-piped kernel
+      const size_t budget = (size_t)sm_smem / per_sm - 1024;    // 1 KB per CTA is reserved by the system
       for (int m = c.m_cap; m >= 16; m--) {
-        const mpc::Layout Lp = mpc::make_layout(h, c.nv_cap, m, 1, kVariantPad[c.variant], 0, 1);
+        const mpc::Layout Lp = mpc::make_layout(h, c.nv_cap, m, 1, kVariantPad[c.variant], packed, 1);
         const size_t need = 16 + 2 * eng->stride + Lp.fast_bytes;
-        if (need > budget) continue;
-        auto kern = mpc_solve_pipe_kernel<MPC_V64_SHAPE, 4>;
+        if (need > budget || (int)need > max_smem) continue;
         int occ = 0;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c.threads, need));
-        if (occ >= 4) {
+        MPC_PIPE_CALL(c.variant, {
+          CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c.threads, need));
+        });
+        if (occ >= per_sm) {
           c.pipe = true;
           c.pipe_m_cap = m;
           c.pipe_L = Lp;
@@ -632,7 +643,7 @@ int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int gr
   if (c.pipe && !prof) {
     SolveParams Pp = P;
     Pp.L = c.pipe_L;
-    mpc_solve_pipe_kernel<MPC_V64_SHAPE, 4><<<grid, c.threads, c.pipe_smem, st>>>(Pp);
+    MPC_PIPE_CALL(c.variant, (kern<<<grid, c.threads, c.pipe_smem, st>>>(Pp)));
     eng->launches++;
     CK(cudaGetLastError());
     return MPC_OK;

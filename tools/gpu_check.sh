@@ -11,7 +11,7 @@ python bench.py 2>&1 | tail -1 | tee gpurun_out/bench_ours.json
 if [ "${1:-}" != "noprof" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/launches_run.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:mpc_solve_kernel -s 8 -c 1 -f -o gpurun_out/prof_solve \
+ncu --set full --clock-control none --import-source on -k regex:mpc_solve -s 8 -c 1 -f -o gpurun_out/prof_solve \
     python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/prof_run.log 2>&1
 ls -la gpurun_out
 fi
