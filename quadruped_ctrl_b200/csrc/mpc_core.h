@@ -246,11 +246,12 @@ struct WarpT {
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 // NTP threads of the CTA (a whole number of warps) working as a group with hardware barrier BAR (not 0, which is
-// __syncthreads): the assembly of the next problem while warp 0 runs the active set of the current one.
-template <int BAR, int NTP>
+// __syncthreads): the assembly of the next problem while another group (or one warp) runs the active set of the
+// current one.
+template <int BAR, int NTP, bool PK = false>
 struct PartT {
   static constexpr bool kOneWarp = false;
-  static constexpr bool kPacked = false;
+  static constexpr bool kPacked = PK;
   static constexpr int kUnroll = 1;
   int tid, nt;  // 0..NTP-1, NTP
   __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NTP) : "memory"); }

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "mpc_core.h"
@@ -294,7 +295,9 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
 // active set up.  The two roles share no shared memory (piped layout, mpc_core.h: disjoint assembly / active-set
 // scratch, moment sums outside the H^{-1} tile, scalars and stance lists twice), the record of problem n-1 stays in
 // its buffer until its active set is done, and the arithmetic per problem is exactly that of mpc_solve_kernel.
-template <int NT, int GR, int R, int GC, int C, int MINB, bool PK>
+// NG: threads of the active-set role (32: one warp with __syncwarp / shuffles; more: a group on hardware barrier 2);
+// the other NT - NG threads assemble on hardware barrier 1.
+template <int NT, int GR, int R, int GC, int C, int MINB, bool PK, int NG>
 __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) char smem[];
   const int count = P.count ? *P.count : P.batch;
@@ -304,8 +307,11 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
   char* fast = recbuf + 2 * P.stride;
   const int tid = (int)threadIdx.x;
   const mpc::CtaT<PK> cx{tid, NT};
-  const mpc::PartT<1, NT - 32> px{tid - 32, NT - 32};
-  const mpc::WarpT<PK> wx{tid & 31, 32};
+  const mpc::PartT<1, NT - NG> px{tid - NG, NT - NG};
+  // the active-set role: one warp, or a group of NG threads with its own barrier
+  using GCtx = typename std::conditional<NG == 32, mpc::WarpT<PK>, mpc::PartT<2, NG, PK>>::type;
+  const GCtx wx{tid, NG};
+  auto gsync = [&]() { if (NG == 32) __syncwarp(); else wx.sync(); };
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -327,13 +333,13 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
     const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
     if (have) mbar_wait(&bar[cur], (uint32_t)((it >> 1) & 1));
     // ---- phase X: active set + scatter of the previous problem (warp 0) || front half of this problem's assembly ----
-    if (tid < 32) {
+    if (tid < NG) {
       if (prev_b >= 0) {
         const mpc::Work kg = mpc::carve(P.L, fast, nullptr, cur ^ 1);
         const float* recp = (const float*)(recbuf + (size_t)(cur ^ 1) * P.stride);
         const unsigned char* gaitp = (const unsigned char*)recp + 4 * (MPC_REC_TRAJ + 12 * P.h);
         mpc::active_set(wx, recp, gaitp, kg, P.max_iter);
-        __syncwarp();
+        gsync();
         const int code = kg.sc->status;
         if (code == mpc::STATUS_RETRY_BIG && P.retry_list) {
           if (tid == 0) {
@@ -341,9 +347,9 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
             P.retry_list[slot] = prev_b;
           }
         } else {
-          __syncwarp();
+          gsync();
           if (code == mpc::STATUS_RETRY_BIG && tid == 0) kg.sc->status = MPC_STATUS_MAX_ITER;
-          __syncwarp();
+          gsync();
           mpc::scatter(wx, kg, P.forces + (size_t)12 * prev_b,
                        P.solution ? P.solution + (size_t)12 * P.h * prev_b : nullptr, P.status ? P.status + prev_b : nullptr);
           if (P.n_peers > 0 && tid < 12) {
@@ -503,10 +509,20 @@ enum { V_64 = 0, V_96, V_128, V_GENERIC, V_COUNT };
   }
 #define MPC_VARIANT_CALL(v, prof, EXPR)                       \
   if (prof) { MPC_VARIANT_CALL1(v, true, EXPR) } else { MPC_VARIANT_CALL1(v, false, EXPR) }
-#define MPC_PIPE_CALL(v, EXPR)                                                                                \
-  switch (v) {                                                                                               \
-    case V_64: { auto kern = mpc_solve_pipe_kernel<MPC_V64_SHAPE, MPC_MINB0, false>; EXPR; } break;          \
-    default: { auto kern = mpc_solve_pipe_kernel<256, 16, 6, 16, 6, MPC_MINB96, false>; EXPR; } break;       \
+#ifndef MPC_NG64   // threads of the active-set role in the piped kernels (32: one warp; more: a barrier group)
+#define MPC_NG64 32
+#endif
+#ifndef MPC_NG96
+#define MPC_NG96 128
+#endif
+#ifndef MPC_NG128
+#define MPC_NG128 128
+#endif
+#define MPC_PIPE_CALL(v, EXPR)                                                                                 \
+  switch (v) {                                                                                                \
+    case V_64: { auto kern = mpc_solve_pipe_kernel<MPC_V64_SHAPE, MPC_MINB0, false, MPC_NG64>; EXPR; } break;       \
+    case V_96: { auto kern = mpc_solve_pipe_kernel<256, 16, 6, 16, 6, MPC_MINB96, false, MPC_NG96>; EXPR; } break; \
+    default: { auto kern = mpc_solve_pipe_kernel<256, 16, 8, 16, 8, MPC_MINB128, true, MPC_NG128>; EXPR; } break; \
   }
 const int kVariantThreads[V_COUNT] = {MPC_V64_NT, 256, 256, 256};
 const int kVariantPad[V_COUNT] = {64, 96, 128, 0};
@@ -566,10 +582,11 @@ int build_classes(mpc_batch* eng) {
     if ((int)c.smem > max_smem) continue;
     int rc = configure_kernel(eng, c);
     if (rc) return rc;
-    // Piped for nv <= 60 (+12 % on trot horizon 10) and nv <= 96 (+6 % on gallop horizon 16).  Not for nv <= 128:
-    // with nine working-set changes per problem on average the active set is better off on the whole CTA than on one
-    // warp beside the next assembly (measured -9 % on four-stance horizon 10).  MPC_NO_PIPE: development switch.
-    const bool try_pipe = !getenv("MPC_NO_PIPE") && c.variant != V_128;
+    // Piped: +12 % for nv <= 60 (trot horizon 10, active set on one warp), +13 % for nv <= 96 (gallop horizon 16) and
+    // +11 % for nv <= 128 (four-stance horizon 10), the latter two with the active set on a 128-thread group (on one
+    // warp the nv <= 128 class LOSES 9 %: nine working-set changes per problem).
+    const char* np = getenv("MPC_NO_PIPE");  // development switch: "1" nothing piped, "2" not the nv <= 128 class
+    const bool try_pipe = !(np && (np[0] == '1' || (np[0] == '2' && c.variant == V_128)));
     if (try_pipe && (c.variant != V_64 || MPC_V64_NT == 128)) {
       // piped layout: the largest working-set tile that keeps the class's CTAs per SM; not worth it below 16 rows
       int sm_smem = 0;
