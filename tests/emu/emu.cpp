@@ -112,4 +112,33 @@ void emu_build_records(const float* ticks, int batch, int h, unsigned char* reco
                                 state_out ? state_out + 4 * b : nullptr);
 }
 
+// Layout check (no solve): byte ranges [begin, end) inside the fast workspace of every region a Work points to, for
+// per-problem set `set` of make_layout(h, nv_cap, m_cap, 1, npad, packed, pipe).  out[2*i], out[2*i+1]; returns the
+// number of regions, *fast_bytes the workspace size.  Order: sc, g, x, stance, posk, amask, W, Wia, Wiz, C, M, xs, qe,
+// psum, mom, T, ck, ub, Wca, Wcz, w, r, u, tcol, red, Hm.
+int emu_layout_regions(int h, int nv_cap, int m_cap, int npad, int packed, int pipe, int set, long* out, long* fast_bytes) {
+  using namespace mpc;
+  const Layout L = make_layout(h, nv_cap, m_cap, 1, npad, packed, pipe);
+  std::vector<char> fast(L.fast_bytes + 64);
+  char* base = fast.data();
+  while (((uintptr_t)base & 15) != 0) base++;
+  const Work k = carve(L, base, nullptr, set);
+  *fast_bytes = L.fast_bytes;
+  const int hm = packed ? nv_cap * (nv_cap + 1) / 2 : nv_cap * L.ld;
+  struct R { const void* p; long bytes; };
+  const R regs[] = {
+      {k.sc, (long)sizeof(Scalars)}, {k.g, 8L * nv_cap}, {k.x, 8L * nv_cap}, {k.stance, 16L * h}, {k.posk, 16L * h},
+      {k.amask, 16L * h}, {k.W, 4L * (m_cap + 1)}, {k.Wia, 4L * (m_cap + 1)}, {k.Wiz, 4L * (m_cap + 1)},
+      {k.C, 8L * 3 * 156}, {k.M, 8L * 6 * 144}, {k.xs, 8L * 39}, {k.qe, 8L * 12 * h}, {k.psum, 8L * 5 * h},
+      {k.mom, 8L * 3 * 12 * h}, {k.T, 8L * m_cap * L.ldT}, {k.ck, 8L * L.ck_len}, {k.ub, 8L * 4 * h},
+      {k.Wca, 8L * (m_cap + 1)}, {k.Wcz, 8L * (m_cap + 1)}, {k.w, 8L * (m_cap + 1)}, {k.r, 8L * (m_cap + 1)},
+      {k.u, 8L * (m_cap + 1)}, {k.tcol, 8L * (m_cap + 1)}, {k.red, 8L * kRedDoubles}, {k.Hm, 8L * hm}};
+  const int n = (int)(sizeof(regs) / sizeof(regs[0]));
+  for (int i = 0; i < n; i++) {
+    out[2 * i] = (long)((const char*)regs[i].p - base);
+    out[2 * i + 1] = out[2 * i] + regs[i].bytes;
+  }
+  return n;
+}
+
 }  // extern "C"

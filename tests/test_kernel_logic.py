@@ -168,3 +168,53 @@ def test_packed_layout_gives_the_same_answers(monkeypatch):
         assert np.array_equal(packed["H"], full["H"]) and np.array_equal(packed["g"], full["g"])
         assert rel(packed["sol"], full["sol"]).max() < 1e-10
         assert (packed["iters"] == full["iters"]).all()
+
+
+REGIONS = ["sc", "g", "x", "stance", "posk", "amask", "W", "Wia", "Wiz", "C", "M", "xs", "qe", "psum", "mom", "T", "ck",
+           "ub", "Wca", "Wcz", "w", "r", "u", "tcol", "red", "Hm"]
+
+
+def _regions(h, nv_cap, m_cap, npad, packed, pipe, which):
+    import ctypes
+    from common import emu_lib
+    L = emu_lib()
+    out = (ctypes.c_long * (2 * len(REGIONS)))()
+    fb = ctypes.c_long()
+    n = L.emu_layout_regions(h, nv_cap, m_cap, npad, packed, pipe, which, out, ctypes.byref(fb))
+    assert n == len(REGIONS)
+    return {REGIONS[i]: (out[2 * i], out[2 * i + 1]) for i in range(n)}, fb.value
+
+
+@pytest.mark.parametrize("h,nv_cap,m_cap,npad,packed", [(10, 60, 27, 64, 0), (14, 60, 21, 64, 0), (16, 96, 33, 96, 0),
+                                                         (10, 120, 31, 128, 1), (20, 128, 33, 128, 1)])
+def test_piped_layout_keeps_the_two_roles_apart(h, nv_cap, m_cap, npad, packed):
+    """mpc_solve_pipe_kernel: while one role runs the active set of problem n-1 (set A) the other assembles problem n
+    (set B).  Everything the assembly front writes must be disjoint from everything the active set touches, every
+    region must lie inside the workspace, and the two per-problem sets must not share their scalars / stance lists."""
+    A, fb = _regions(h, nv_cap, m_cap, npad, packed, 1, 0)
+    B, fb2 = _regions(h, nv_cap, m_cap, npad, packed, 1, 1)
+    assert fb == fb2
+    for R in (A, B):
+        for name, (lo, hi) in R.items():
+            assert 0 <= lo <= hi <= fb, (name, lo, hi, fb)
+    front_writes = ["sc", "stance", "posk", "amask", "C", "M", "xs", "qe", "psum", "mom", "g"]
+    active_set = ["sc", "x", "posk", "amask", "W", "Wia", "Wiz", "T", "ub", "Wca", "Wcz", "w", "r", "u", "tcol", "Hm"]
+
+    def overlap(a, b):
+        return a[0] < b[1] and b[0] < a[1]
+    for f in front_writes:
+        for g in active_set:
+            assert not overlap(B[f], A[g]), (f, g, B[f], A[g])
+            assert not overlap(A[f], B[g]), (f, g)
+    # within one set no two distinct regions overlap either, except the deliberate aliases of the un-piped layout
+    names = list(A)
+    for i, a in enumerate(names):
+        for b in names[i + 1:]:
+            assert not overlap(A[a], A[b]), (a, b, A[a], A[b])
+
+
+def test_unpiped_layout_regions_are_inside_the_workspace():
+    for packed in (0, 1):
+        R, fb = _regions(10, 60, 33, 64, packed, 0, 0)
+        for name, (lo, hi) in R.items():
+            assert 0 <= lo <= hi <= fb, (name, lo, hi, fb)
