@@ -187,7 +187,7 @@ def run_ours(args):
     n_sets = max(2, min(N_SETS, int(np.ceil(2.2 * L2_BYTES / (B * stride)))))
     host_sets = [W.config2(B, h, 1234 + 1000 * rank + i) for i in range(n_sets)]
     dev_sets = [torch.from_numpy(s).to(dev) for s in host_sets]
-    # Consecutive steps are independent batches, so they alternate between the engine's two scratch slots on two
+    # Consecutive steps are independent batches, so they alternate between two of the engine's scratch slots on two
     # streams: the tail of step i (a few CTAs still solving) shares the GPU with the head of step i+1.
     streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
     forces2 = [torch.empty((B, 12), dtype=torch.float32, device=dev) for _ in range(2)]
@@ -337,7 +337,7 @@ def run_ours(args):
                                    "friction-cone rows per step, seed 1234+" % (B, h),
                        "l2": "inputs rotate over %d distinct record sets (%.0f MB > 126 MB L2), no flush needed"
                              % (n_sets, n_sets * B * stride / 1e6),
-                       "pipelining": ("steps alternate between the engine's two scratch slots / streams (independent batches)"
+                       "pipelining": ("steps alternate between two of the engine's scratch slots / streams (independent batches)"
                                       if overlap else "one stream, steps strictly one after another"),
                        "collective": ("none (N=1)" if world == 1 else
                                       "peer stores from the solve kernel + device-side flag barrier (no NCCL on the path)" if peer else
