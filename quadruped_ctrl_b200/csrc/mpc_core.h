@@ -601,28 +601,29 @@ MPC_HD void assemble_front(const Cx& cx, const float* rec, const unsigned char* 
     }
     k.g[v] = 2.0 * (acc0 + acc1);
   }
-  // six tables M_ab, a <= b (M_ba = M_ab'), of which only those with b < na are needed (three without drag); one
-  // thread per ENTRY (table, i, j), rows q ascending -- 432 entries over the CTA instead of 36 threads doing a row
-  // of twelve each
-  {
-    const int ntab = na == 2 ? 3 : 6;
-    MPC_FOR(e, ntab * 144) {
-      const int t = e / 144, ij = e - 144 * t, i = ij / 12, j = ij - 12 * i;
-      // na == 2: tables 0 (0,0), 1 (0,1), 3 (1,1);  na == 3: all six in order
-      const int tb = na == 2 ? (t == 2 ? 3 : t) : t;
-      const int a = tb < 3 ? 0 : (tb < 5 ? 1 : 2), b = tb < 3 ? tb : (tb < 5 ? tb - 2 : 2);
+  // six tables M_ab, a <= b (M_ba = M_ab'), of which only those with b < na are needed; one thread per (table,
+  // row): twelve independent accumulators, each weighted C_a entry loaded once.  (One thread per ENTRY spreads the
+  // work over the whole CTA and was 2 % faster in the one-problem kernel, but it is the longer chain, and in the
+  // piped kernel this phase sits on the critical path beside the other problem's active set: -3 %.)
+  MPC_FOR(e, 6 * 12) {
+    const int tb = e / 12, i = e - 12 * tb;
+    const int a = tb < 3 ? 0 : (tb < 5 ? 1 : 2), b = tb < 3 ? tb : (tb < 5 ? tb - 2 : 2);
+    if (b < na) {  // a <= b
       const double* Ca = C0 + 156 * a;
       const double* Cb = C0 + 156 * b;
       const unsigned mask = rowmask[a] & rowmask[b];
-      double acc = 0.0;
-#pragma unroll 4
+      double acc[12];
+#pragma unroll
+      for (int j = 0; j < 12; j++) acc[j] = 0.0;
       for (int q = 0; q < 12; q++) {
         if ((mask >> q) & 1u) {
           const double wa = (double)rec[MPC_REC_WEIGHTS + q] * Ca[q * 12 + i];
-          acc += wa * Cb[q * 12 + j];
+#pragma unroll
+          for (int j = 0; j < 12; j++) acc[j] += wa * Cb[q * 12 + j];
         }
       }
-      k.M[tb * 144 + ij] = acc;
+#pragma unroll
+      for (int j = 0; j < 12; j++) k.M[tb * 144 + i * 12 + j] = acc[j];
     }
   }
   cx.sync();
