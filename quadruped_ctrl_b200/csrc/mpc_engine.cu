@@ -159,6 +159,32 @@ __global__ void mpc_gather_barrier_kernel(unsigned* const* peer_flags, const uns
   }
 }
 
+// Shard-and-gather epilogue: one problem's 12 forces go straight into every rank's gather buffer over NVLink -- three
+// 16-byte stores per peer (lanes 0..2) when the rows are 16-byte aligned, twelve 4-byte ones otherwise.  Called by the
+// threads that just wrote forces[12*b ..] (lane i wrote element i, so a lane reads back what lanes of its own warp
+// stored: the caller has synchronised them).
+__device__ __forceinline__ void peer_store_forces(const SolveParams& P, int b, int tid) {
+  const float* src = P.forces + (size_t)12 * b;
+  const size_t row = (size_t)12 * (P.rank_offset + b);
+  bool wide = (((uintptr_t)P.forces) & 15) == 0;
+#pragma unroll
+  for (int q = 0; q < kMaxPeers; q++)
+    if (q < P.n_peers && P.peers[q]) wide = wide && ((((uintptr_t)P.peers[q]) & 15) == 0);
+  if (wide) {
+    if (tid < 3) {
+      const float4 f = *reinterpret_cast<const float4*>(src + 4 * tid);
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; q++)
+        if (q < P.n_peers && P.peers[q]) *reinterpret_cast<float4*>(P.peers[q] + row + 4 * tid) = f;
+    }
+  } else if (tid < 12) {
+    const float f = src[tid];
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; q++)
+      if (q < P.n_peers && P.peers[q]) P.peers[q][row + tid] = f;
+  }
+}
+
 // NT threads per CTA.  R > 0: register-resident inversion with R x C tiles on a GR x GC thread grid (NT == GR*GC,
 // padded size GR*R == GC*C).  R == 0: the generic shared/global-memory sweep, used by the catch-all class whose
 // matrix does not fit in the register file of one SM.
@@ -269,12 +295,9 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
       __syncthreads();
       mpc::scatter(cx, k, P.forces + (size_t)12 * b, P.solution ? P.solution + (size_t)12 * P.h * b : nullptr,
                    P.status ? P.status + b : nullptr);
-      if (P.n_peers > 0 && threadIdx.x < 12) {
-        // shard-and-gather epilogue: the forces go straight into every rank's gather buffer over NVLink
-        const float f = P.forces[(size_t)12 * b + threadIdx.x];
-#pragma unroll
-        for (int q = 0; q < kMaxPeers; q++)
-          if (q < P.n_peers && P.peers[q]) P.peers[q][(size_t)12 * (P.rank_offset + b) + threadIdx.x] = f;
+      if (P.n_peers > 0) {
+        __syncwarp();  // lanes 0..11 wrote the forces, lanes 0..2 read them back four at a time
+        peer_store_forces(P, b, (int)threadIdx.x);
       }
     }
     __syncthreads();
@@ -352,11 +375,9 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
           gsync();
           mpc::scatter(wx, kg, P.forces + (size_t)12 * prev_b,
                        P.solution ? P.solution + (size_t)12 * P.h * prev_b : nullptr, P.status ? P.status + prev_b : nullptr);
-          if (P.n_peers > 0 && tid < 12) {
-            const float f = P.forces[(size_t)12 * prev_b + tid];
-#pragma unroll
-            for (int q = 0; q < kMaxPeers; q++)
-              if (q < P.n_peers && P.peers[q]) P.peers[q][(size_t)12 * (P.rank_offset + prev_b) + tid] = f;
+          if (P.n_peers > 0) {
+            __syncwarp();
+            peer_store_forces(P, prev_b, tid);
           }
         }
       }
@@ -384,11 +405,9 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
       __syncthreads();
       mpc::scatter(cx, k, P.forces + (size_t)12 * b, P.solution ? P.solution + (size_t)12 * P.h * b : nullptr,
                    P.status ? P.status + b : nullptr);
-      if (P.n_peers > 0 && tid < 12) {
-        const float f = P.forces[(size_t)12 * b + tid];
-#pragma unroll
-        for (int q = 0; q < kMaxPeers; q++)
-          if (q < P.n_peers && P.peers[q]) P.peers[q][(size_t)12 * (P.rank_offset + b) + tid] = f;
+      if (P.n_peers > 0) {
+        __syncwarp();
+        peer_store_forces(P, b, tid);
       }
       prev_b = -1;
       __syncthreads();
