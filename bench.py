@@ -189,11 +189,12 @@ def run_ours(args):
     dev_sets = [torch.from_numpy(s).to(dev) for s in host_sets]
     # Consecutive steps are independent batches, so they alternate between two of the engine's scratch slots on two
     # streams: the tail of step i (a few CTAs still solving) shares the GPU with the head of step i+1.
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-    forces2 = [torch.empty((B, 12), dtype=torch.float32, device=dev) for _ in range(2)]
-    status2 = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(2)]
+    nq = max(1, min(args.inflight, E.SLOTS))   # batches in flight on the device-resident path
+    streams = [torch.cuda.Stream(dev) for _ in range(nq)]
+    forces2 = [torch.empty((B, 12), dtype=torch.float32, device=dev) for _ in range(nq)]
+    status2 = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(nq)]
     forces, status = forces2[0], status2[0]
-    gathered2 = [torch.empty((world * B, 12), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    gathered2 = [torch.empty((world * B, 12), dtype=torch.float32, device=dev) for _ in range(nq)] if world > 1 else None
     gathered = gathered2[0] if world > 1 else None
     peer = world > 1 and args.gather == "peer"
     if peer:  # fused: the solve kernel stores every force straight into all ranks' gather buffers over NVLink
@@ -202,7 +203,7 @@ def run_ours(args):
     overlap = not args.serial
 
     def step(i):
-        q = (i & 1) if overlap else 0
+        q = (i % nq) if overlap else 0
         if overlap:
             with torch.cuda.stream(streams[q]):
                 eng.solve_device(dev_sets[i % n_sets], forces=forces2[q], status=status2[q], stream=streams[q], slot=q)
@@ -337,7 +338,7 @@ def run_ours(args):
                                    "friction-cone rows per step, seed 1234+" % (B, h),
                        "l2": "inputs rotate over %d distinct record sets (%.0f MB > 126 MB L2), no flush needed"
                              % (n_sets, n_sets * B * stride / 1e6),
-                       "pipelining": ("steps alternate between two of the engine's scratch slots / streams (independent batches)"
+                       "pipelining": ("steps rotate over %d of the engine's scratch slots / streams (independent batches)" % nq
                                       if overlap else "one stream, steps strictly one after another"),
                        "collective": ("none (N=1)" if world == 1 else
                                       "peer stores from the solve kernel + device-side flag barrier (no NCCL on the path)" if peer else
@@ -376,6 +377,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--serial", action="store_true", help="one stream, no overlap between consecutive steps")
+    ap.add_argument("--inflight", type=int, default=3, help="batches in flight on the device-resident path (<= 3)")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
                     help="N>1: NCCL all-gather of the forces (default) or the kernel's fused peer-store epilogue")
     args = ap.parse_args()
