@@ -81,6 +81,10 @@ struct Scalars {
 constexpr int kSweepGroup = 16;  // pivots per pass of the generic sweep (see invert_spd)
 constexpr int kAsmDoubles(int h) { return 3 * 156 + 6 * 144 + 39 + 12 * h + 5 * h; }
 constexpr int kRedDoubles = 40;
+// DMMA grouped sweep (invert_spd_mma): its panel buffers live in the Hm region, which must be large enough
+constexpr int kMmaGroup = 8;                                              // pivots per group (= block size)
+constexpr int mma_panel_ld(int nvp) { return nvp + 4; }                   // = 4 mod 16: fragment loads conflict-free
+constexpr int mma_panel_doubles(int nvp) { return 3 * kMmaGroup * mma_panel_ld(nvp) + kMmaGroup * kMmaGroup + kMmaGroup; }  // G, F, U, T, 1/d
 
 inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
@@ -121,6 +125,7 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
   int t_doubles = m_cap * L.ldT;
   int hm_doubles = packed ? nv_cap * (nv_cap + 1) / 2 : nv_cap * L.ld;
   if (hm_doubles < 3 * 12 * h) hm_doubles = 3 * 12 * h;  // the assembly parks its moment sums there
+  if (npad > 0 && hm_doubles < mma_panel_doubles(npad)) hm_doubles = mma_panel_doubles(npad);  // panel of the DMMA sweep
   if (big_in_fast) gi += t_doubles;
   if (pipe) {
     o += 8 * un;                 // assembly scratch
@@ -139,6 +144,7 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
   }
   L.off_red = o;
   o += 8 * kRedDoubles;
+  o = (o + 15) / 16 * 16;  // the DMMA sweep stores 16 bytes at a time into its panel (in the Hm region)
   L.off_Hm = o;
   L.off_T = pipe ? L.off_gi : L.off_union;  // T sits at the start of the active-set scratch
   if (big_in_fast) o += 8 * hm_doubles;
@@ -1016,6 +1022,279 @@ __device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid, bool wi
             if (!sweep_block_kept<GR, GC>(c / GR, r / (2 * GC))) Hm[c * ld + r] = val;
           } else if (r >= c) {
             Hm[tri_index(r, c)] = val;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// Stage 2 on the FP64 tensor pipe (device only): a grouped symmetric sweep whose rank-8 updates, panel and pivot
+// block all run as DMMA.8x8x4 (mma.sync.m8n8k4.f64).
+//
+// The sweep of invert_spd_tiles applies one rank-1 update per pivot, with a publish -> barrier -> load -> update
+// chain per pivot (60 barriers for a trot problem) and 8 issue slots per 256 FMAs.  Here pivots are taken eight at
+// a time (a block row of the 8x8 block grid).  Nothing is inverted blockwise -- the group's pivots are still
+// eliminated one after the other, through the factored form, so the alpha-regularised null space that rules out
+// block sweeps (see invert_spd) does not matter:
+//   (A)  gather      the 8 pivot rows of the group (= block row b and, by symmetry, block column b) go from the
+//                    accumulator fragments to shared memory (G);
+//   (B1) pivot block one warp sweeps the 8x8 block of the pivot columns pivot by pivot (fragment layout, one
+//                    rank-1 DMMA per pivot), carrying the row operations along on an identity block.  Row g of
+//                    either block is frozen the moment g becomes the pivot: that gives the frozen pivot-column
+//                    part of row g (slot p holding d-1, as in invert_spd_tiles), u_g = -row_g/d_g, 1/d_g, and
+//                    row g of T, the accumulated row operation (unit lower triangular);
+//   (B2) panel       frozen rows of all other columns F = T G, two DMMAs per 8 columns, and U = -D^{-1} F;
+//   (C)  update      A += U' F for every stored 8x8 block: two DMMAs (pivots 0-3, 4-7, i.e. pivot order) fed by
+//                    one A fragment (u values of the block's rows) and one B fragment (frozen rows of its columns).
+// Three CTA barriers per GROUP instead of one per pivot, and 1/8 of the issue slots for the same FMAs.
+//
+// Storage: the NVP x NVP matrix (NVP = 8*NB, identity padding, row nv = the gradient as in invert_spd_tiles) is
+// held as 8x8 accumulator fragments (lane l: row l/4, columns 2*(l%4), 2*(l%4)+1).  Of every pair of mirror
+// blocks only one is stored, chosen cyclically so that every warp owns whole block rows with the same number of
+// blocks: block row i holds the columns (i+k) mod NB for k = 0 .. NB/2-1, plus k = NB/2 for the rows i with
+// (i < NB/2) != (i odd) -- each pair {i, i+NB/2} exactly once.  Warp w owns block rows w*RW .. w*RW+RW-1.
+// The panel buffers live in the Hm region (H is in registers for the whole sweep and H^{-1} is only stored at the
+// end), so the stage needs no shared memory of its own.
+// ---------------------------------------------------------------------------
+// shared-window accesses by 32-bit byte address (volatile: ordered with each other and with the DMMAs)
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void lds_f64x2(uint32_t a, double& v0, double& v1) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(a));
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f64_if(bool p, uint32_t a, double v) {  // predicated: no branch, no divergence
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %0, 0;\n@q st.shared.f64 [%1], %2;\n}" ::"r"((int)p), "r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t a, double v0, double v1) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v0), "d"(v1) : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// NT threads in the CTA, of which the first NWS warps sweep (the others only meet the barriers).
+template <int NT, int NWS, int NB, bool kPacked>
+__device__ __forceinline__ void invert_spd_mma(const Work& k, int tid, bool with_g) {
+  constexpr int NVP = 8 * NB, RW = NB / NWS, HB = NB / 2, NSLOT = HB + 1, NCOL = RW - 1 + NSLOT;
+  constexpr int LDP = NVP + 4, KG = 8;  // = mma_panel_ld(NVP), kMmaGroup (host-side constexpr functions)
+  static_assert(NB % NWS == 0 && HB % 2 == 0 && NWS * 32 <= NT && (NWS & (NWS - 1)) == 0, "block rows per warp");
+  Scalars* sc = k.sc;
+  const int nv = sc->nv, ld = k.ld;
+  double* Hm = k.Hm;
+  const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+  const bool gaug = with_g && nv < NVP;
+  const bool active = warp < NWS;
+  const int i0 = warp * RW;  // first block row of this warp
+  // slot (ri, ks): block row i0 + ri, block column colb[ri + ks] = (i0 + ri + ks) mod NB; ks == HB only for the
+  // "extra" rows
+  auto extra = [](int i) { return (i < HB) != ((i & 1) != 0); };
+  int colb[NCOL];
+  bool ext[RW];
+#pragma unroll
+  for (int t = 0; t < NCOL; t++) colb[t] = (i0 + t >= NB) ? i0 + t - NB : i0 + t;
+#pragma unroll
+  for (int ri = 0; ri < RW; ri++) ext[ri] = extra(i0 + ri);
+  double c[RW][NSLOT][2];
+  if (active) {
+#pragma unroll
+    for (int ri = 0; ri < RW; ri++) {
+      const int r = 8 * (i0 + ri) + lr;
+#pragma unroll
+      for (int ks = 0; ks < NSLOT; ks++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int cc = 8 * colb[ri + ks] + 2 * lc + e;
+          double v = (r == cc) ? 1.0 : 0.0;
+          if (ks < HB || ext[ri]) {
+            if (r < nv && cc < nv) v = Hm[hixT<kPacked>(ld, r, cc)];
+            if (gaug && r == nv && cc < nv) v = k.g[cc];
+            if (gaug && cc == nv && r < nv) v = k.g[r];
+          }
+          c[ri][ks][e] = v;
+        }
+      }
+    }
+  }
+  __syncthreads();  // H is in registers everywhere: the Hm region becomes the panel buffer
+  // carve() picks Hm from shared memory or the global slab at run time, which leaves a generic pointer behind, and
+  // generic LD / ST on the panel cost three times what LDS / STS do: the panel is addressed in the shared window
+  // explicitly (32-bit byte addresses, ld.shared / st.shared)
+  const uint32_t G = (uint32_t)__cvta_generic_to_shared(Hm);  // [KG][LDP]  gathered rows of the current group
+  const uint32_t F = G + 8 * KG * LDP;                         // [KG][LDP]  frozen rows
+  const uint32_t U = G + 8 * 2 * KG * LDP;                     // [KG][LDP]  -frozen row / pivot
+  const uint32_t TF = G + 8 * 3 * KG * LDP;                    // [KG][KG]   frozen rows of the row operation T
+  const uint32_t DI = TF + 8 * KG * KG;                        // [KG]       reciprocals of the group's pivots
+  const uint32_t frag = 8 * (lc * LDP + lr);                   // fragment position: row lc (+4), column lr
+  bool bad = false;
+  const int ngroups = (nv + KG - 1) / KG;
+#ifdef MPC_SWEEP_CLK  // harness only (tools/microbench/sweep_mma_test.cu): cycles per phase, summed over the groups
+  long long tA = 0, tB = 0, tB1 = 0, tC = 0, wA = 0, wB1 = 0, wB = 0, tq = clock64();
+#define MPC_SWEEP_TICK(acc) do { const long long now_ = clock64(); acc += now_ - tq; tq = now_; } while (0)
+#else
+#define MPC_SWEEP_TICK(acc) do { } while (0)
+#endif
+#pragma unroll 1
+  for (int b = 0; b < ngroups; b++) {
+    const int p0 = KG * b;
+    // ---- (A) gather: block row b as rows, block column b transposed ----
+    if (active) {
+#pragma unroll
+      for (int ri = 0; ri < RW; ri++) {
+        if (i0 + ri == b) {  // uniform per warp
+#pragma unroll
+          for (int ks = 0; ks < NSLOT; ks++)
+            if (ks < HB || ext[ri])
+              sts_f64x2(G + 8 * (lr * LDP + 2 * lc) + 64 * colb[ri + ks], c[ri][ks][0], c[ri][ks][1]);
+        } else {
+          const uint32_t gt = G + 8 * ((2 * lc) * LDP + 8 * (i0 + ri) + lr);
+#pragma unroll
+          for (int ks = 1; ks < NSLOT; ks++)
+            if (colb[ri + ks] == b && (ks < HB || ext[ri])) {
+              sts_f64(gt, c[ri][ks][0]);
+              sts_f64(gt + 8 * LDP, c[ri][ks][1]);
+            }
+        }
+      }
+    }
+    MPC_SWEEP_TICK(tA);
+    __syncthreads();
+    MPC_SWEEP_TICK(wA);
+    // ---- (B1) pivot block, one warp.  d = the 8x8 block of the pivot columns, t = T' (the transposed row
+    //      operation, starts as the identity), both in fragment layout.  Pivot g: the pivot row at index lr comes
+    //      from COLUMN g of d (the block is symmetric; the element sits in this lane's own quad), row g of T from
+    //      column g of t; both are frozen (stored) and the rank-1 updates d += a v', t += w a' are one DMMA each
+    //      with the operands in the k = 0 slot.  Straight-line code: the pivots past the last one of a short last
+    //      group are turned into no-ops by selects (d = 1, zero row), not by branches -- one basic block, so the
+    //      stores and the T update fill the gaps of the chain. ----
+    if (warp == (b & (NWS - 1))) {
+      double d0, d1;
+      lds_f64x2(G + 8 * (lr * LDP + p0 + 2 * lc), d0, d1);
+      double t0 = (lr == 2 * lc) ? 1.0 : 0.0, t1 = (lr == 2 * lc + 1) ? 1.0 : 0.0;
+      const bool k0 = lc == 0;
+      const uint32_t fo = F + 8 * (p0 + lr), uo = U + 8 * (p0 + lr), to = TF + 8 * lr;
+#pragma unroll
+      for (int g = 0; g < KG; g++) {
+        const int src = (lane & ~3) + (g >> 1);
+        const bool live = p0 + g < nv;  // uniform
+        double v = __shfl_sync(0xffffffffu, (g & 1) ? d1 : d0, src);                // D(lr, g) = D(g, lr)
+        double dp = __shfl_sync(0xffffffffu, (g & 1) ? d1 : d0, 4 * g + (g >> 1));  // D(g, g)
+        double w = __shfl_sync(0xffffffffu, (g & 1) ? t1 : t0, src);                // T'(lr, g) = T(g, lr)
+        v = live ? v : 0.0;
+        dp = live ? dp : 1.0;
+        w = live ? w : 0.0;
+        const double dinv = fast_rcp(dp);
+        // positive, normal and < 1e300, tested on the high word (see invert_spd_tiles)
+        bad = bad || (unsigned)(__double2hiint(dinv) - 0x00100000) >= (unsigned)(0x7E37E43C - 0x00100000);
+        if (lr == g) v = dp - 1.0;
+        const double a = -v * dinv;
+        const double az = k0 ? a : 0.0;
+        dmma884(d0, d1, az, k0 ? v : 0.0);
+        dmma884(t0, t1, k0 ? w : 0.0, az);
+        // frozen row g at the pivot columns, its scaled copy, row g of T, 1/d (predicated stores: a branch here
+        // would diverge the warp once per pivot, in the middle of the chain)
+        sts_f64_if(k0, fo + 8 * g * LDP, v);
+        sts_f64_if(k0, uo + 8 * g * LDP, a);
+        sts_f64_if(k0, to + 8 * g * KG, w);
+        sts_f64_if(lane == 0, DI + 8 * g, dinv);
+      }
+    }
+    MPC_SWEEP_TICK(tB1);
+    __syncthreads();
+    MPC_SWEEP_TICK(wB1);
+    // ---- (B2) frozen rows of the other columns, F = T G (rows past the last pivot come out as zeros), U = -F/d ----
+    if (active) {
+      const double ta0 = lds_f64(TF + 8 * (lr * KG + lc)), ta1 = lds_f64(TF + 8 * (lr * KG + 4 + lc));
+      const double ndi = -lds_f64(DI + 8 * lr);
+#pragma unroll
+      for (int j = 0; j < RW; j++) {
+        const int cbk = i0 + j;
+        if (cbk == b) continue;  // uniform: the pivot columns are done
+        const double g0 = lds_f64(G + frag + 64 * cbk), g1 = lds_f64(G + frag + 8 * 4 * LDP + 64 * cbk);
+        double f0 = 0.0, f1 = 0.0;
+        dmma884(f0, f1, ta0, g0);
+        dmma884(f0, f1, ta1, g1);
+        sts_f64x2(F + 8 * (lr * LDP + 2 * lc) + 64 * cbk, f0, f1);
+        sts_f64x2(U + 8 * (lr * LDP + 2 * lc) + 64 * cbk, f0 * ndi, f1 * ndi);
+      }
+    }
+    MPC_SWEEP_TICK(tB);
+    __syncthreads();
+    MPC_SWEEP_TICK(wB);
+    // ---- (C) rank-8 update of every stored block on the tensor pipe ----
+    if (active) {
+      const uint32_t Fp = F + frag;  // B fragment: F[g = lc (+4)][8*cb + lr]
+      const uint32_t Up = U + frag;  // A fragment: U[g = lc (+4)][8*i + lr]
+      double a0[RW], a1[RW];
+#pragma unroll
+      for (int ri = 0; ri < RW; ri++) {
+        a0[ri] = lds_f64(Up + 64 * (i0 + ri));
+        a1[ri] = lds_f64(Up + 8 * 4 * LDP + 64 * (i0 + ri));
+      }
+      // t = ri + ks: one B fragment serves every row that has column colb[t].  The fragment loads are volatile asm
+      // (ordered with the DMMAs) and pipelined one step ahead by hand: left to itself the compiler hoists all of
+      // them above the first DMMA and spills accumulators in the larger classes.
+      double b0 = lds_f64(Fp + 64 * colb[0]), b1 = lds_f64(Fp + 8 * 4 * LDP + 64 * colb[0]);
+#pragma unroll
+      for (int t = 0; t < NCOL; t++) {
+        const double b0c = b0, b1c = b1;
+        if (t + 1 < NCOL) {
+          b0 = lds_f64(Fp + 64 * colb[t + 1]);
+          b1 = lds_f64(Fp + 8 * 4 * LDP + 64 * colb[t + 1]);
+        }
+#pragma unroll
+        for (int ri = 0; ri < RW; ri++) {
+          const int ks = t - ri;
+          if (ks < 0 || ks >= NSLOT) continue;
+          if (ks == HB && !ext[ri]) continue;  // uniform per warp
+          dmma884(c[ri][ks][0], c[ri][ks][1], a0[ri], b0c);
+          dmma884(c[ri][ks][0], c[ri][ks][1], a1[ri], b1c);
+        }
+      }
+    }
+    MPC_SWEEP_TICK(tC);
+  }
+#ifdef MPC_SWEEP_CLK
+  if (k.clk && lane == 0 && warp < 4) { long long* c_ = k.clk + 8 * (1 + warp); c_[0] += tA; c_[1] += wA; c_[2] += tB1; c_[3] += wB1; c_[4] += tB; c_[5] += wB; c_[6] += tC; }
+#endif
+  if (__syncthreads_or(bad)) {  // also: everybody is done with the panel buffers
+    if (tid == 0) sc->status = MPC_STATUS_NOT_PD;
+    __syncthreads();
+    return;
+  }
+  // store H^{-1} = -(swept matrix), the 2 taken off the swept diagonal; row / column nv -> x = -H^{-1} g
+  if (active) {
+#pragma unroll
+    for (int ri = 0; ri < RW; ri++) {
+      const int i = i0 + ri, r = 8 * i + lr;
+#pragma unroll
+      for (int ks = 0; ks < NSLOT; ks++) {
+        if (!(ks < HB || ext[ri])) continue;
+        const int cb = colb[ri + ks];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int cc = 8 * cb + 2 * lc + e;
+          const double v = c[ri][ks][e];
+          if (gaug && r == nv && cc < nv) k.x[cc] = -v;
+          if (gaug && cc == nv && r < nv && i != cb) k.x[r] = -v;
+          if (r < nv && cc < nv) {
+            const double val = (cc == r) ? (2.0 - v) : -v;
+            if (!kPacked) {
+              Hm[r * ld + cc] = val;
+              if (i != cb) Hm[cc * ld + r] = val;
+            } else if (i != cb || r >= cc) {  // one writer per unordered pair
+              Hm[tri_index(r, cc)] = val;
+            }
           }
         }
       }

@@ -34,6 +34,10 @@ constexpr int kSlots = MPC_BATCH_SLOTS;  // scratch slots per engine: that many 
 constexpr int kMaxClasses = 6;
 constexpr int kRing = 256;
 
+#ifndef MPC_SWEEP_DEFAULT
+#define MPC_SWEEP_DEFAULT 0
+#endif
+
 struct SolveParams {
   const char* records;
   unsigned long long stride;
@@ -190,7 +194,9 @@ __device__ __forceinline__ void peer_store_forces(const SolveParams& P, int b, i
 // matrix does not fit in the register file of one SM.
 // PROF: the instantiation that serves the profiling / debugging entries (phase clocks, assemble-only output, stage
 // stop).  The production instantiation carries none of that code (2% faster: the kernel is instruction-fetch heavy).
-template <int NT, int GR, int R, int GC, int C, int MINB, bool PK, bool PROF>
+// SW: the register-resident inversion -- 0: invert_spd_tiles (rank-1 updates on the FP64 FMA pipe), 1: invert_spd_mma
+// (grouped sweep, rank-8 updates as DMMA.8x8x4 on the FP64 tensor pipe; NWS sweeping warps, NB = NVP / 8 block rows).
+template <int NT, int GR, int R, int GC, int C, int MINB, bool PK, bool PROF, int SW = 0>
 __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) char smem[];
   const int count = P.count ? *P.count : P.batch;
@@ -252,7 +258,8 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
       if constexpr (R > 0) {
         static_assert(R == 0 || NT == GR * GC, "thread grid");
-        mpc::invert_spd_tiles<GR, R, GC, C, PK>(k, (int)threadIdx.x, true);
+        if constexpr (SW == 1) mpc::invert_spd_mma<NT, (GR * R == 128 ? 8 : 4), GR * R / 8, PK>(k, (int)threadIdx.x, true);
+        else mpc::invert_spd_tiles<GR, R, GC, C, PK>(k, (int)threadIdx.x, true);
       } else {
         mpc::invert_spd(cx, k);
       }
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
 // its buffer until its active set is done, and the arithmetic per problem is exactly that of mpc_solve_kernel.
 // NG: threads of the active-set role (32: one warp with __syncwarp / shuffles; more: a group on hardware barrier 2);
 // the other NT - NG threads assemble on hardware barrier 1.
-template <int NT, int GR, int R, int GC, int C, int MINB, bool PK, int NG>
+template <int NT, int GR, int R, int GC, int C, int MINB, bool PK, int NG, int SW = 0>
 __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) char smem[];
   const int count = P.count ? *P.count : P.batch;
@@ -397,7 +404,10 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
     // ---- phase Y: H blocks, inversion, active-set set-up (all warps) ----
     const mpc::Work k = mpc::carve(P.L, fast, nullptr, cur);
     if (k.sc->status == MPC_STATUS_OPTIMAL) mpc::assemble_H(cx, rec, k);
-    if (k.sc->status == MPC_STATUS_OPTIMAL) mpc::invert_spd_tiles<GR, R, GC, C, PK>(k, tid, true);
+    if (k.sc->status == MPC_STATUS_OPTIMAL) {
+      if constexpr (SW == 1) mpc::invert_spd_mma<NT, (GR * R == 128 ? 8 : 4), GR * R / 8, PK>(k, tid, true);
+      else mpc::invert_spd_tiles<GR, R, GC, C, PK>(k, tid, true);
+    }
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
       mpc::active_set_init(cx, rec, gait, k, k.sc->nv < GR * R);  // x = -H^{-1} g came out of the sweep if it had room
       prev_b = b;
@@ -480,6 +490,7 @@ struct mpc_batch {
   unsigned** peer_flags_dev = nullptr;  // [kSlots][kMaxPeers]
   long long* phase_clk = nullptr;
   int ctas_per_sm_limit = 0;
+  int sweep = MPC_SWEEP_DEFAULT;  // inversion of the register-resident classes: 0 FMA tiles, 1 DMMA grouped sweep
   int debug_stop = 0;
   bool no_host_classify = false;  // env MPC_NO_HOST_CLASSIFY: batches of one take the general path too
   void* peer_open[kMaxPeers] = {nullptr};
@@ -519,15 +530,17 @@ namespace {
 #endif
 #define MPC_V64_SHAPE MPC_V64_NT, MPC_V64_GR, MPC_V64_R, MPC_V64_GC, MPC_V64_C
 enum { V_64 = 0, V_96, V_128, V_GENERIC, V_COUNT };
-#define MPC_VARIANT_CALL1(v, PROF, EXPR)                                                                     \
+#define MPC_VARIANT_CALL2(v, PROF, SW, EXPR)                                                                  \
   switch (v) {                                                                                               \
-    case V_64: { auto kern = mpc_solve_kernel<MPC_V64_SHAPE, MPC_MINB0, false, PROF>; EXPR; } break;          \
-    case V_96: { auto kern = mpc_solve_kernel<256, 16, 6, 16, 6, MPC_MINB96, false, PROF>; EXPR; } break;     \
-    case V_128: { auto kern = mpc_solve_kernel<256, 16, 8, 16, 8, MPC_MINB128, true, PROF>; EXPR; } break;    \
-    default: { auto kern = mpc_solve_kernel<256, 0, 0, 0, 0, MPC_MINBG, false, PROF>; EXPR; } break;                  \
+    case V_64: { auto kern = mpc_solve_kernel<MPC_V64_SHAPE, MPC_MINB0, false, PROF, SW>; EXPR; } break;      \
+    case V_96: { auto kern = mpc_solve_kernel<256, 16, 6, 16, 6, MPC_MINB96, false, PROF, SW>; EXPR; } break; \
+    case V_128: { auto kern = mpc_solve_kernel<256, 16, 8, 16, 8, MPC_MINB128, true, PROF, SW>; EXPR; } break; \
+    default: { auto kern = mpc_solve_kernel<256, 0, 0, 0, 0, MPC_MINBG, false, PROF, 0>; EXPR; } break;        \
   }
-#define MPC_VARIANT_CALL(v, prof, EXPR)                       \
-  if (prof) { MPC_VARIANT_CALL1(v, true, EXPR) } else { MPC_VARIANT_CALL1(v, false, EXPR) }
+// prof: the profiling instantiation (always the FMA sweep); sw: which inversion the production instantiation runs
+#define MPC_VARIANT_CALL(v, prof, sw, EXPR)                                                           \
+  if (prof) { MPC_VARIANT_CALL2(v, true, 0, EXPR) }                                                   \
+  else if (sw) { MPC_VARIANT_CALL2(v, false, 1, EXPR) } else { MPC_VARIANT_CALL2(v, false, 0, EXPR) }
 #ifndef MPC_NG64   // threads of the active-set role in the piped kernels (32: one warp; more: a barrier group)
 #define MPC_NG64 32
 #endif
@@ -537,12 +550,14 @@ enum { V_64 = 0, V_96, V_128, V_GENERIC, V_COUNT };
 #ifndef MPC_NG128
 #define MPC_NG128 128
 #endif
-#define MPC_PIPE_CALL(v, EXPR)                                                                                 \
-  switch (v) {                                                                                                \
-    case V_64: { auto kern = mpc_solve_pipe_kernel<MPC_V64_SHAPE, MPC_MINB0, false, MPC_NG64>; EXPR; } break;       \
-    case V_96: { auto kern = mpc_solve_pipe_kernel<256, 16, 6, 16, 6, MPC_MINB96, false, MPC_NG96>; EXPR; } break; \
-    default: { auto kern = mpc_solve_pipe_kernel<256, 16, 8, 16, 8, MPC_MINB128, true, MPC_NG128>; EXPR; } break; \
+#define MPC_PIPE_CALL2(v, SW, EXPR)                                                                                \
+  switch (v) {                                                                                                    \
+    case V_64: { auto kern = mpc_solve_pipe_kernel<MPC_V64_SHAPE, MPC_MINB0, false, MPC_NG64, SW>; EXPR; } break;       \
+    case V_96: { auto kern = mpc_solve_pipe_kernel<256, 16, 6, 16, 6, MPC_MINB96, false, MPC_NG96, SW>; EXPR; } break; \
+    default: { auto kern = mpc_solve_pipe_kernel<256, 16, 8, 16, 8, MPC_MINB128, true, MPC_NG128, SW>; EXPR; } break; \
   }
+#define MPC_PIPE_CALL(v, sw, EXPR) \
+  if (sw) { MPC_PIPE_CALL2(v, 1, EXPR) } else { MPC_PIPE_CALL2(v, 0, EXPR) }
 const int kVariantThreads[V_COUNT] = {MPC_V64_NT, 256, 256, 256};
 const int kVariantPad[V_COUNT] = {64, 96, 128, 0};
 
@@ -552,10 +567,15 @@ int configure_kernel(mpc_batch* eng, ClassCfg& c) {
   CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, eng->device));
   int occ = 0;
   for (int prof = 1; prof >= 0; prof--) {  // the production instantiation last: its occupancy sizes the grid
-    MPC_VARIANT_CALL(c.variant, prof, {
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c.threads, c.smem));
-    });
+    for (int sw = 1; sw >= 0; sw--) {
+      if (prof && sw) continue;
+      int o = 0;
+      MPC_VARIANT_CALL(c.variant, prof, sw, {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, c.threads, c.smem));
+      });
+      occ = (prof || occ == 0) ? o : std::min(occ, o);  // one grid serves both production sweeps
+    }
   }
   if (occ < 1) {
     eng->err = "solve kernel does not fit on an SM";
@@ -616,11 +636,15 @@ int build_classes(mpc_batch* eng) {
         const mpc::Layout Lp = mpc::make_layout(h, c.nv_cap, m, 1, kVariantPad[c.variant], packed, 1);
         const size_t need = 16 + 2 * eng->stride + Lp.fast_bytes;
         if (need > budget || (int)need > max_smem) continue;
-        int occ = 0;
-        MPC_PIPE_CALL(c.variant, {
-          CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c.threads, need));
-        });
+        int occ = 1 << 30;
+        for (int sw = 0; sw < 2; sw++) {
+          int o = 0;
+          MPC_PIPE_CALL(c.variant, sw, {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, c.threads, need));
+          });
+          occ = std::min(occ, o);
+        }
         if (occ >= per_sm) {
           c.pipe = true;
           c.pipe_m_cap = m;
@@ -679,12 +703,12 @@ int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int gr
   if (c.pipe && !prof) {
     SolveParams Pp = P;
     Pp.L = c.pipe_L;
-    MPC_PIPE_CALL(c.variant, (kern<<<grid, c.threads, c.pipe_smem, st>>>(Pp)));
+    MPC_PIPE_CALL(c.variant, eng->sweep, (kern<<<grid, c.threads, c.pipe_smem, st>>>(Pp)));
     eng->launches++;
     CK(cudaGetLastError());
     return MPC_OK;
   }
-  MPC_VARIANT_CALL(c.variant, prof, (kern<<<grid, c.threads, c.smem, st>>>(P)));
+  MPC_VARIANT_CALL(c.variant, prof, eng->sweep, (kern<<<grid, c.threads, c.smem, st>>>(P)));
   eng->launches++;
   CK(cudaGetLastError());
   return MPC_OK;
@@ -795,6 +819,7 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
   } while (0)
   if (const char* ds = getenv("MPC_DEBUG_STOP")) eng->debug_stop = atoi(ds);
   eng->no_host_classify = getenv("MPC_NO_HOST_CLASSIFY") != nullptr;
+  if (const char* sw = getenv("MPC_SWEEP")) eng->sweep = (sw[0] == 'm' || sw[0] == '1') ? 1 : 0;  // "mma" / "fma"
   eng->device = device;
   eng->h = horizon;
   eng->max_batch = max_batch;
@@ -1116,6 +1141,13 @@ void* mpc_batch_gather_buffer_slot(mpc_batch_t* eng, int slot) {
   if (!eng || !eng->gather_buf || slot < 0 || slot >= kSlots) return nullptr;
   return (char*)eng->gather_buf + eng->gather_slot_bytes * slot;
 }
+
+int mpc_batch_set_sweep_variant(mpc_batch_t* eng, int variant) {
+  if (!eng || variant < 0 || variant > 1) return MPC_E_ARG;
+  eng->sweep = variant;
+  return MPC_OK;
+}
+int mpc_batch_sweep_variant(const mpc_batch_t* eng) { return eng ? eng->sweep : -1; }
 
 int mpc_batch_set_max_iterations(mpc_batch_t* eng, int max_iter) {
   if (!eng || max_iter < 1) return MPC_E_ARG;

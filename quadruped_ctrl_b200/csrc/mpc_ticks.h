@@ -130,7 +130,8 @@ MPC_TK_HD void build_record_from_tick(const float* tick, int h, char* rec_bytes,
     // x_comp_integral += cmpc_x_drag * pz_err * dtMPC / vxy[0] when |v_x| > 0.3 (:634-640), float, left to right
     float xi = tick[MPC_TICK_XDRAG];
     const float vwx = tick[MPC_TICK_V];
-    if (vwx > 0.3f || vwx < -0.3f) {
+    // the reference compares the float with the DOUBLE literal 0.3 (:636): v_x == 0.3f (0.300000012) integrates
+    if ((double)vwx > 0.3 || (double)vwx < -0.3) {
       const float pz_err = tk_add(tick[MPC_TICK_P + 2], -tick[MPC_TICK_HEIGHT]);
       xi = tk_add(xi, tk_mul(tk_mul(3.0f, pz_err), dt) / vwx);
     }

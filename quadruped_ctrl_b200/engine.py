@@ -27,7 +27,7 @@ BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_creat
                  "mpc_batch_solve_device", "mpc_batch_solve_device_slot", "mpc_batch_solve_host", "mpc_batch_submit_host", "mpc_batch_wait_host",
                  "mpc_batch_assemble_device", "mpc_batch_build_records_device", "mpc_batch_solve_ticks_device",
                  "mpc_batch_set_gather_peers", "mpc_batch_gather_alloc", "mpc_batch_gather_connect",
-                 "mpc_batch_gather_buffer", "mpc_batch_gather_buffer_slot", "mpc_batch_gather_sync", "mpc_batch_gather_sync_slot", "mpc_batch_set_max_iterations", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
+                 "mpc_batch_gather_buffer", "mpc_batch_gather_buffer_slot", "mpc_batch_gather_sync", "mpc_batch_gather_sync_slot", "mpc_batch_set_max_iterations", "mpc_batch_set_sweep_variant", "mpc_batch_sweep_variant", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
                  "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
                  "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_class_kernel_ms", "mpc_batch_timing_mark",
                  "mpc_batch_timing_collect", "mpc_batch_host_buffers",
@@ -44,7 +44,8 @@ class MpcError(RuntimeError):
 def build(force=False):
     """Compiles csrc/ for sm_100a into libquadruped_mpc_b200.so (nvcc cross-compiles without a GPU)."""
     src = os.path.join(_HERE, "csrc")
-    deps = [os.path.join(src, f) for f in ("mpc_engine.cu", "mpc_core.h", "convexMPC_interface.cpp", "Makefile")]
+    deps = [os.path.join(src, f) for f in ("mpc_engine.cu", "mpc_core.h", "mpc_ticks.h", "convexMPC_interface.cpp",
+                                           "Makefile")]
     deps += [os.path.join(_HERE, "..", "include", f) for f in ("mpc_batch.h", "convexMPC_interface.h")]
     stale = force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(map(os.path.getmtime, deps))
     if stale:
@@ -87,6 +88,8 @@ def lib():
     L.mpc_batch_gather_buffer.argtypes = [vp]
     L.mpc_batch_gather_buffer.restype = vp
     L.mpc_batch_set_max_iterations.argtypes = [vp, i32]
+    L.mpc_batch_set_sweep_variant.argtypes = [vp, i32]
+    L.mpc_batch_sweep_variant.argtypes = [vp]
     L.mpc_batch_set_timing.argtypes = [vp, i32]
     L.mpc_batch_set_timed_class.argtypes = [vp, i32]
     L.mpc_batch_set_phase_clock_buffer.argtypes = [vp, vp]
@@ -166,6 +169,14 @@ class MpcBatch:
     # ---- configuration ------------------------------------------------------------------
     def set_max_iterations(self, n):
         self._check(self._L.mpc_batch_set_max_iterations(self._h, int(n)), "set_max_iterations")
+
+    def set_sweep_variant(self, variant):
+        """0 / "fma": rank-1 sweep on the FP64 FMA pipe; 1 / "mma": grouped sweep on the FP64 tensor pipe (DMMA)."""
+        v = {"fma": 0, "mma": 1}.get(variant, variant)
+        self._check(self._L.mpc_batch_set_sweep_variant(self._h, int(v)), "set_sweep_variant")
+
+    def sweep_variant(self):
+        return "mma" if self._L.mpc_batch_sweep_variant(self._h) == 1 else "fma"
 
     def set_timing(self, on):
         self._check(self._L.mpc_batch_set_timing(self._h, int(bool(on))), "set_timing")

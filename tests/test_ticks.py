@@ -79,3 +79,21 @@ def test_ticks_reproduce_config1(oracle):
                       (0, 5, 5, 0), (5, 5, 5, 5), np.arange(B), body_height=0.25)
     rec_t, _ = oracle.build_records(tk, h)
     assert np.array_equal(rec_t, rec)
+
+
+def test_x_drag_integrator_threshold_is_the_reference_double_compare(oracle):
+    """ConvexMPCLocomotion.cpp:636 compares the float v_x with the DOUBLE literal 0.3: v_x == 0.3f
+    (0.300000012 > 0.3) integrates, v_x just below does not.  Kernel body == oracle on exactly those values."""
+    h = 10
+    tk = T.synth_ticks(8, h, 21)
+    edge = np.float32(0.3)
+    below = np.nextafter(edge, np.float32(0))
+    tk[:, T.TICK_V] = np.array([edge, -edge, below, -below, np.nextafter(edge, np.float32(1)), 0.0, 0.31, -0.31],
+                               np.float32)
+    tk[:, T.TICK_XDRAG] = 0.125
+    tk[:, T.TICK_P + 2] = 0.29
+    rec_o, st_o = oracle.build_records(tk, h)
+    rec_e, st_e = emu_build_records(tk, h)
+    assert np.array_equal(rec_o, rec_e) and np.array_equal(st_o, st_e)
+    moved = st_o[:, 2] != np.float32(0.125)
+    assert moved.tolist() == [True, True, False, False, True, False, True, True]
