@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- MPC QP solves/s of the batched sm_100a engine (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--config 1..5] [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--sweep fma|mma]
     N > 1:  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path (record -> assembled QP -> 12 contact forces) over one batch of
-synthetic problems.  Workload at N=1: BASELINE.json configs[1] -- B=4096 independent robots, trot,
-horizon 10 (workloads.config2, seed 1234).  At N>1 every rank solves its own 4096-problem shard (weak
-scaling) and the step ends with the all-gather of the [N*4096, 12] forces (north_star: "a single NCCL
-all-gather of solved forces only when the batch is split").
+One "step" = one pass of the hot path (record -> assembled QP -> 12 contact forces) over one batch of synthetic
+problems.  `--config` picks the BASELINE.json workload; the default, and what the driver runs, is
+config 2: B=4096 independent robots per GPU, trot, horizon 10 (weak scaling; at N>1 the step ends with the gather of
+the [N*4096, 12] forces -- north_star: "a single NCCL all-gather of solved forces only when the batch is split").
+Configs 4 and 5 are one 65536-problem batch cut into N contiguous shards (sharding.shard_bounds, strong scaling);
+config 1 is one robot through the reference's own C interface, one MPC tick at a time.
 
 The line printed by rank 0 carries
-  value     whole-job solves/s with the records resident in HBM (device entry of the C ABI),
+  value     whole-job solves/s with the records resident in HBM (device entry of the C ABI, batches in flight on the
+            engine's slots), `serial` the same with one batch at a time,
   e2e       the same through the host entry (pinned host records -> H2D -> kernels -> D2H forces),
   roofline  algorithmic bytes of the dominant kernel / its CUDA-event duration vs the measured HBM peak,
+  parity    computed IN THIS RUN: 256 sampled problems of the workload against the CPU oracle (fp64 truth and the
+            reference-faithful fp32 path); `value` counts a batch's problems as solved only in the proportion that
+            came back optimal,
   cpu_baseline  the CPU oracle (reference qpOASES when oracle/_ref exists) on the box's host cores.
 `--impl reference` times that CPU path alone (all host cores) and prints the same line shape.
 """
@@ -32,10 +37,31 @@ sys.path.insert(0, ROOT)
 
 METRIC = "mpc_qp_solves_per_sec"
 UNIT = "solves/s"
-HORIZON = 10
-BATCH = 4096
-N_SETS = 96          # distinct record sets rotated through so that every step reads cold (non-L2) inputs
 L2_BYTES = 126e6
+
+# BASELINE.json configs[0..4].  per_gpu: every rank solves `batch` problems (weak scaling); otherwise
+# `batch` is the whole job and is cut into contiguous shards (strong scaling).
+CONFIGS = {
+    1: dict(key="config1", h=10, batch=1, per_gpu=True,
+            text="config1: 1 robot, trot gait, horizon=10, plane terrain, through the reference's C interface "
+                 "(setup_problem ... get_solution), one MPC tick at a time"),
+    2: dict(key="config2", h=10, batch=4096, per_gpu=True, seed=1234,
+            text="config2: B=%d independent robots per GPU, trot, horizon=10, 12 forces, 20 friction-cone rows per "
+                 "step, seed 1234+"),
+    3: dict(key="config3", h=20, batch=4096, per_gpu=True, seed=2345,
+            text="config3: B=%d per GPU, horizon=20, mixed gaits 0-11, randomised body inertia and mass, seed 2345+"),
+    4: dict(key="config4", h=10, batch=65536, per_gpu=False, seed=3456,
+            text="config4: B=%d, horizon=10, trot with stairs-terrain foothold perturbations, one batch sharded over "
+                 "the GPUs + gather of the forces, seed 3456+"),
+    5: dict(key="config5", h=16, batch=65536, per_gpu=False, seed=4567,
+            text="config5: B=%d, horizon=16, galloping, one batch sharded over the GPUs + gather of the forces, "
+                 "seed 4567+"),
+}
+
+
+def workload_text(cfg, batch):
+    """The one string both arms print as config.workload."""
+    return cfg["text"] % batch if "%d" in cfg["text"] else cfg["text"]
 
 
 def load_peaks():
@@ -46,21 +72,29 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_traffic():
-    """(dram bytes per launch, on-chip pipe figures) of the dominant kernel from the committed ncu capture
-    (profiles/roofline_traffic.json), or (None, None)."""
+def load_static_profile(cfg_id):
+    """Figures that come from committed ncu captures / microbenchmarks, NOT from this run (labelled static):
+    DRAM bytes per launch of the dominant kernel, its pipe utilisation, the measured fp64 peaks."""
+    out = {"static": True}
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    traffic = None
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return d.get("dram_bytes_per_launch"), {"fp64_pipe_pct_of_peak": d.get("fp64_pipe_pct_of_peak"),
-                                                "issue_slots_pct_of_peak": d.get("issue_slots_pct_of_peak"),
-                                                "source": d.get("source")}
-    return None, None
+        e = d.get("config%d" % cfg_id) or (d if cfg_id == 2 and "dram_bytes_per_launch" in d else None)
+        if e:
+            traffic = e.get("dram_bytes_per_launch")
+            out.update({k: e.get(k) for k in ("fp64_pipe_pct_of_peak", "issue_slots_pct_of_peak",
+                                              "tensor_pipe_pct_of_peak", "source") if e.get(k) is not None})
+    p = os.path.join(ROOT, "profiles", "fp64_peak.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            out["fp64_peaks_measured"] = json.load(f)
+    return traffic, out
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -109,6 +143,9 @@ class ClockSampler:
         return out
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# CPU legs (the oracle is the checker and the reported baseline, never the product path)
+# ---------------------------------------------------------------------------------------------------------------
 def cpu_reference_leg(records, horizon, target_seconds=12.0, workers=None):
     """Times the CPU oracle (reference qpOASES + fp32 assembly restatement) over all host cores.
     Returns (solves_per_s, dict)."""
@@ -133,25 +170,139 @@ def cpu_reference_leg(records, horizon, target_seconds=12.0, workers=None):
                         single_core_us_per_solve=per * 1e6)
 
 
+def build_legacy_stub(oracle_side):
+    """g++-compiles tools/legacy_tick_bench.cpp against the product library (include/convexMPC_interface.h) or, with
+    -DLEGACY_ORACLE, against oracle/liboracle.so.  Returns (exe, extra argv)."""
+    src = os.path.join(ROOT, "tools", "legacy_tick_bench.cpp")
+    exe = os.path.join(tempfile.gettempdir(), "legacy_tick_bench_%s_%d" % ("oracle" if oracle_side else "gpu", os.getpid()))
+    if oracle_side:
+        from oracle import oracle as O
+        O.lib()
+        odir = os.path.join(ROOT, "oracle")
+        subprocess.check_call(["g++", "-O2", "-std=c++14", "-DLEGACY_ORACLE", src, "-o", exe, "-L", odir,
+                               "-l:liboracle.so", "-Wl,-rpath," + odir, "-ldl"])
+        return exe, [os.path.join(odir, "_ref", "libqpoases_ref.so")]
+    from quadruped_ctrl_b200 import engine as E
+    libdir = os.path.dirname(E.LIB_PATH)
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           src, "-o", exe, "-L", libdir, "-l:" + os.path.basename(E.LIB_PATH), "-Wl,-rpath," + libdir])
+    return exe, []
+
+
+def run_legacy_stub(exe, extra, ticks, h=10):
+    """-> (median us, p95 us, mean us, forces [h, 12])."""
+    try:
+        r = subprocess.run([exe, str(ticks), str(h)] + extra, capture_output=True, text=True, timeout=1200)
+    finally:
+        os.unlink(exe)
+    if r.returncode != 0:
+        raise SystemExit("legacy_tick_bench failed: " + r.stderr[-500:])
+    lines = r.stdout.splitlines()
+    med, p95, mean = [float(x) for x in lines[0].split()[1:4]]
+    forces = np.array([[float(x) for x in l.split()[3:15]] for l in lines[1:1 + h]])
+    return med, p95, mean, forces, r.stderr
+
+
+def parity_block(eng, rec, h, n_sample=256):
+    """256 sampled problems of the workload, solved by the engine (host entry, whole 12h solution) and by the CPU
+    oracle in both precisions; SURVEY 8d criterion.  Runs inside bench.py so that every reported number sits beside
+    the parity of the very build that produced it."""
+    from oracle import oracle as O
+    from quadruped_ctrl_b200 import engine as E
+    rng = np.random.default_rng(0)
+    idx = np.sort(rng.choice(rec.shape[0], size=min(n_sample, rec.shape[0]), replace=False))
+    sub = np.ascontiguousarray(rec[idx])
+    forces, sol, status = eng.solve_host(sub, want_solution=True)
+    backend = O.default_backend()
+    o64 = O.solve_batch(sub, h, 64, backend)
+    o32 = O.solve_batch(sub, h, 32, backend)
+
+    def rel(a, b):
+        return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1.0)
+
+    code = E.status_code(status)
+    ok64 = o64["rc"] == 0
+    e64 = rel(sol, o64["sol"])
+    cloud = rel(o32["forces"], o64["forces"])
+    e32 = rel(forces.astype(np.float64), o32["forces"])
+    well = ok64 & (o32["rc"] == 0) & (cloud <= 1e-5)   # SURVEY 8d: the reference's own fp32 answer is within 1e-5
+    passed = (code == 0) & np.where(well, e32 <= 1e-4, True) & np.where(ok64, e64 <= 1e-9, True)
+    return {
+        "sampled": int(len(idx)), "oracle_backend": backend,
+        "status_optimal": int((code == 0).sum()),
+        "vs_oracle64_max_rel_12h": float(e64[ok64].max()) if ok64.any() else None,
+        "vs_oracle32_max_rel_forces_well_conditioned": float(e32[well].max()) if well.any() else None,
+        "well_conditioned": int(well.sum()),
+        "reference_fp32_cloud_max": float(cloud[ok64].max()) if ok64.any() else None,
+        "vs_oracle32_max_rel_forces_all": float(e32[ok64].max()) if ok64.any() else None,
+        "reference_failed_nwsr": int((~ok64).sum()),
+        "passed": int(passed.sum()),
+        "criterion": "status optimal; 12h solution within 1e-9 of reference qpOASES on the fp64-assembled QP; first-step "
+                     "forces within 1e-4 of the reference-faithful fp32 path wherever that path is itself within 1e-5 "
+                     "of the fp64 answer (elsewhere the fp32 path's own rounding cloud is larger than the target)",
+    }
+
+
+def count_classes(rec, h, classes):
+    """Problems per size class, from the gait tables (the classify kernel's rule)."""
+    go = 4 * (48 + 12 * h)
+    gait = rec[:, go:go + 4 * h].astype(np.float32)
+    fmax = rec.view(np.float32)[:, 46:47]
+    ub = gait * fmax
+    ns = (~((ub < 0.01) & (ub > -0.01))).sum(1)
+    nv = 3 * ns
+    caps = [c["nv_cap"] for c in classes]
+    idx = np.zeros(len(nv), np.int64)
+    for i in range(len(caps) - 1):
+        idx += nv > caps[i]
+    return np.bincount(idx, minlength=len(caps)), nv
+
+
+# ---------------------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
+    h = cfg["h"]
+    if args.config == 1:
+        exe, extra = build_legacy_stub(True)
+        ticks = max(200, 50 * (args.steps + args.warmup))
+        med, p95, mean, _, _ = run_legacy_stub(exe, extra, ticks)
+        from oracle import oracle as O
+        kind = "reference" if O.have_reference_qpoases() else "port"
+        value = 1e6 / mean
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e-3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 assembly / f64 QP (reference CPU path)",
+            "data": "synthetic", "config": {"workload": workload_text(cfg, 1),
+                                            "note": "%d ticks, one after the other, 1 host core" % ticks},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                             "sample": "%d MPC ticks through the oracle's legacy C interface; median %.1f us, p95 %.1f us"
+                                       % (ticks, med, p95)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
     from quadruped_ctrl_b200 import workloads as W
-    rec = W.config2(args.batch, HORIZON, 1234)
+    batch = args.batch or cfg["batch"]
+    rec = W.CONFIGS[cfg["key"]](min(batch, 4096), h, cfg["seed"])
     vals = []
     info = None
     per_step_target = 4.0
     for i in range(args.warmup + args.steps):
-        v, info = cpu_reference_leg(rec, HORIZON, target_seconds=per_step_target * (os.cpu_count() or 1))
+        v, info = cpu_reference_leg(rec, h, target_seconds=per_step_target * (os.cpu_count() or 1))
         if i >= args.warmup:
             vals.append(v)
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * args.batch / value, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * batch / value, "higher_is_better": True,
+        "scaling": "weak" if cfg["per_gpu"] else "strong",
         "vs_baseline": None, "dtype": "f32 assembly / f64 QP (reference CPU path)", "data": "synthetic",
-        "config": {"workload": "config2: B=%d independent robots, trot, horizon=%d, seed 1234" % (args.batch, HORIZON),
+        "config": {"workload": workload_text(cfg, batch),
                    "note": "each step is a bounded sample of the workload on all host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                          "sample": info["sample"]},
@@ -161,11 +312,106 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------------------------------
+def run_config1(args):
+    """One robot through the reference's C interface: every tick is a batch of one on the GPU (host classifies the
+    problem, one kernel launch, one copy back)."""
+    import torch
+    from quadruped_ctrl_b200 import engine as E
+    from quadruped_ctrl_b200 import records as R
+    from quadruped_ctrl_b200 import workloads as W
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return   # replicas only: a single robot never leaves GPU 0 (SURVEY 8e)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path (use --impl reference for the CPU leg)")
+    cfg = CONFIGS[1]
+    h = 10
+    ticks = max(500, 100 * args.steps)
+    sampler = ClockSampler(0)
+    sampler.start()
+    exe, extra = build_legacy_stub(False)
+    med, p95, mean, f_gpu, err = run_legacy_stub(exe, extra, ticks)
+    clocks = sampler.stop()
+    # parity of those very ticks: the ten gait phases of config 1 against the oracle
+    from oracle import oracle as O
+    rec = W.config1(h)
+    o64 = O.solve_batch(rec, h, 64)
+    o32 = O.solve_batch(rec, h, 32)
+    # the stub's phase k is the gait table of iteration k, i.e. workloads.config1 record k
+    e64 = np.linalg.norm(f_gpu - o64["forces"], axis=1) / np.maximum(np.linalg.norm(o64["forces"], axis=1), 1.0)
+    e32 = np.linalg.norm(f_gpu - o32["forces"], axis=1) / np.maximum(np.linalg.norm(o32["forces"], axis=1), 1.0)
+    cloud = np.linalg.norm(o32["forces"] - o64["forces"], axis=1) / np.maximum(np.linalg.norm(o64["forces"], axis=1), 1.0)
+    # device-resident figure: the same problem as a batch of one through the batched entry
+    eng = E.MpcBatch(h, 1, 0)
+    eng.set_sweep_variant(args.sweep)
+    d = torch.from_numpy(rec[:1]).cuda()
+    f = torch.empty((1, 12), dtype=torch.float32, device="cuda")
+    st = torch.empty((1,), dtype=torch.int32, device="cuda")
+    for _ in range(20):
+        eng.solve_device(d, forces=f, status=st)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.kernel_launches()
+    n = 200
+    ev0.record()
+    for _ in range(n):
+        eng.solve_device(d, forces=f, status=st)
+    ev1.record()
+    torch.cuda.synchronize()
+    dev_us = ev0.elapsed_time(ev1) * 1e3 / n
+    launches = (eng.kernel_launches() - l0) // n
+    eng.set_timing(True)
+    eng.solve_device(d, forces=f, status=st)
+    torch.cuda.synchronize()
+    k_ms = max(eng.last_class_kernel_ms(c) for c in range(len(eng.classes())))
+    peak, peak_src = load_peaks()
+    traffic, on_chip = load_static_profile(1)
+    achieved = R.algorithmic_bytes(h) / (k_ms * 1e-3) / 1e9
+    exe_o, extra_o = build_legacy_stub(True)
+    cmed, cp95, cmean, _, _ = run_legacy_stub(exe_o, extra_o, 400)
+    line = {
+        "metric": METRIC, "value": 1e6 / dev_us, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_us * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_text(cfg, 1),
+                   "note": "value: batch of one through mpc_batch_solve_device, back to back (launch-bound); e2e: %d "
+                           "ticks through the legacy C interface from a C++ caller (tools/legacy_tick_bench.cpp)" % ticks,
+                   "l2": "latency benchmark of a single problem: inputs are 720 bytes, L2 state is irrelevant",
+                   "sweep": args.sweep},
+        "e2e": {"value": 1e6 / mean, "unit": UNIT, "h2d_bytes_per_step": R.record_stride(h),
+                "d2h_bytes_per_step": 12 * 4 + 4 + 12 * h * 8, "us_per_tick_median": med, "us_per_tick_p95": p95,
+                "api": "setup_problem / update_x_drag / update_solver_settings / update_problem_data_floats / "
+                       "12 x get_solution (ConvexMPCLocomotion.cpp:630-674)"},
+        "gpu_launches": int(launches * args.steps),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "on_chip": on_chip, "kernel_ms": k_ms,
+                     "kernel": "the problem's size-class kernel, one CTA",
+                     "algorithmic_bytes_per_solve": R.algorithmic_bytes(h),
+                     "note": "one problem on one SM: latency-bound by construction"},
+        "parity": {"sampled": 10, "vs_oracle64_max_rel_forces": float(e64.max()),
+                   "vs_oracle32_max_rel_forces": float(e32.max()), "reference_fp32_cloud_max": float(cloud.max()),
+                   "passed": int(((e64 <= 1e-6) & (e32 <= 1e-4)).sum()),
+                   "criterion": "forces of the ten gait phases returned by get_solution(0..11): within 1e-4 of the "
+                                "reference-faithful fp32 path and 1e-6 (float output) of the fp64 answer"},
+        "clocks": clocks,
+        "cpu_baseline": {"value": 1e6 / cmean, "unit": UNIT, "cores": 1, "kind": "reference" if O.have_reference_qpoases() else "port",
+                         "sample": "400 MPC ticks through the oracle's legacy C interface (fp32 assembly + qpOASES), "
+                                   "median %.1f us, p95 %.1f us" % (cmed, cp95),
+                         "single_core_us_per_solve": cmean},
+    }
+    print(json.dumps(line))
+    eng.close()
+
+
 def run_ours(args):
+    if args.config == 1:
+        return run_config1(args)
     import torch
     import torch.distributed as dist
     from quadruped_ctrl_b200 import engine as E
     from quadruped_ctrl_b200 import records as R
+    from quadruped_ctrl_b200 import sharding as S
     from quadruped_ctrl_b200 import workloads as W
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,56 +424,68 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B, h = args.batch, HORIZON
+    cfg = CONFIGS[args.config]
+    h = cfg["h"]
+    total = args.batch or cfg["batch"]
+    if cfg["per_gpu"]:
+        B, lo = total, rank * total            # every rank its own batch (weak scaling)
+        job = world * total
+    else:
+        lo, hi = S.shard_bounds(total, world, rank)   # one batch, contiguous shards (strong scaling)
+        if (hi - lo) * world != total:
+            raise SystemExit("bench.py: --batch must divide by the number of GPUs for the sharded configs")
+        B, job = hi - lo, total
+    gen = W.CONFIGS[cfg["key"]]
     eng = E.MpcBatch(h, B, local_rank)
-    eng.set_timed_class(0)   # CUDA events around the dominant kernel only (size class 0 holds every trot problem)
+    eng.set_sweep_variant(args.sweep)
     classes = eng.classes()
     stride = eng.stride
-    # ---- synthetic inputs: N_SETS distinct batches per rank (rotation keeps every step's inputs out of L2) ----
-    n_sets = max(2, min(N_SETS, int(np.ceil(2.2 * L2_BYTES / (B * stride)))))
-    host_sets = [W.config2(B, h, 1234 + 1000 * rank + i) for i in range(n_sets)]
+    # ---- synthetic inputs: distinct batches per rank, rotated so that every step reads cold (non-L2) inputs ----
+    n_sets = max(3, min(96, int(np.ceil(2.2 * L2_BYTES / (B * stride)))))
+    host_sets = [gen(B, h, cfg["seed"] + 1000 * rank + i) for i in range(n_sets)]
     dev_sets = [torch.from_numpy(s).to(dev) for s in host_sets]
-    # Consecutive steps are independent batches, so they alternate between two of the engine's scratch slots on two
-    # streams: the tail of step i (a few CTAs still solving) shares the GPU with the head of step i+1.
-    nq = max(1, min(args.inflight, E.SLOTS))   # batches in flight on the device-resident path
+    per_class, _ = count_classes(host_sets[0], h, classes)
+    # Consecutive steps are independent batches: they rotate over the engine's scratch slots / streams, so the tail
+    # of step i (a few CTAs still solving) shares the GPU with the head of step i+1.
+    nq = max(1, min(args.inflight, E.SLOTS))
     streams = [torch.cuda.Stream(dev) for _ in range(nq)]
     forces2 = [torch.empty((B, 12), dtype=torch.float32, device=dev) for _ in range(nq)]
     status2 = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(nq)]
-    forces, status = forces2[0], status2[0]
     gathered2 = [torch.empty((world * B, 12), dtype=torch.float32, device=dev) for _ in range(nq)] if world > 1 else None
-    gathered = gathered2[0] if world > 1 else None
     peer = world > 1 and args.gather == "peer"
     if peer:  # fused: the solve kernel stores every force straight into all ranks' gather buffers over NVLink
-        gathered = eng.setup_peer_gather(world * B, rank * B)
+        eng.setup_peer_gather(world * B, rank * B)
         gathered2 = eng.gather_views   # one region per scratch slot
-    overlap = not args.serial
+    # NCCL gather on a stream of its own: the next batch's kernels never queue behind the collective
+    comm = torch.cuda.Stream(dev) if world > 1 and not peer else None
+    gather_done = [torch.cuda.Event() for _ in range(nq)]
 
-    def step(i):
+    def step(i, overlap=True):
         q = (i % nq) if overlap else 0
-        if overlap:
-            with torch.cuda.stream(streams[q]):
-                eng.solve_device(dev_sets[i % n_sets], forces=forces2[q], status=status2[q], stream=streams[q], slot=q)
-                if world > 1:
-                    if peer:
-                        eng.gather_sync(stream=streams[q], slot=q)  # device-side flag exchange over NVLink
-                    else:
+        st = streams[q]
+        with torch.cuda.stream(st):
+            if comm is not None:
+                st.wait_event(gather_done[q])   # the previous gather out of this slot's forces has finished
+            eng.solve_device(dev_sets[i % n_sets], forces=forces2[q], status=status2[q], stream=st, slot=q)
+            if world > 1:
+                if peer:
+                    eng.gather_sync(stream=st, slot=q)  # device-side flag exchange over NVLink
+                else:
+                    comm.wait_stream(st)
+                    with torch.cuda.stream(comm):
                         dist.all_gather_into_tensor(gathered2[q], forces2[q])
-            return
-        eng.solve_device(dev_sets[i % n_sets], forces=forces, status=status)
-        if world > 1:
-            if peer:
-                eng.gather_sync()  # device-side flag exchange over NVLink: everybody's stores have landed
-            else:
-                dist.all_gather_into_tensor(gathered, forces)
+                        gather_done[q].record(comm)
+                    if not overlap:
+                        st.wait_stream(comm)
 
     def fork():
         cur = torch.cuda.current_stream(dev)
-        for st in streams:
+        for st in streams + ([comm] if comm is not None else []):
             st.wait_stream(cur)
 
     def join():
         cur = torch.cuda.current_stream(dev)
-        for st in streams:
+        for st in streams + ([comm] if comm is not None else []):
             cur.wait_stream(st)
 
     def barrier():
@@ -235,79 +493,110 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(n, first, overlap):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        eng.timing_mark()
+        ev0.record()
+        fork()
+        for i in range(n):
+            step(first + i, overlap)
+        join()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     fork()
     for i in range(args.warmup):
         step(i)
     join()
     barrier()
-    # all problems must have solved to optimality before anything is timed
-    for st_ in (status2 if overlap else status2[:1]):
-        codes = (st_.cpu().numpy() & 0xff)
-        assert (codes == 0).all(), "non-optimal status in warm-up: %s" % np.bincount(codes)
+    # which size class dominates this workload: every class kernel timed alone (events around each, one batch at a
+    # time); the timed runs below then carry events around that kernel only
+    eng.set_timing(True)
+    eng.timing_mark()
+    for i in range(4):
+        step(i, False)
+    join()
+    barrier()
+    k_alone = [eng.timing_collect(c) for c in range(len(classes))]
+    dominant = int(np.argmax([ms for ms, _ in k_alone]))
+    eng.set_timed_class(dominant)
+
+    def optimal_fraction():
+        bad = 0
+        for st_ in status2:
+            bad += int(((st_ & 0xff) != 0).sum().item())
+        return 1.0 - bad / float(len(status2) * B)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
     launches0 = eng.kernel_launches()
-    dominant = 0  # size class 0 (nv <= 60) holds every trot problem of this workload
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    eng.timing_mark()
-    ev0.record()
-    fork()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    join()
-    ev1.record()
-    barrier()
-    total_ms = ev0.elapsed_time(ev1)
+    total_ms = timed(args.steps, args.warmup, True)
     launches = eng.kernel_launches() - launches0
-    # mean duration of the dominant kernel over the timed steps (events recorded on the launching stream); with
-    # overlapping steps two launches share the GPU, so each one's duration is longer than its share of the step
-    k_ms_timed, k_n = eng.timing_collect(dominant)
-    # the same kernel timed alone: the same steps once more, one at a time on one stream (roofline figure)
-    k_ms = k_ms_timed
-    if overlap:
-        eng.timing_mark()
-        for i in range(min(args.steps, 32)):
-            eng.solve_device(dev_sets[(args.warmup + i) % n_sets], forces=forces, status=status)
-        torch.cuda.synchronize()
-        k_ms, _ = eng.timing_collect(dominant)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    k_timed = eng.timing_collect(dominant)
+    frac_ok = optimal_fraction()   # statuses of the LAST batch on every slot, i.e. of timed steps
+    value = frac_ok * job * args.steps / (total_ms * 1e-3)
+    # ---- the same steps one batch at a time on one stream: latency-style figure and the kernels timed alone ----
+    n_serial = min(args.steps, 32)
+    serial_ms = timed(n_serial, args.warmup, False)
+    serial_value = frac_ok * job * n_serial / (serial_ms * 1e-3)
+    k_ms, k_n = eng.timing_collect(dominant)
+    # ---- check of what was timed: the last step's forces against a fresh solve of the same batch, the gather against
+    #      its inputs (exact integer checksum), every status optimal ----
+    last = args.warmup + n_serial - 1
+    ref_f, _, ref_st = eng.solve_device(dev_sets[last % n_sets])
+    torch.cuda.synchronize()
+    results_ok = bool(torch.equal(ref_f, forces2[0])) and frac_ok == 1.0
+    gather_ok = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = world * B * args.steps / (total_ms * 1e-3)
+        mine = forces2[0].view(torch.int32).to(torch.int64).sum()
+        tot = mine.clone()
+        dist.all_reduce(tot)
+        g = gathered2[0]
+        gather_ok = bool(torch.equal(g[rank * B:(rank + 1) * B], forces2[0])) and \
+            int(g.view(torch.int32).to(torch.int64).sum().item()) == int(tot.item())
+        flag = torch.tensor([int(gather_ok)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = bool(flag.item())
 
     # ---- end to end through the host entry: pinned host records -> H2D -> kernels -> D2H, every step.
-    # The slotted host API is used the way a caller with a stream of batches uses it: submit step i, then
-    # collect step i-2, so one step's transfers and the host's work overlap the other steps' kernels.  Every step's inputs come from
-    # pinned host memory and every step's forces + status are read back to the host inside the timed region.
-    pinned_sets = [torch.from_numpy(s).pin_memory() for s in host_sets[:8]]
+    # The slotted host API is used the way a caller with a stream of batches uses it: submit step i, then collect step
+    # i-2.  Every step's inputs come from pinned host memory and its forces + status are read back inside the timed
+    # region; at N>1 the gather takes the slot's device forces (no second upload).
+    pinned_sets = [torch.from_numpy(s).pin_memory() for s in host_sets[:min(8, n_sets)]]
     nslots = E.SLOTS
-    depth = nslots - 1          # batches submitted ahead of the one being collected
+    depth = nslots - 1
     out_f = [eng.host_buffers(q)[1] for q in range(nslots)]
     out_s = [eng.host_buffers(q)[3] for q in range(nslots)]
+    dev_f = [eng.device_forces(q) for q in range(nslots)] if world > 1 else None
     checksum = [0.0]
+    e2e_bad = [0]
 
     def collect(slot):
         eng.wait_host(slot)                       # results stay in the slot's pinned buffers
-        checksum[0] += float(out_f[slot][0, 2]) + float(out_s[slot][0])
+        checksum[0] += float(out_f[slot][0, 2])
+        e2e_bad[0] += int((out_s[slot][:B] & 0xff != 0).sum())
         if world > 1:
-            forces.copy_(torch.from_numpy(out_f[slot][:B]), non_blocking=True)
-            dist.all_gather_into_tensor(gathered, forces)
+            dist.all_gather_into_tensor(gathered2[0], dev_f[slot][:B])
 
     def e2e_run(n):
         for i in range(n):
-            eng.submit_host(i % nslots, pinned_sets[i % len(pinned_sets)].numpy())
+            eng.submit_host(i % nslots, pinned_sets[i % len(pinned_sets)].numpy(), zero_copy=True)
             if i >= depth:
                 collect((i - depth) % nslots)
         for j in range(max(0, n - depth), n):
             collect(j % nslots)
         torch.cuda.synchronize()
 
+    eng.set_timing(False)
     e2e_run(max(args.warmup, 2 * len(pinned_sets) + 4))   # every pinned set has been through the DMA path once
+    e2e_bad[0] = 0
     barrier()
     t0 = time.perf_counter()
     e2e_run(args.steps)
@@ -316,49 +605,60 @@ def run_ours(args):
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(t.item())
+    e2e_value = (1.0 - e2e_bad[0] / float(B * args.steps)) * job * args.steps / float(t.item())
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        traffic, on_chip = load_traffic()
-        alg_bytes = R.algorithmic_bytes(h) * B
+        traffic, on_chip = load_static_profile(args.config)
+        n_dom = int(per_class[dominant])
+        alg_bytes = R.algorithmic_bytes(h) * max(n_dom, 1)
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        if on_chip is not None:
-            # secondary figure: fp64 rate of the dominant kernel against the fp64 peak measured on this pool's B200s
-            # with tools/microbench/dfma.cu (36.8 TFLOP/s); every problem of this workload has nv = 60
-            flops = R.algorithmic_flops(h, 60) * B
-            on_chip.update(fp64_tflops_achieved=flops / (k_ms * 1e-3) / 1e12, fp64_tflops_peak_measured=36.8,
-                           algorithmic_fp64_flops_per_solve=R.algorithmic_flops(h, 60))
+        nv_dom = min(classes[dominant]["nv_cap"], 12 * h)
+        on_chip.update(algorithmic_fp64_flops_per_solve=R.algorithmic_flops(h, nv_dom),
+                       fp64_tflops_achieved=R.algorithmic_flops(h, nv_dom) * n_dom / (k_ms * 1e-3) / 1e12)
+        parity = parity_block(eng, host_sets[0], h)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak" if cfg["per_gpu"] else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config2: B=%d independent robots per GPU, trot, horizon=%d, 12 forces, 20 "
-                                   "friction-cone rows per step, seed 1234+" % (B, h),
+            "config": {"workload": workload_text(cfg, total), "problems_per_gpu": B,
                        "l2": "inputs rotate over %d distinct record sets (%.0f MB > 126 MB L2), no flush needed"
                              % (n_sets, n_sets * B * stride / 1e6),
-                       "pipelining": ("steps rotate over %d of the engine's scratch slots / streams (independent batches)" % nq
-                                      if overlap else "one stream, steps strictly one after another"),
+                       "pipelining": "steps rotate over %d of the engine's scratch slots / streams (independent "
+                                     "batches); ms_per_step is therefore an inverse throughput, `serial` is the "
+                                     "one-batch-at-a-time figure" % nq,
                        "collective": ("none (N=1)" if world == 1 else
                                       "peer stores from the solve kernel + device-side flag barrier (no NCCL on the path)" if peer else
-                                      "all_gather_into_tensor of [N*B,12] fp32 forces"),
-                       "classes": classes},
+                                      "all_gather_into_tensor of [N*B,12] fp32 forces on a communication stream of its own"),
+                       "sweep": eng.sweep_variant(), "classes": classes,
+                       "problems_per_class": [int(x) for x in per_class]},
+            "serial": {"value": serial_value, "unit": UNIT, "ms_per_batch": serial_ms / n_serial, "steps": n_serial,
+                       "note": "one batch at a time on one stream (BASELINE configs are single batches)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * stride,
                     "d2h_bytes_per_step": B * 48 + B * 4,
-                    "api": "mpc_batch_submit_host / mpc_batch_wait_host (%d slots, %d batches submitted ahead; page-locked host buffers read in place)" % (nslots, depth)},
+                    "api": "mpc_batch_submit_host / mpc_batch_wait_host (%d slots, %d batches submitted ahead; "
+                           "page-locked caller buffers handed over zero-copy with mpc_batch_submit_host_pinned)" % (nslots, depth)},
             "gpu_launches": launches,
+            "results_ok": results_ok, "optimal_fraction": frac_ok,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "on_chip": on_chip,
-                         "kernel": "mpc_solve_pipe_kernel<128,...> (size class nv<=60, two problems in flight per CTA)", "kernel_ms": k_ms, "kernel_launches_timed": k_n,
-                         "kernel_ms_in_timed_region": k_ms_timed,
+                         "kernel": "size class %d (nv <= %d, %d threads): %d of the batch's %d problems"
+                                   % (dominant, classes[dominant]["nv_cap"], classes[dominant]["threads"], n_dom, B),
+                         "kernel_ms": k_ms, "kernel_launches_timed": k_n,
+                         "kernel_ms_in_timed_region": k_timed[0],
+                         "class_kernel_ms_alone": [ms for ms, _ in k_alone],
                          "algorithmic_bytes_per_solve": R.algorithmic_bytes(h),
                          "note": "on-chip fp64/latency bound by construction: H and g never leave shared memory, so "
                                  "the HBM fraction is tiny; see DESIGN.md for the fp64-pipe figures"},
+            "parity": parity,
             "clocks": clocks,
         }
+        if gather_ok is not None:
+            line["gather_ok"] = gather_ok
         if world == 1 and not args.no_cpu:
-            v, info = cpu_reference_leg(host_sets[0], h, target_seconds=1.5 * (os.cpu_count() or 1))
+            v, info = cpu_reference_leg(host_sets[0][:4096], h, target_seconds=1.5 * (os.cpu_count() or 1))
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                                     "sample": info["sample"],
                                     "single_core_us_per_solve": info["single_core_us_per_solve"]}
@@ -371,13 +671,15 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json workload (1..5)")
+    ap.add_argument("--batch", type=int, default=0, help="override the config's batch size")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--serial", action="store_true", help="one stream, no overlap between consecutive steps")
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight on the device-resident path (<= 3)")
+    ap.add_argument("--sweep", default=os.environ.get("MPC_SWEEP", "fma"), choices=["fma", "mma"],
+                    help="inversion of the register-resident classes: FP64 FMA pipe or FP64 tensor pipe (DMMA)")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
                     help="N>1: NCCL all-gather of the forces (default) or the kernel's fused peer-store epilogue")
     args = ap.parse_args()

@@ -91,6 +91,11 @@ EXTERNC void mpc_set_robot(const float* I_body_diag, float mass);
 /* Additive: the inputs last given to setup_problem / update_x_drag / update_problem_data* as one batch
  * record of include/mpc_batch.h (out holds mpc_record_stride(horizon) bytes); returns the horizon. */
 EXTERNC int mpc_legacy_record(void* out);
+/* Additive: the use_jcqp mode last requested through update_solver_settings (0, 1, 2).  The reference's JCQP ADMM
+ * alternative (SolverMPC.cpp:406-420, 558-619; never selected upstream, ConvexMPCLocomotion.cpp:649) has no
+ * counterpart here: the active-set kernel returns the exact optimum of the same QP, the request is reported on
+ * stderr once, and rho / sigma / solver_alpha / terminate / max_iter are ignored. */
+EXTERNC int mpc_jcqp_requested(void);
 /* Additive: destroys the cached GPU engines. */
 EXTERNC void mpc_shutdown(void);
 #endif

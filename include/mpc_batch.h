@@ -102,7 +102,7 @@ enum {
  *   bits 0..7   code (MPC_STATUS_*), bits 8..31 working-set iterations taken. */
 enum {
   MPC_STATUS_OPTIMAL = 0,      /* KKT-exact optimum of the reduced QP                      */
-  MPC_STATUS_MAX_ITER = 1,     /* iteration cap hit; forces are the last dual-feasible iterate */
+  MPC_STATUS_MAX_ITER = 1,     /* iteration cap hit; forces = 0 (a dual active-set iterate is not primal feasible) */
   MPC_STATUS_BAD_INPUT = 2,    /* non-finite input or mu/mass/inertia/dt <= 0; forces = 0  */
   MPC_STATUS_NOT_PD = 3,       /* Hessian not positive definite (alpha <= 0 with zero weights) */
   MPC_STATUS_NO_STANCE = 4     /* every leg in swing over the whole horizon: all-zero optimum */
@@ -151,13 +151,20 @@ int mpc_batch_solve_host(mpc_batch_t* eng, const void* records_host, int batch,
                          int32_t* status_host);
 
 /* Pipelined host-resident solve.  The engine has MPC_BATCH_SLOTS slots, each with its own stream, pinned
- * staging and device buffers.  submit stages `records_host` into the slot and queues H2D, kernels and
- * D2H on the slot's stream without waiting for the GPU; wait blocks until that slot is done and copies
- * the results out (pass the slot's own pinned pointers from mpc_batch_host_buffers to skip the copies).
+ * staging and device buffers (allocated on first use).  submit COPIES `records_host` into the slot's pinned
+ * staging buffer before it returns -- the caller may reuse its buffer at once, whatever kind of memory it is --
+ * and queues H2D, kernels and D2H on the slot's stream without waiting for the GPU; wait blocks until that slot
+ * is done and copies the results out (pass the slot's own pinned pointers from mpc_batch_host_buffers to skip
+ * the copies: records written straight into the slot's buffer are not copied again).
  * Alternating slots overlaps one batch's transfers and host-side packing with the other's kernels.
  * mpc_batch_solve_host == submit(slot 0) + wait(slot 0). */
 int mpc_batch_submit_host(mpc_batch_t* eng, int slot, const void* records_host, int batch,
                           int want_solution);
+/* Zero-copy variant, opt-in: `records_pinned` must be page-locked (cudaHostAlloc / cudaHostRegister; checked,
+ * MPC_E_ARG otherwise) and MUST NOT BE MODIFIED until mpc_batch_wait_host(slot) returns -- the DMA engine reads
+ * it in place after this call has returned. */
+int mpc_batch_submit_host_pinned(mpc_batch_t* eng, int slot, const void* records_pinned, int batch,
+                                 int want_solution);
 int mpc_batch_wait_host(mpc_batch_t* eng, int slot, float* forces_host, double* solution_host,
                         int32_t* status_host);
 
@@ -269,6 +276,10 @@ int mpc_batch_timing_collect(mpc_batch_t* eng, int idx, float* mean_ms, int* n_s
  * mpc_batch_solve_host (slot 0) / submit_host / wait_host skips the pageable->pinned copies. */
 int mpc_batch_host_buffers(mpc_batch_t* eng, int slot, void** records, float** forces,
                            double** solution, int32_t** status);
+/* Slot `slot`'s DEVICE result buffers of the host entry ([max_batch*12] fp32 forces, [max_batch] int32 status):
+ * valid after mpc_batch_wait_host(slot) until the next submit on that slot.  Lets a sharded job hand the forces
+ * to its gather without uploading again what was just downloaded. */
+int mpc_batch_device_buffers(mpc_batch_t* eng, int slot, float** forces_dev, int32_t** status_dev);
 /* Human-readable description of the last error on this engine ("" if none). */
 const char* mpc_batch_last_error(const mpc_batch_t* eng);
 /* Library-level: text of the last error when no engine exists (create failed). */

@@ -121,7 +121,22 @@ void update_solver_settings(int max_iter, double rho, double sigma, double solve
   if (use_jcqp > 1.5) update.use_jcqp = 2;
   else if (use_jcqp > 0.5) update.use_jcqp = 1;
   else update.use_jcqp = 0;
+  // Upstream, use_jcqp = 1 / 2 hands the same QP (full / reduced) to the JCQP ADMM solver instead of qpOASES
+  // (SolverMPC.cpp:406-420, 558-619) and stops at the residual tolerance `terminate`; the shipped caller hard-wires
+  // 0.0 (ConvexMPCLocomotion.cpp:649).  This engine has one QP kernel: it returns the KKT-exact optimum that ADMM
+  // iterates towards, so rho / sigma / solver_alpha / terminate / max_iter have nothing to act on.  Said once, loudly,
+  // rather than silently ignored; mpc_jcqp_requested() lets a caller check.
+  static int told = 0;
+  if (update.use_jcqp != 0 && !told) {
+    told = 1;
+    fprintf(stderr, "[quadruped_mpc_b200] update_solver_settings: use_jcqp=%d requested -- there is no ADMM path in this "
+                    "library; the QP is solved to its exact optimum by the active-set kernel and rho/sigma/alpha/"
+                    "terminate/max_iter are ignored\n", update.use_jcqp);
+  }
 }
+
+// Additive: the use_jcqp mode last requested through update_solver_settings (0, 1 or 2); see the note there.
+extern "C" int mpc_jcqp_requested(void) { return update.use_jcqp; }
 
 // reference: convexMPC_interface.cpp:121-169
 void update_problem_data_floats(float* p, float* v, float* q, float* w, float* r, float yaw, float* weights,

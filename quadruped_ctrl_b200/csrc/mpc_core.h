@@ -1564,13 +1564,15 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
 // Stage 4: scatter (SolverMPC.cpp:545-557): eliminated variables are exactly 0.
 //   forces   [12] fp32  = q_soln[0..11] (what get_solution(0..11) hands the caller)
 //   solution [12h] fp64 = q_soln (optional)
-// On any failure status the forces are zero (the reference would return stale memory).
+// On any failure status -- the iteration cap included -- the forces are zero (the reference would return stale memory).
 // ---------------------------------------------------------------------------
 template <class Cx>
 MPC_HD void scatter(const Cx& cx, const Work& k, float* forces, double* solution, int32_t* status) {
   const Scalars* sc = k.sc;
   const int code = sc->status;
-  const bool ok = (code == MPC_STATUS_OPTIMAL || code == MPC_STATUS_MAX_ITER);
+  // MAX_ITER: a dual active-set method walks through primal-INFEASIBLE points (outside the friction cone, negative
+  // fz) until it terminates, so an iterate cut short must not be handed out as forces: zeros, and the flag
+  const bool ok = code == MPC_STATUS_OPTIMAL;
   MPC_FOR(i, 12) {
     const int pos = k.posk[i / 3];
     forces[i] = (ok && pos >= 0) ? (float)k.x[3 * pos + (i % 3)] : 0.f;

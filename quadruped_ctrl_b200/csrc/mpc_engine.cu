@@ -499,6 +499,30 @@ struct mpc_batch {
 
 namespace {
 
+// Entry points run on the engine's device and put the caller's current device back afterwards (a process that
+// drives several GPUs must not find its thread's device changed by a call on another engine).
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) {
+      err = cudaSetDevice(dev);
+      changed = err == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    if (changed && prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define ON_DEVICE(eng)                                                     \
+  DeviceGuard dev_guard_((eng)->device);                                   \
+  if (dev_guard_.err != cudaSuccess) {                                     \
+    (eng)->err = std::string("cudaSetDevice: ") + cudaGetErrorString(dev_guard_.err); \
+    return MPC_E_CUDA;                                                     \
+  }
+
 #define CK(call)                                                                        \
   do {                                                                                  \
     cudaError_t e_ = (call);                                                            \
@@ -719,10 +743,13 @@ int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int gr
 // single-robot tick -- where launch overhead, not the solve, is most of the latency.  A working set that outgrows the
 // class's tile cannot be re-queued on this path; it comes back as MAX_ITER with few iterations and the host entry
 // repeats the solve on the general path.
+int ensure_slot(mpc_batch* eng, int q);
+
 int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, float* forces, double* solution,
                     int32_t* status, cudaStream_t st, int32_t* nvar_out, double* H_out, double* g_out,
                     int single_class = -1) {
   if (batch == 0) return MPC_OK;
+  if (int rc = ensure_slot(eng, slot)) return rc;
   const int nc = (int)eng->classes.size();
   mpc_batch::Slot& S = eng->s[slot];
   if (single_class >= 0) {
@@ -778,6 +805,58 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
   return MPC_OK;
 }
 
+// Scratch slot q: stream, device / pinned buffers, class lists, and the catch-all class's per-CTA slab (sized for the
+// CTAs a batch of max_batch problems can occupy).  Allocated on first use.
+int ensure_slot(mpc_batch* eng, int q) {
+  mpc_batch::Slot& S = eng->s[q];
+  if (S.stream) return MPC_OK;
+#define CKS(call)                                                                        \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      eng->err = std::string(#call) + ": " + cudaGetErrorString(e_);                     \
+      return e_ == cudaErrorMemoryAllocation ? MPC_E_NOMEM : MPC_E_CUDA;                 \
+    }                                                                                    \
+  } while (0)
+  const size_t B = (size_t)eng->max_batch, NU = 12 * (size_t)eng->h;
+  const ClassCfg& big = eng->classes.back();
+  cudaStream_t st = nullptr;
+  CKS(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CKS(cudaMalloc(&S.rec_dev, B * eng->stride));
+  // forces | status | solution in ONE block per side, so that a small batch's results come back in one copy
+  const size_t off_st = (B * 12 * sizeof(float) + 15) / 16 * 16;
+  const size_t off_sol = (off_st + B * sizeof(int32_t) + 15) / 16 * 16;
+  S.out_bytes = off_sol + B * NU * sizeof(double);
+  CKS(cudaMalloc(&S.out_dev, S.out_bytes));
+  S.forces_dev = (float*)S.out_dev;
+  S.status_dev = (int32_t*)(S.out_dev + off_st);
+  S.sol_dev = (double*)(S.out_dev + off_sol);
+  CKS(cudaMallocHost(&S.rec_pin, B * eng->stride));
+  CKS(cudaMallocHost(&S.out_pin, S.out_bytes));
+  S.forces_pin = (float*)S.out_pin;
+  S.status_pin = (int32_t*)(S.out_pin + off_st);
+  S.sol_pin = (double*)(S.out_pin + off_sol);
+  CKS(cudaMalloc(&S.lists, sizeof(int) * kMaxClasses * B));
+  CKS(cudaMalloc(&S.counts, sizeof(int) * 2 * kMaxClasses));
+  CKS(cudaMemset(S.counts, 0, sizeof(int) * 2 * kMaxClasses));
+  CKS(cudaMalloc(&S.slab, big.L.slab_bytes * (size_t)std::min<long long>(big.grid, eng->max_batch)));
+  S.stream = st;  // last: marks the slot as complete
+#undef CKS
+  return MPC_OK;
+}
+
+// Event ring of the kernel timing, created when timing is first switched on.
+int ensure_timing(mpc_batch* eng) {
+  if (!eng->ring0.empty()) return MPC_OK;
+  eng->ring0.assign((size_t)kRing * kMaxClasses, nullptr);
+  eng->ring1.assign((size_t)kRing * kMaxClasses, nullptr);
+  for (size_t i = 0; i < eng->ring0.size(); i++) {
+    CK(cudaEventCreate(&eng->ring0[i]));
+    CK(cudaEventCreate(&eng->ring1[i]));
+  }
+  return MPC_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -825,41 +904,17 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
   eng->max_batch = max_batch;
   eng->sms = prop.multiProcessorCount;
   eng->stride = mpc_record_stride(horizon);
-  CKC(cudaSetDevice(device));
+  DeviceGuard guard(device);  // the caller's current device is put back on return
+  if (guard.err != cudaSuccess) {
+    eng->err = std::string("cudaSetDevice: ") + cudaGetErrorString(guard.err);
+    return fail(MPC_E_CUDA);
+  }
   CKC(cudaEventCreate(&eng->ev0));
   CKC(cudaEventCreate(&eng->ev1));
-  eng->ring0.assign((size_t)kRing * kMaxClasses, nullptr);
-  eng->ring1.assign((size_t)kRing * kMaxClasses, nullptr);
-  for (size_t i = 0; i < eng->ring0.size(); i++) {
-    CKC(cudaEventCreate(&eng->ring0[i]));
-    CKC(cudaEventCreate(&eng->ring1[i]));
-  }
   int rc = build_classes(eng);
   if (rc) return fail(rc);
-  const size_t B = (size_t)max_batch, NU = 12 * (size_t)horizon;
-  const ClassCfg& big = eng->classes.back();
-  for (int q = 0; q < kSlots; q++) {
-    mpc_batch::Slot& S = eng->s[q];
-    CKC(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
-    CKC(cudaMalloc(&S.rec_dev, B * eng->stride));
-    // forces | status | solution in ONE block per side, so that a small batch's results come back in one copy
-    const size_t off_st = (B * 12 * sizeof(float) + 15) / 16 * 16;
-    const size_t off_sol = (off_st + B * sizeof(int32_t) + 15) / 16 * 16;
-    S.out_bytes = off_sol + B * NU * sizeof(double);
-    CKC(cudaMalloc(&S.out_dev, S.out_bytes));
-    S.forces_dev = (float*)S.out_dev;
-    S.status_dev = (int32_t*)(S.out_dev + off_st);
-    S.sol_dev = (double*)(S.out_dev + off_sol);
-    CKC(cudaMallocHost(&S.rec_pin, B * eng->stride));
-    CKC(cudaMallocHost(&S.out_pin, S.out_bytes));
-    S.forces_pin = (float*)S.out_pin;
-    S.status_pin = (int32_t*)(S.out_pin + off_st);
-    S.sol_pin = (double*)(S.out_pin + off_sol);
-    CKC(cudaMalloc(&S.lists, sizeof(int) * kMaxClasses * B));
-    CKC(cudaMalloc(&S.counts, sizeof(int) * 2 * kMaxClasses));
-    CKC(cudaMemset(S.counts, 0, sizeof(int) * 2 * kMaxClasses));
-    CKC(cudaMalloc(&S.slab, big.L.slab_bytes * (size_t)big.grid));
-  }
+  rc = ensure_slot(eng, 0);  // the other scratch slots are allocated on first use (the legacy single-robot engine never needs them)
+  if (rc) return fail(rc);
   CKC(cudaMalloc(&eng->caps_dev, sizeof(int) * kMaxClasses));
   int caps[kMaxClasses] = {0};
   for (size_t i = 0; i < eng->classes.size(); i++) caps[i] = eng->classes[i].nv_cap;
@@ -871,7 +926,7 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
 
 void mpc_batch_destroy(mpc_batch_t* eng) {
   if (!eng) return;
-  cudaSetDevice(eng->device);
+  DeviceGuard guard(eng->device);
   for (int q = 0; q < kMaxPeers; q++)
     if (eng->peer_open[q]) cudaIpcCloseMemHandle(eng->peer_open[q]);
   cudaFree(eng->gather_buf);
@@ -904,7 +959,7 @@ int mpc_batch_solve_device(mpc_batch_t* eng, const void* records_dev, int batch,
     eng->err = "mpc_batch_solve_device: bad argument (null pointer, batch out of range or records not 16-byte aligned)";
     return MPC_E_ARG;
   }
-  CK(cudaSetDevice(eng->device));
+  ON_DEVICE(eng);
   return solve_on_stream(eng, 0, records_dev, batch, forces_dev, solution_dev, status_dev, (cudaStream_t)cuda_stream,
                          nullptr, nullptr, nullptr);
 }
@@ -917,35 +972,55 @@ int mpc_batch_solve_device_slot(mpc_batch_t* eng, int slot, const void* records_
     eng->err = "mpc_batch_solve_device_slot: bad argument";
     return MPC_E_ARG;
   }
-  CK(cudaSetDevice(eng->device));
+  ON_DEVICE(eng);
   return solve_on_stream(eng, slot, records_dev, batch, forces_dev, solution_dev, status_dev,
                          (cudaStream_t)cuda_stream, nullptr, nullptr, nullptr);
 }
 
+// zero_copy: the caller vouches that records_host is page-locked and stays untouched until wait_host(slot)
+static int submit_host_impl(mpc_batch_t* eng, int slot, const void* records_host, int batch, int want_solution,
+                            bool zero_copy);
+
 int mpc_batch_submit_host(mpc_batch_t* eng, int slot, const void* records_host, int batch, int want_solution) {
+  return submit_host_impl(eng, slot, records_host, batch, want_solution, false);
+}
+
+int mpc_batch_submit_host_pinned(mpc_batch_t* eng, int slot, const void* records_pinned, int batch, int want_solution) {
+  if (eng && records_pinned) {
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, records_pinned) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) {
+      cudaGetLastError();
+      eng->err = "mpc_batch_submit_host_pinned: records are not in page-locked host memory";
+      return MPC_E_ARG;
+    }
+  }
+  return submit_host_impl(eng, slot, records_pinned, batch, want_solution, true);
+}
+
+static int submit_host_impl(mpc_batch_t* eng, int slot, const void* records_host, int batch, int want_solution,
+                            bool zero_copy) {
   if (!eng) return MPC_E_ARG;
   if (slot < 0 || slot >= kSlots || !records_host || batch < 0 || batch > eng->max_batch) {
     eng->err = "mpc_batch_submit_host: bad argument";
     return MPC_E_ARG;
   }
-  CK(cudaSetDevice(eng->device));
+  ON_DEVICE(eng);
+  if (int rc = ensure_slot(eng, slot)) return rc;
   mpc_batch::Slot& S = eng->s[slot];
   S.pending_batch = batch;
   S.pending_solution = want_solution != 0;
   if (batch == 0) return MPC_OK;
   const size_t NU = 12 * (size_t)eng->h;
-  // pageable -> pinned staging on the host (skipped when the caller filled the slot's pinned buffer in place),
-  // then H2D, kernels and D2H queued on the slot's stream; nothing here waits for the GPU
+  // The records are COPIED before this call returns (staged into the slot's pinned buffer chunk by chunk, chunk c's
+  // DMA overlapping the host copy of chunk c+1), so the caller may reuse its buffer at once -- whatever kind of
+  // memory it is.  The DMA reads a buffer in place only when it is the slot's own pinned buffer or when the caller
+  // opted in (mpc_batch_submit_host_pinned: page-locked, untouched until wait_host).
   const size_t bytes = (size_t)batch * eng->stride;
-  bool in_place = records_host == (const void*)S.rec_pin;
-  if (!in_place) {  // a page-locked caller buffer (cudaHostAlloc / cudaHostRegister) is read by the DMA in place
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, records_host) == cudaSuccess) in_place = attr.type == cudaMemoryTypeHost;
-    else cudaGetLastError();
-  }
+  const bool in_place = zero_copy || records_host == (const void*)S.rec_pin;
   if (in_place) {
     CK(cudaMemcpyAsync(S.rec_dev, records_host, bytes, cudaMemcpyHostToDevice, S.stream));
-  } else {  // pageable: staged chunk by chunk, so that chunk c's DMA overlaps the host copy of chunk c+1
+  } else {
     const size_t chunk = 512u << 10;
     for (size_t off = 0; off < bytes; off += chunk) {
       const size_t n = std::min(chunk, bytes - off);
@@ -988,12 +1063,13 @@ int mpc_batch_wait_host(mpc_batch_t* eng, int slot, float* forces_host, double* 
     return MPC_E_ARG;
   }
   mpc_batch::Slot& S = eng->s[slot];
+  if (!S.stream) return MPC_OK;  // nothing was ever submitted on this slot
   const int batch = S.pending_batch;
   if (solution_host && !S.pending_solution) {
     eng->err = "mpc_batch_wait_host: the solution was not requested at submit time";
     return MPC_E_ARG;
   }
-  CK(cudaSetDevice(eng->device));
+  ON_DEVICE(eng);
   CK(cudaStreamSynchronize(S.stream));
   const size_t NU = 12 * (size_t)eng->h;
   if (S.pending_single_class >= 0 && S.pending_single_class < (int)eng->classes.size() - 1 && batch == 1 &&
@@ -1037,7 +1113,7 @@ int mpc_batch_build_records_device(mpc_batch_t* eng, const void* ticks_dev, int 
     return MPC_E_ARG;
   }
   if (batch == 0) return MPC_OK;
-  CK(cudaSetDevice(eng->device));
+  ON_DEVICE(eng);
   mpc_build_records_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(
       (const float*)ticks_dev, batch, eng->h, (char*)records_dev, eng->stride, state_out_dev);
   eng->launches++;
@@ -1060,7 +1136,7 @@ int mpc_batch_assemble_device(mpc_batch_t* eng, const void* records_dev, int bat
     eng->err = "mpc_batch_assemble_device: bad argument";
     return MPC_E_ARG;
   }
-  CK(cudaSetDevice(eng->device));
+  ON_DEVICE(eng);
   return solve_on_stream(eng, 0, records_dev, batch, eng->s[0].forces_dev, nullptr, nullptr, (cudaStream_t)cuda_stream,
                          nvar_dev, H_dev, g_dev);
 }
@@ -1075,7 +1151,7 @@ int mpc_batch_set_gather_peers(mpc_batch_t* eng, float* const* peers, int n_peer
 
 int mpc_batch_gather_alloc(mpc_batch_t* eng, int world_batch, void* ipc_handle_out) {
   if (!eng || world_batch < 1 || !ipc_handle_out) return MPC_E_ARG;
-  CK(cudaSetDevice(eng->device));
+  ON_DEVICE(eng);
   if (eng->gather_buf) CK(cudaFree(eng->gather_buf));
   eng->gather_buf = nullptr;
   eng->gather_slot_bytes = ((size_t)world_batch * 12 * sizeof(float) + kMaxPeers * sizeof(unsigned) + 255) / 256 * 256;
@@ -1093,7 +1169,7 @@ int mpc_batch_gather_alloc(mpc_batch_t* eng, int world_batch, void* ipc_handle_o
 int mpc_batch_gather_connect(mpc_batch_t* eng, const void* ipc_handles, int world, int rank, int rank_offset) {
   if (!eng || !ipc_handles || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !eng->gather_buf)
     return MPC_E_ARG;
-  CK(cudaSetDevice(eng->device));
+  ON_DEVICE(eng);
   float* peers[kMaxPeers] = {nullptr};
   for (int q = 0; q < world; q++) {
     if (q == rank) {
@@ -1121,7 +1197,7 @@ int mpc_batch_gather_connect(mpc_batch_t* eng, const void* ipc_handles, int worl
 
 int mpc_batch_gather_sync_slot(mpc_batch_t* eng, int slot, void* cuda_stream) {
   if (!eng || slot < 0 || slot >= kSlots || !eng->peer_flags_dev || eng->gather_world < 1) return MPC_E_ARG;
-  CK(cudaSetDevice(eng->device));
+  ON_DEVICE(eng);
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const unsigned epoch = ++eng->gather_epoch[slot];
   const unsigned* my_flags =
@@ -1169,6 +1245,10 @@ int mpc_batch_set_ctas_per_sm_limit(mpc_batch_t* eng, int limit) {
 
 int mpc_batch_set_timing(mpc_batch_t* eng, int enabled) {
   if (!eng) return MPC_E_ARG;
+  if (enabled) {
+    ON_DEVICE(eng);
+    if (int rc = ensure_timing(eng)) return rc;
+  }
   eng->timed = enabled != 0;
   eng->timed_class = -1;
   return MPC_OK;
@@ -1176,6 +1256,8 @@ int mpc_batch_set_timing(mpc_batch_t* eng, int enabled) {
 
 int mpc_batch_set_timed_class(mpc_batch_t* eng, int idx) {
   if (!eng || idx < -1 || idx >= (int)eng->classes.size()) return MPC_E_ARG;
+  ON_DEVICE(eng);
+  if (int rc = ensure_timing(eng)) return rc;
   eng->timed = true;
   eng->timed_class = idx;
   return MPC_OK;
@@ -1225,11 +1307,26 @@ int mpc_batch_timing_collect(mpc_batch_t* eng, int idx, float* mean_ms, int* n_s
 int mpc_batch_host_buffers(mpc_batch_t* eng, int slot, void** records, float** forces, double** solution,
                            int32_t** status) {
   if (!eng || slot < 0 || slot >= kSlots) return MPC_E_ARG;
+  {
+    ON_DEVICE(eng);
+    if (int rc = ensure_slot(eng, slot)) return rc;
+  }
   mpc_batch::Slot& S = eng->s[slot];
   if (records) *records = S.rec_pin;
   if (forces) *forces = S.forces_pin;
   if (solution) *solution = S.sol_pin;
   if (status) *status = S.status_pin;
+  return MPC_OK;
+}
+
+int mpc_batch_device_buffers(mpc_batch_t* eng, int slot, float** forces_dev, int32_t** status_dev) {
+  if (!eng || slot < 0 || slot >= kSlots) return MPC_E_ARG;
+  {
+    ON_DEVICE(eng);
+    if (int rc = ensure_slot(eng, slot)) return rc;
+  }
+  if (forces_dev) *forces_dev = eng->s[slot].forces_dev;
+  if (status_dev) *status_dev = eng->s[slot].status_dev;
   return MPC_OK;
 }
 

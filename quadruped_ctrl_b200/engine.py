@@ -24,17 +24,17 @@ STATUS_OPTIMAL, STATUS_MAX_ITER, STATUS_BAD_INPUT, STATUS_NOT_PD, STATUS_NO_STAN
 
 # every symbol include/mpc_batch.h and include/convexMPC_interface.h declare
 BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_create", "mpc_batch_destroy",
-                 "mpc_batch_solve_device", "mpc_batch_solve_device_slot", "mpc_batch_solve_host", "mpc_batch_submit_host", "mpc_batch_wait_host",
+                 "mpc_batch_solve_device", "mpc_batch_solve_device_slot", "mpc_batch_solve_host", "mpc_batch_submit_host", "mpc_batch_submit_host_pinned", "mpc_batch_wait_host",
                  "mpc_batch_assemble_device", "mpc_batch_build_records_device", "mpc_batch_solve_ticks_device",
                  "mpc_batch_set_gather_peers", "mpc_batch_gather_alloc", "mpc_batch_gather_connect",
                  "mpc_batch_gather_buffer", "mpc_batch_gather_buffer_slot", "mpc_batch_gather_sync", "mpc_batch_gather_sync_slot", "mpc_batch_set_max_iterations", "mpc_batch_set_sweep_variant", "mpc_batch_sweep_variant", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
                  "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
                  "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_class_kernel_ms", "mpc_batch_timing_mark",
-                 "mpc_batch_timing_collect", "mpc_batch_host_buffers",
+                 "mpc_batch_timing_collect", "mpc_batch_host_buffers", "mpc_batch_device_buffers",
                  "mpc_batch_last_error", "mpc_last_error", "mpc_batch_horizon"]
 LEGACY_SYMBOLS = ["setup_problem", "update_problem_data", "update_problem_data_floats", "get_solution",
                   "update_solver_settings", "_Z13update_x_dragf", "mpc_last_status", "mpc_last_iterations",
-                  "mpc_set_robot", "mpc_shutdown", "mpc_legacy_record"]
+                  "mpc_set_robot", "mpc_shutdown", "mpc_legacy_record", "mpc_jcqp_requested"]
 
 
 class MpcError(RuntimeError):
@@ -77,6 +77,7 @@ def lib():
     L.mpc_batch_gather_sync_slot.argtypes = [vp, i32, vp]
     L.mpc_batch_solve_host.argtypes = [vp, vp, i32, vp, vp, vp]
     L.mpc_batch_submit_host.argtypes = [vp, i32, vp, i32, i32]
+    L.mpc_batch_submit_host_pinned.argtypes = [vp, i32, vp, i32, i32]
     L.mpc_batch_wait_host.argtypes = [vp, i32, vp, vp, vp]
     L.mpc_batch_assemble_device.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.mpc_batch_build_records_device.argtypes = [vp, vp, i32, vp, vp, vp]
@@ -107,6 +108,7 @@ def lib():
     L.mpc_batch_timing_collect.argtypes = [vp, i32, ctypes.POINTER(f32), ctypes.POINTER(i32)]
     L.mpc_batch_host_buffers.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                          ctypes.POINTER(vp)]
+    L.mpc_batch_device_buffers.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.mpc_batch_last_error.argtypes = [vp]
     L.mpc_batch_last_error.restype = ctypes.c_char_p
     L.mpc_last_error.restype = ctypes.c_char_p
@@ -227,6 +229,22 @@ class MpcBatch:
                 view(ptrs[2], B * NU * 8, np.float64, (B, NU)),
                 view(ptrs[3], B * 4, np.int32, (B,)))
 
+    def device_forces(self, slot=0):
+        """Slot `slot`'s device forces buffer of the host entry as a cuda tensor [max_batch, 12] f32 (valid after
+        wait_host(slot) until the next submit on the slot)."""
+        torch = _torch()
+        pf, ps = ctypes.c_void_p(), ctypes.c_void_p()
+        self._check(self._L.mpc_batch_device_buffers(self._h, int(slot), ctypes.byref(pf), ctypes.byref(ps)),
+                    "device_buffers")
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (self.max_batch, 12), "typestr": "<f4", "data": (int(pf.value), False),
+                                        "version": 2, "strides": None}
+        keep = getattr(self, "_dev_keep", [])
+        keep.append(_Buf())
+        self._dev_keep = keep
+        return torch.as_tensor(keep[-1], device=torch.device("cuda", self.device))
+
     def kernel_launches(self):
         return int(self._L.mpc_batch_kernel_launches(self._h))
 
@@ -293,6 +311,7 @@ class MpcBatch:
         B = records.shape[0]
         assert records.shape[1] == self.stride, (records.shape, self.stride)
         dev = records.device
+        assert dev.index == self.device, "records live on cuda:%s, the engine on cuda:%d" % (dev.index, self.device)
         if forces is None:
             forces = torch.empty((B, 12), dtype=torch.float32, device=dev)
         if solution is None and want_solution:
@@ -322,12 +341,15 @@ class MpcBatch:
         self._check(rc, "mpc_batch_solve_host")
         return forces, sol, status
 
-    def submit_host(self, slot, records, want_solution=False):
-        """Queues H2D + kernels + D2H for `records` (numpy uint8 [B, stride]) on slot 0..SLOTS-1; returns at once."""
+    def submit_host(self, slot, records, want_solution=False, zero_copy=False):
+        """Queues H2D + kernels + D2H for `records` (numpy uint8 [B, stride]) on slot 0..SLOTS-1; returns at once.
+        The records are copied before the call returns, so the array may be reused immediately.  zero_copy=True
+        (opt-in): `records` is page-locked memory that the DMA engine reads in place -- it must stay untouched
+        until wait_host(slot)."""
         records = np.ascontiguousarray(records, np.uint8)
         assert records.shape[1] == self.stride
-        rc = self._L.mpc_batch_submit_host(self._h, int(slot), records.ctypes.data, records.shape[0],
-                                           int(bool(want_solution)))
+        fn = self._L.mpc_batch_submit_host_pinned if zero_copy else self._L.mpc_batch_submit_host
+        rc = fn(self._h, int(slot), records.ctypes.data, records.shape[0], int(bool(want_solution)))
         self._check(rc, "mpc_batch_submit_host")
 
     def wait_host(self, slot, out_forces=None, out_solution=None, out_status=None):

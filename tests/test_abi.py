@@ -69,12 +69,20 @@ int main(void) {
          offsetof(struct update_data_t, x_drag));
   return 0;
 }'''
+    ref_dir = "/root/reference/src/MPC_Ctrl"
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
         open(c, "w").write(src)
         exe = os.path.join(d, "t")
         subprocess.check_call(["gcc", "-I", INC, c, "-o", exe])
         l1, l2 = subprocess.check_output([exe], text=True).splitlines()
+        if os.path.exists(os.path.join(ref_dir, "convexMPC_interface.h")):
+            # the reference is mounted (build container): compile the SAME probe against ITS header (no Eigen in
+            # that file; read in place, nothing copied) and compare the two compilers' views line for line
+            exe_ref = os.path.join(d, "t_ref")
+            subprocess.check_call(["g++", "-x", "c++", "-I", ref_dir, c, "-o", exe_ref])
+            r1, r2 = subprocess.check_output([exe_ref], text=True).splitlines()
+            assert (l1, l2) == (r1, r2)
     assert [int(x) for x in l1.split()] == [16, 0, 4, 8, 12]
     # floats: p0 v12 q24 w40 r52 yaw100 weights104 traj152 (+12*36*4=1728) alpha1880; u8 gait1884 (+36) pad1920 (+1000)
     # -> 2920; int max_iterations 2920; doubles rho 2928, sigma 2936, solver_alpha 2944, terminate 2952;

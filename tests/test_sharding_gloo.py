@@ -1,7 +1,8 @@
 """N>1 plumbing on the CPU tier: two gloo ranks shard a batch, each solves its range, one all-gather of the
 forces, and every rank ends with the unsharded answer.  The per-shard compute is a stand-in here (the
-host emulation of the kernel source from tests/emu -- there is no GPU on this tier); the -m gpu tier and
-bench.py run the same ShardedSolver over NCCL with the CUDA engine."""
+host emulation of the kernel source from tests/emu -- there is no GPU on this tier).  On the GPUs, bench.py cuts
+configs 4 and 5 with the same sharding.shard_bounds and gathers with all_gather_into_tensor over NCCL (checked in the
+run: `gather_ok`); tests/gpu_peer_gather_check.py covers the fused peer-store gather."""
 import os
 import socket
 import sys
