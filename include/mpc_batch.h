@@ -98,6 +98,43 @@ enum {
 };
 #define MPC_TICK_STRIDE (4 * MPC_TICK_WORDS)
 
+/* ------------------------------------------------------------------------
+ * Gait record / gait state: OffsetDurationGait on the device.
+ * Input, 12 int32 words per robot: iterationsPerMPC, currentIteration, nIterations (segments of the gait cycle),
+ * reserved, offsets[4], durations[4] -- the arguments of Gait::setIterations (Gait.cpp:187-193) and the gait
+ * definition (Gait.cpp:23-41).  Output, 10 32-bit words per robot: _iteration (int32), _phase (fp32),
+ * getContactState()[4] (Gait.cpp:61-80), getSwingState()[4] (Gait.cpp:97-123); optionally getMpcTable()
+ * (Gait.cpp:142-166) as 4*nIterations bytes.
+ * ---------------------------------------------------------------------- */
+enum {
+  MPC_GAIT_ITERATIONS_PER_MPC = 0, MPC_GAIT_CURRENT_ITERATION = 1, MPC_GAIT_SEGMENTS = 2,
+  MPC_GAIT_OFFSETS = 4, MPC_GAIT_DURATIONS = 8, MPC_GAIT_WORDS = 12
+};
+enum {
+  MPC_GAIT_STATE_ITERATION = 0, MPC_GAIT_STATE_PHASE = 1, MPC_GAIT_STATE_CONTACT = 2, MPC_GAIT_STATE_SWING = 6,
+  MPC_GAIT_STATE_WORDS = 10
+};
+
+/* ------------------------------------------------------------------------
+ * Leg record: what the reference does with the 12 solved forces, per robot, on the device --
+ * f_ff = -rBody * f (ConvexMPCLocomotion.cpp:672-685, rBody from the orientation quaternion,
+ * orientation_tools.h:170-188) and LegController::updateCommand (LegController.cpp:114-155: Cartesian PD on top
+ * of the feed-forward force, torque = tauFeedForward + J' force with J from computeLegJacobianAndPosition
+ * (:204-240), joint-space damping).  100 fp32 words (400 bytes):
+ *   0..3   orientation (w,x,y,z)            4..15  joint angles q[leg*3+joint]     16..27 joint rates qd
+ *   28..39 pDes[leg*3+axis]                 40..51 vDes                             52..63 kpCartesian diagonal
+ *   64..75 kdCartesian diagonal             76..87 tauFeedForward[leg*3+joint]
+ *   88,89  crtlParam(2), crtlParam(3) (joint-space kp, kd)
+ *   90..93 (int32) 1 where the leg takes the MPC force as forceFeedForward (stance), 0 = none (swing)
+ *   94..97 link lengths: abad, hip, knee, knee y-offset (MiniCheetah.h:31-37: 0.062, 0.209, 0.195, 0.004)
+ *   98,99  reserved
+ * ---------------------------------------------------------------------- */
+enum {
+  MPC_LEG_Q = 0, MPC_LEG_JOINT_Q = 4, MPC_LEG_JOINT_QD = 16, MPC_LEG_PDES = 28, MPC_LEG_VDES = 40, MPC_LEG_KP = 52,
+  MPC_LEG_KD = 64, MPC_LEG_TAU_FF = 76, MPC_LEG_JOINT_GAINS = 88, MPC_LEG_USE_FF = 90, MPC_LEG_LINKS = 94,
+  MPC_LEG_WORDS = 100
+};
+
 /* Per-problem status word written next to the forces:
  *   bits 0..7   code (MPC_STATUS_*), bits 8..31 working-set iterations taken. */
 enum {
@@ -180,6 +217,17 @@ int mpc_batch_build_records_device(mpc_batch_t* eng, const void* ticks_dev, int 
 int mpc_batch_solve_ticks_device(mpc_batch_t* eng, const void* ticks_dev, int batch,
                                  float* forces_dev, double* solution_dev, int32_t* status_dev,
                                  float* state_out_dev, void* cuda_stream);
+
+/* SURVEY 8f row N2 on the device, one robot per thread: gait_dev [batch][MPC_GAIT_WORDS] int32 ->
+ * state_out_dev [batch][MPC_GAIT_STATE_WORDS]; table_out_dev (optional) receives each robot's contact table at
+ * table_out_dev + i * table_stride (4 * nIterations bytes each; table_stride >= 4 * the largest nIterations). */
+int mpc_batch_gait_state_device(mpc_batch_t* eng, const void* gait_dev, int batch, void* state_out_dev,
+                                unsigned char* table_out_dev, int table_stride, void* cuda_stream);
+/* SURVEY 8f row N4 on the device, one robot per thread: legs_dev [batch][MPC_LEG_WORDS], forces_dev [batch*12]
+ * (what a solve returned) -> f_ff_dev [batch*12] body-frame feed-forward forces, tau_dev [batch*12] joint torques
+ * (tau_abad/hip/knee_ff per leg, [leg*3+joint]). */
+int mpc_batch_leg_commands_device(mpc_batch_t* eng, const void* legs_dev, const float* forces_dev, int batch,
+                                  float* f_ff_dev, float* tau_dev, void* cuda_stream);
 
 /* Debug / parity entry: assembles the reduced QP only and writes it out.
  *   nvar_dev [batch] int32: reduced variable count nv = 3 * (#stance (step,leg))

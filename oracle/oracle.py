@@ -20,7 +20,7 @@ _LIB = None
 def build(force=False):
     """Compiles liboracle.so and, when /root/reference is present, _ref/libqpoases_ref.so."""
     need = force or not os.path.exists(os.path.join(_HERE, "liboracle.so"))
-    src_t = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("mpc_oracle.cpp", "qp_port.cpp", "tick_oracle.cpp",
+    src_t = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("mpc_oracle.cpp", "qp_port.cpp", "tick_oracle.cpp", "leg_oracle.cpp",
                                                                    "Makefile"))
     if not need and os.path.getmtime(os.path.join(_HERE, "liboracle.so")) < src_t:
         need = True
@@ -54,6 +54,11 @@ def lib():
         L.oracle_build_records.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                            ctypes.c_void_p]
         L.oracle_build_records.restype = None
+        L.oracle_gait_state.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.oracle_gait_state.restype = None
+        L.oracle_leg_commands.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_void_p]
+        L.oracle_leg_commands.restype = None
         L.oracle_load_qpoases(os.path.join(_HERE, "_ref", "libqpoases_ref.so").encode())
         _LIB = L
     return _LIB
@@ -129,3 +134,28 @@ def build_records(ticks, horizon):
     st = np.zeros((B, 4), np.float32)
     L.oracle_build_records(ticks.ctypes.data, B, horizon, rec.ctypes.data, st.ctypes.data)
     return rec, st
+
+
+def gait_state(gait, want_table=False):
+    """gait: int32 [B, 12] gait records (include/mpc_batch.h).  Returns (state float32 [B, 10] (word 0 an int32),
+    tables uint8 [B, 4*max nIterations] | None) as the reference's OffsetDurationGait would produce them."""
+    L = lib()
+    gait = np.ascontiguousarray(gait, np.int32).reshape(-1, 12)
+    B = gait.shape[0]
+    state = np.zeros((B, 10), np.float32)
+    stride = 4 * int(gait[:, 2].max()) if want_table else 0
+    tables = np.zeros((B, stride), np.uint8) if want_table else None
+    L.oracle_gait_state(gait.ctypes.data, B, state.ctypes.data, tables.ctypes.data if want_table else None, stride)
+    return state, tables
+
+
+def leg_commands(legs, forces):
+    """legs: float32-viewable [B, 100] leg records, forces float32 [B, 12].  Returns (f_ff [B,12], tau [B,12])."""
+    L = lib()
+    legs = np.ascontiguousarray(legs).view(np.float32).reshape(-1, 100)
+    forces = np.ascontiguousarray(forces, np.float32).reshape(-1, 12)
+    B = legs.shape[0]
+    f_ff = np.zeros((B, 12), np.float32)
+    tau = np.zeros((B, 12), np.float32)
+    L.oracle_leg_commands(legs.ctypes.data, forces.ctypes.data, B, f_ff.ctypes.data, tau.ctypes.data)
+    return f_ff, tau

@@ -26,6 +26,7 @@
 
 #include "mpc_core.h"
 #include "mpc_ticks.h"
+#include "mpc_legs.h"
 
 namespace {
 
@@ -143,6 +144,21 @@ __global__ void mpc_build_records_kernel(const float* ticks, int batch, int h, c
   if (b >= batch) return;
   mpc::build_record_from_tick(ticks + (size_t)b * MPC_TICK_WORDS, h, records + stride * b, (size_t)stride,
                               state_out ? state_out + 4 * (size_t)b : nullptr);
+}
+
+// SURVEY 8f rows N2 / N4, one robot per thread (bodies in mpc_legs.h).
+__global__ void mpc_gait_state_kernel(const int32_t* gait, int batch, float* state_out, unsigned char* table_out,
+                                      int table_stride) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  mpc::gait_state_from_record(gait + (size_t)b * MPC_GAIT_WORDS, state_out + (size_t)b * MPC_GAIT_STATE_WORDS,
+                              table_out ? table_out + (size_t)b * table_stride : nullptr);
+}
+__global__ void mpc_leg_commands_kernel(const float* legs, const float* forces, int batch, float* f_ff, float* tau) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  mpc::leg_commands_from_record(legs + (size_t)b * MPC_LEG_WORDS, forces + (size_t)12 * b, f_ff + (size_t)12 * b,
+                                tau + (size_t)12 * b);
 }
 
 // Device-side barrier of the fused gather: after this rank's solve kernels have completed (stream order), tell every
@@ -1127,6 +1143,38 @@ int mpc_batch_solve_ticks_device(mpc_batch_t* eng, const void* ticks_dev, int ba
   int rc = mpc_batch_build_records_device(eng, ticks_dev, batch, eng->s[0].rec_dev, state_out_dev, cuda_stream);
   if (rc) return rc;
   return mpc_batch_solve_device(eng, eng->s[0].rec_dev, batch, forces_dev, solution_dev, status_dev, cuda_stream);
+}
+
+int mpc_batch_gait_state_device(mpc_batch_t* eng, const void* gait_dev, int batch, void* state_out_dev,
+                                unsigned char* table_out_dev, int table_stride, void* cuda_stream) {
+  if (!eng) return MPC_E_ARG;
+  if (!gait_dev || !state_out_dev || batch < 0 || (table_out_dev && table_stride < 4)) {
+    eng->err = "mpc_batch_gait_state_device: bad argument";
+    return MPC_E_ARG;
+  }
+  if (batch == 0) return MPC_OK;
+  ON_DEVICE(eng);
+  mpc_gait_state_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(
+      (const int32_t*)gait_dev, batch, (float*)state_out_dev, table_out_dev, table_stride);
+  eng->launches++;
+  CK(cudaGetLastError());
+  return MPC_OK;
+}
+
+int mpc_batch_leg_commands_device(mpc_batch_t* eng, const void* legs_dev, const float* forces_dev, int batch,
+                                  float* f_ff_dev, float* tau_dev, void* cuda_stream) {
+  if (!eng) return MPC_E_ARG;
+  if (!legs_dev || !forces_dev || !f_ff_dev || !tau_dev || batch < 0) {
+    eng->err = "mpc_batch_leg_commands_device: bad argument";
+    return MPC_E_ARG;
+  }
+  if (batch == 0) return MPC_OK;
+  ON_DEVICE(eng);
+  mpc_leg_commands_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(
+      (const float*)legs_dev, forces_dev, batch, f_ff_dev, tau_dev);
+  eng->launches++;
+  CK(cudaGetLastError());
+  return MPC_OK;
 }
 
 int mpc_batch_assemble_device(mpc_batch_t* eng, const void* records_dev, int batch, int32_t* nvar_dev, double* H_dev,

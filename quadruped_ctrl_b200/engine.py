@@ -26,6 +26,7 @@ STATUS_OPTIMAL, STATUS_MAX_ITER, STATUS_BAD_INPUT, STATUS_NOT_PD, STATUS_NO_STAN
 BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_create", "mpc_batch_destroy",
                  "mpc_batch_solve_device", "mpc_batch_solve_device_slot", "mpc_batch_solve_host", "mpc_batch_submit_host", "mpc_batch_submit_host_pinned", "mpc_batch_wait_host",
                  "mpc_batch_assemble_device", "mpc_batch_build_records_device", "mpc_batch_solve_ticks_device",
+                 "mpc_batch_gait_state_device", "mpc_batch_leg_commands_device",
                  "mpc_batch_set_gather_peers", "mpc_batch_gather_alloc", "mpc_batch_gather_connect",
                  "mpc_batch_gather_buffer", "mpc_batch_gather_buffer_slot", "mpc_batch_gather_sync", "mpc_batch_gather_sync_slot", "mpc_batch_set_max_iterations", "mpc_batch_set_sweep_variant", "mpc_batch_sweep_variant", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
                  "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
@@ -44,7 +45,7 @@ class MpcError(RuntimeError):
 def build(force=False):
     """Compiles csrc/ for sm_100a into libquadruped_mpc_b200.so (nvcc cross-compiles without a GPU)."""
     src = os.path.join(_HERE, "csrc")
-    deps = [os.path.join(src, f) for f in ("mpc_engine.cu", "mpc_core.h", "mpc_ticks.h", "convexMPC_interface.cpp",
+    deps = [os.path.join(src, f) for f in ("mpc_engine.cu", "mpc_core.h", "mpc_ticks.h", "mpc_legs.h", "convexMPC_interface.cpp",
                                            "Makefile")]
     deps += [os.path.join(_HERE, "..", "include", f) for f in ("mpc_batch.h", "convexMPC_interface.h")]
     stale = force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(map(os.path.getmtime, deps))
@@ -82,6 +83,8 @@ def lib():
     L.mpc_batch_assemble_device.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.mpc_batch_build_records_device.argtypes = [vp, vp, i32, vp, vp, vp]
     L.mpc_batch_solve_ticks_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.mpc_batch_gait_state_device.argtypes = [vp, vp, i32, vp, vp, i32, vp]
+    L.mpc_batch_leg_commands_device.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     L.mpc_batch_set_gather_peers.argtypes = [vp, ctypes.POINTER(vp), i32, i32]
     L.mpc_batch_gather_alloc.argtypes = [vp, i32, vp]
     L.mpc_batch_gather_connect.argtypes = [vp, vp, i32, i32, i32]
@@ -393,6 +396,39 @@ class MpcBatch:
                                                   state.data_ptr() if state is not None else None, st.cuda_stream)
         self._check(rc, "mpc_batch_solve_ticks_device")
         return forces, sol, status, state
+
+    def gait_state_device(self, gait, want_table=False, stream=None):
+        """gait records (cuda int32 [B, 12], see gait.pack_gait_records) -> (state [B, 10] float32 with
+        word 0 an int32, table uint8 [B, 4*max nIterations] | None)."""
+        torch = _torch()
+        assert gait.is_cuda and gait.dtype == torch.int32 and gait.shape[1] == 12 and gait.is_contiguous()
+        B = gait.shape[0]
+        state = torch.empty((B, 10), dtype=torch.float32, device=gait.device)
+        table = None
+        stride = 0
+        if want_table:
+            stride = 4 * int(gait[:, 2].max().item())
+            table = torch.zeros((B, stride), dtype=torch.uint8, device=gait.device)
+        st = stream if stream is not None else torch.cuda.current_stream(gait.device)
+        rc = self._L.mpc_batch_gait_state_device(self._h, gait.data_ptr(), B, state.data_ptr(),
+                                                 table.data_ptr() if table is not None else None, stride, st.cuda_stream)
+        self._check(rc, "mpc_batch_gait_state_device")
+        return state, table
+
+    def leg_commands_device(self, legs, forces, stream=None):
+        """leg records (cuda float32 [B, 100], see legs.pack_leg_records) + solved forces [B, 12] ->
+        (f_ff [B, 12] body-frame feed-forward forces, tau [B, 12] joint torques)."""
+        torch = _torch()
+        assert legs.is_cuda and legs.is_contiguous() and legs.element_size() * legs.shape[1] == 400
+        assert forces.is_cuda and forces.dtype == torch.float32 and forces.is_contiguous()
+        B = legs.shape[0]
+        f_ff = torch.empty((B, 12), dtype=torch.float32, device=legs.device)
+        tau = torch.empty((B, 12), dtype=torch.float32, device=legs.device)
+        st = stream if stream is not None else torch.cuda.current_stream(legs.device)
+        rc = self._L.mpc_batch_leg_commands_device(self._h, legs.data_ptr(), forces.data_ptr(), B, f_ff.data_ptr(),
+                                                   tau.data_ptr(), st.cuda_stream)
+        self._check(rc, "mpc_batch_leg_commands_device")
+        return f_ff, tau
 
     def assemble_device(self, records, stream=None):
         """Parity entry: the reduced QP only.  Returns (nv [B] int32, H [B,12h,12h] f64, g [B,12h] f64)."""

@@ -33,8 +33,9 @@ def emu_lib():
         so = os.path.join(ROOT, "tests", "emu", "libmpc_emu.so")
         core = os.path.join(ROOT, "quadruped_ctrl_b200", "csrc", "mpc_core.h")
         ticks = os.path.join(ROOT, "quadruped_ctrl_b200", "csrc", "mpc_ticks.h")
+        legs = os.path.join(ROOT, "quadruped_ctrl_b200", "csrc", "mpc_legs.h")
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core),
-                                                                 os.path.getmtime(ticks)):
+                                                                 os.path.getmtime(ticks), os.path.getmtime(legs)):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Wno-unknown-pragmas", "-ffp-contract=off", "-fPIC", "-shared", src, "-o", so])
         _EMU = ctypes.CDLL(so)
     return _EMU
@@ -69,3 +70,29 @@ def emu_build_records(ticks, h):
     L.emu_build_records(ctypes.c_void_p(ticks.ctypes.data), B, h, ctypes.c_void_p(rec.ctypes.data),
                         ctypes.c_void_p(st.ctypes.data))
     return rec, st
+
+
+def emu_gait_state(gait, want_table=False):
+    """Host build of the device-side gait-state body (csrc/mpc_legs.h)."""
+    L = emu_lib()
+    gait = np.ascontiguousarray(gait, np.int32).reshape(-1, 12)
+    B = gait.shape[0]
+    state = np.full((B, 10), np.nan, np.float32)
+    stride = 4 * int(gait[:, 2].max()) if want_table else 0
+    tables = np.zeros((B, stride), np.uint8) if want_table else None
+    L.emu_gait_state(ctypes.c_void_p(gait.ctypes.data), B, ctypes.c_void_p(state.ctypes.data),
+                     ctypes.c_void_p(tables.ctypes.data) if want_table else None, stride)
+    return state, tables
+
+
+def emu_leg_commands(legs, forces):
+    """Host build of the device-side leg-command body (csrc/mpc_legs.h)."""
+    L = emu_lib()
+    legs = np.ascontiguousarray(legs).view(np.float32).reshape(-1, 100)
+    forces = np.ascontiguousarray(forces, np.float32).reshape(-1, 12)
+    B = legs.shape[0]
+    f_ff = np.full((B, 12), np.nan, np.float32)
+    tau = np.full((B, 12), np.nan, np.float32)
+    L.emu_leg_commands(ctypes.c_void_p(legs.ctypes.data), ctypes.c_void_p(forces.ctypes.data), B,
+                       ctypes.c_void_p(f_ff.ctypes.data), ctypes.c_void_p(tau.ctypes.data))
+    return f_ff, tau

@@ -11,6 +11,7 @@
 
 #include "../../quadruped_ctrl_b200/csrc/mpc_core.h"
 #include "../../quadruped_ctrl_b200/csrc/mpc_ticks.h"
+#include "../../quadruped_ctrl_b200/csrc/mpc_legs.h"
 
 static std::vector<double> g_dbg_u, g_dbg_minv;
 static std::vector<int> g_dbg_W;
@@ -142,3 +143,15 @@ int emu_layout_regions(int h, int nv_cap, int m_cap, int npad, int packed, int p
 }
 
 }  // extern "C"
+
+// Host build of the N2 / N4 device bodies (csrc/mpc_legs.h).
+extern "C" void emu_gait_state(const int32_t* gait, int batch, float* state, unsigned char* tables, int table_stride) {
+  for (int b = 0; b < batch; b++)
+    mpc::gait_state_from_record(gait + (size_t)b * MPC_GAIT_WORDS, state + (size_t)b * MPC_GAIT_STATE_WORDS,
+                                tables ? tables + (size_t)b * table_stride : nullptr);
+}
+extern "C" void emu_leg_commands(const float* legs, const float* forces, int batch, float* f_ff, float* tau) {
+  for (int b = 0; b < batch; b++)
+    mpc::leg_commands_from_record(legs + (size_t)b * MPC_LEG_WORDS, forces + (size_t)12 * b, f_ff + (size_t)12 * b,
+                                  tau + (size_t)12 * b);
+}

@@ -510,3 +510,38 @@ def test_fused_peer_gather_two_gpus():
                           "--master-addr", "127.0.0.1", "--master-port", "29531", script], capture_output=True,
                          text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_gait_state_and_leg_commands_on_device(oracle, cuda_engine_factory):
+    """SURVEY 8f rows N2 and N4 on the GPU: OffsetDurationGait's iteration / phase / contact and swing progress /
+    contact table, and the reference's use of the solved forces (f_ff = -rBody f, LegController::updateCommand),
+    one robot per thread -- bit for bit what the oracle's restatement of the reference's host code gives, also when
+    the forces come straight out of a solve on the device."""
+    from quadruped_ctrl_b200 import gait as G
+    from quadruped_ctrl_b200 import legs as LG
+    rng = np.random.default_rng(31)
+    recs = []
+    for b in range(2000):
+        nseg = int(rng.choice([10, 14, 16, 20, 36]))
+        name = list(G.GAITS_14)[int(rng.integers(0, len(G.GAITS_14)))]
+        off, dur = G.rescale(*G.GAITS_14[name], nseg)
+        recs.append(LG.pack_gait_records(13, int(rng.integers(0, 200000)), nseg, off, dur))
+    g = np.concatenate(recs)
+    eng = cuda_engine_factory(10, 2048)
+    st_d, tb_d = eng.gait_state_device(torch.from_numpy(g).cuda(), want_table=True)
+    st_o, tb_o = oracle.gait_state(g, want_table=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(st_d.cpu().numpy().view(np.int32), st_o.view(np.int32))
+    assert np.array_equal(tb_d.cpu().numpy(), tb_o)
+    # forces out of a solve -> leg commands, everything on the device
+    B = 2048
+    rec = W.config2(B, 10, 41)
+    forces, _, status = eng.solve_device(torch.from_numpy(rec).cuda())
+    legs = LG.synth_leg_records(B, 42)
+    f_ff, tau = eng.leg_commands_device(torch.from_numpy(legs).cuda(), forces)
+    torch.cuda.synchronize()
+    assert (E.status_code(status.cpu().numpy()) == E.STATUS_OPTIMAL).all()
+    fo, to = oracle.leg_commands(legs, forces.cpu().numpy())
+    assert np.array_equal(f_ff.cpu().numpy().view(np.int32), fo.view(np.int32))
+    assert np.array_equal(tau.cpu().numpy().view(np.int32), to.view(np.int32))
+    assert np.abs(fo).max() > 1.0
