@@ -280,6 +280,17 @@ int mpc_batch_gather_sync_slot(mpc_batch_t* eng, int slot, void* cuda_stream);
 int mpc_batch_set_sweep_variant(mpc_batch_t* eng, int variant);
 int mpc_batch_sweep_variant(const mpc_batch_t* eng);
 
+/* Warm start across MPC ticks (the reference cold-starts every solve, SolverMPC.cpp:529).
+ * cache_dev: device memory, [robots][mpc_batch_warm_stride()] int32, zero-initialised by the caller once; the engine
+ * reads a robot's entry before its solve and rewrites it afterwards (the optimal working set as (step, leg, row)
+ * codes).  robot_ids_dev: [batch] int32 robot id of every problem of the coming solves (NULL: the problem's index).
+ * shift: horizon steps the gait table has advanced since the cached solve (1 for consecutive MPC ticks, 0 to
+ * re-solve the same tick).  The result is the cold-start optimum (the QP is strictly convex; the cache only decides
+ * where the dual active-set method starts), in fewer working-set changes.  cache_dev = NULL turns it off.
+ * A robot must not appear twice in one batch. */
+int mpc_batch_set_warm_start(mpc_batch_t* eng, int* cache_dev, const int* robot_ids_dev, int shift);
+int mpc_batch_warm_stride(void);
+
 /* Iteration cap of the active-set loop (working-set additions); default 4000.
  * The reference caps qpOASES at nWSR = 100 (SolverMPC.cpp:435) and returns stale
  * memory beyond it; this engine reports MPC_STATUS_MAX_ITER instead. */

@@ -1561,6 +1561,160 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
 }
 
 // ---------------------------------------------------------------------------
+// Warm start (the reference cold-starts every tick: `QProblem problem_red` is constructed per call,
+// SolverMPC.cpp:529, nWSR = 100 :435).  In a closed-loop rollout consecutive problems of a robot differ by one shifted
+// horizon step, and so do their optimal working sets.  The engine keeps, per robot, the working set of its last solve
+// as (step, leg, row type) codes; the next solve shifts the codes in time, maps them onto its own stance pairs and
+// starts the dual active-set method from the KKT point of that working set instead of from the unconstrained optimum:
+//   S = N' Minv N (four look-ups per entry) is inverted directly, u = S^{-1}(b - N'x0), x = x0 + Minv N u.
+// The Goldfarb-Idnani invariant -- x optimal for its working set, all duals >= 0 -- must hold before the main loop
+// may continue from there, so rows whose dual comes out negative are removed and the set is re-solved (a few
+// rounds; a singular S or too many rounds fall back to the cold start).  The main loop then adds whatever is still
+// violated and ends at the same unique optimum as the cold start.
+// ---------------------------------------------------------------------------
+constexpr int kWarmStride = 128;  // ints per robot in the cache: count + up to 127 codes ((step*4+leg)*6 + type)
+
+// On entry: x = unconstrained optimum, working set empty (active_set_init).  codes: the robot's cached working set.
+template <class Cx>
+MPC_HD void active_set_warm(const Cx& cx, const float* rec, const Work& k, const int* codes, int shift) {
+  Scalars* sc = k.sc;
+  const int nv = sc->nv, ld = k.ld, ldT = k.ldT, h = k.h;
+  const double mu_inv = (double)(1.0f / rec[MPC_REC_MU]);
+  const double* Hm = k.Hm;
+  double* T = k.T;
+  MPC_ONE {  // shift the cached rows in time and map them onto this problem's stance pairs
+    int m = 0;
+    int nc = codes[0];
+    if (nc < 0) nc = 0;
+    if (nc > kWarmStride - 1) nc = kWarmStride - 1;
+    for (int c = 0; c < nc && m < k.m_cap; c++) {
+      const int code = codes[1 + c];
+      if (code < 0) continue;
+      const int kk = code / 6 - 4 * shift, t = code % 6;
+      if (kk < 0 || kk >= 4 * h) continue;
+      const int j = k.posk[kk];
+      if (j < 0 || ((k.amask[j] >> t) & 1)) continue;  // the leg swings at that step now / duplicate
+      const Row r = make_row(6 * j + t, mu_inv);
+      k.W[m] = 6 * j + t;
+      k.Wia[m] = r.ia; k.Wiz[m] = r.iz; k.Wca[m] = r.ca; k.Wcz[m] = r.cz;
+      k.amask[j] |= 1 << t;
+      m++;
+    }
+    sc->m = m;
+  }
+  cx.sync();
+  bool accepted = false;
+  for (int round = 0; round < 4; round++) {
+    const int m = sc->m;
+    if (m == 0) break;  // uniform
+    // S = N' Minv N into T, the right-hand side b - N'x0 into w, S's diagonal into u (singularity scale)
+#pragma unroll 1
+    for (int e = cx.tid; e < m * m; e += cx.nt) {
+      const int a = e / m, b = e - a * m;
+      Row ra, rb;
+      ra.ia = k.Wia[a]; ra.iz = k.Wiz[a]; ra.ca = k.Wca[a]; ra.cz = k.Wcz[a];
+      rb.ia = k.Wia[b]; rb.iz = k.Wiz[b]; rb.ca = k.Wca[b]; rb.cz = k.Wcz[b];
+      const double v = row_minv_row<Cx::kPacked>(Hm, ld, ra, rb);
+      T[a * ldT + b] = v;
+      if (a == b) k.u[a] = v;
+    }
+    MPC_FOR(a, m) {
+      const double b = (k.W[a] % 6 == 5) ? -k.ub[k.W[a] / 6] : 0.0;
+      k.w[a] = b - (k.Wca[a] * k.x[k.Wia[a]] + k.Wcz[a] * k.x[k.Wiz[a]]);
+    }
+    cx.sync();
+    // T <- S^{-1} in place (Gauss-Jordan; S is positive definite for an independent working set, no pivoting)
+    bool singular = false;
+#pragma unroll 1
+    for (int p = 0; p < m; p++) {
+      const double d = T[p * ldT + p];
+      if (!(d > 1e-11 * k.u[p])) { singular = true; break; }  // uniform: every thread reads the same numbers
+      const double dinv = 1.0 / d;
+      MPC_FOR(a, m) k.tcol[a] = T[a * ldT + p];                 // old column p
+      cx.sync();
+      MPC_FOR(b, m) {                                           // new row p
+        const double v = (b == p) ? dinv : T[p * ldT + b] * dinv;
+        k.r[b] = v;
+      }
+      cx.sync();
+#pragma unroll 1
+      for (int e = cx.tid; e < m * m; e += cx.nt) {
+        const int a = e / m, b = e - a * m;
+        double v;
+        if (a == p) v = k.r[b];
+        else if (b == p) v = -k.tcol[a] * dinv;
+        else v = T[a * ldT + b] - k.tcol[a] * k.r[b];
+        T[a * ldT + b] = v;
+      }
+      cx.sync();
+    }
+    if (singular) break;
+    // u = T (b - N'x0); every dual must be >= 0 for the main loop to take over
+    double worst = 0.0;
+    int widx = 0x7fffffff;
+    MPC_FOR(a, m) {
+      double acc = 0;
+#pragma unroll(Cx::kUnroll)
+      for (int b = 0; b < m; b++) acc += T[a * ldT + b] * k.w[b];
+      k.r[a] = acc;
+      if (acc < worst) { worst = acc; widx = a; }
+    }
+    block_argmin(cx, k.red, worst, widx);
+    cx.sync();
+    if (widx == 0x7fffffff) { accepted = true; break; }
+    MPC_ONE {  // remove the rows with negative duals, keep the order of the others
+      int mm = 0;
+      for (int a = 0; a < m; a++) {
+        const int c = k.W[a];
+        if (k.r[a] < 0.0) { k.amask[c / 6] &= ~(1 << (c % 6)); continue; }
+        if (mm != a) {
+          k.W[mm] = c;
+          k.Wia[mm] = k.Wia[a]; k.Wiz[mm] = k.Wiz[a]; k.Wca[mm] = k.Wca[a]; k.Wcz[mm] = k.Wcz[a];
+        }
+        mm++;
+      }
+      sc->m = mm;
+    }
+    cx.sync();
+  }
+  if (!accepted) {  // nothing usable: cold start
+    const int m = sc->m;
+    cx.sync();
+    MPC_ONE {
+      for (int a = 0; a < m; a++) k.amask[k.W[a] / 6] &= ~(1 << (k.W[a] % 6));
+      sc->m = 0;
+    }
+    cx.sync();
+    return;
+  }
+  const int m = sc->m;
+  MPC_FOR(a, m) k.u[a] = k.r[a];
+  MPC_FOR(i, nv) {  // x = x0 + Minv N u
+    double acc0 = 0, acc1 = 0;
+#pragma unroll(Cx::kUnroll)
+    for (int a = 0; a < m; a++) {
+      const double ua = k.r[a];
+      acc0 += ua * k.Wcz[a] * Hm[hixT<Cx::kPacked>(ld, k.Wiz[a], i)];
+      acc1 += ua * k.Wca[a] * Hm[hixT<Cx::kPacked>(ld, k.Wia[a], i)];
+    }
+    k.x[i] += acc0 + acc1;
+  }
+  cx.sync();
+}
+
+// After the solve: the robot's working set for its next tick, as (step, leg, type) codes.
+template <class Cx>
+MPC_HD void active_set_store(const Cx& cx, const Work& k, int* codes) {
+  MPC_ONE {
+    const Scalars* sc = k.sc;
+    int m = (sc->status == MPC_STATUS_OPTIMAL) ? sc->m : 0;
+    if (m > kWarmStride - 1) m = kWarmStride - 1;
+    codes[0] = m;
+    for (int a = 0; a < m; a++) codes[1 + a] = k.stance[k.W[a] / 6] * 6 + k.W[a] % 6;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Stage 4: scatter (SolverMPC.cpp:545-557): eliminated variables are exactly 0.
 //   forces   [12] fp32  = q_soln[0..11] (what get_solution(0..11) hands the caller)
 //   solution [12h] fp64 = q_soln (optional)

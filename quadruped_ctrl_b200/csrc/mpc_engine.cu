@@ -58,6 +58,9 @@ struct SolveParams {
   int n_peers, rank_offset;
   long long* phase_clk;  // optional [batch][24] SM-clock stamps at phase boundaries (profiling aid)
   int debug_stop;        // profiling aid (env MPC_DEBUG_STOP): 1 stop after assembly, 2 after the inversion; forces are NOT valid
+  int* warm_cache;       // [robots][kWarmStride] working-set cache of the warm start (nullptr: cold start)
+  const int* warm_ids;   // robot id of every problem (nullptr: problem index)
+  int warm_shift;        // horizon steps the gait has advanced since the cached solve
   int32_t* nvar_out;  // assemble-only mode when H_out != nullptr
   double* H_out;
   double* g_out;
@@ -287,6 +290,7 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
     if (k.sc->status == MPC_STATUS_OPTIMAL) {
       // register-resident classes: x = -H^{-1} g came out of the sweep (the gradient rode along as row nv)
       mpc::active_set_init(cx, rec, gait, k, R > 0 && k.sc->nv < GR * R);
+      int* const wc = P.warm_cache ? P.warm_cache + (size_t)(P.warm_ids ? P.warm_ids[b] : b) * mpc::kWarmStride : nullptr;
       if constexpr (R > 0) {
         // shared-memory classes: the active-set loop is a chain of tiny steps, so one warp runs it with
         // __syncwarp / shuffles instead of CTA barriers; the other warps wait at the barrier below
@@ -296,15 +300,21 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
 #else
           const int aw = 0;
 #endif
-          if ((int)(threadIdx.x >> 5) == aw)
-            mpc::active_set(mpc::WarpT<PK>{(int)(threadIdx.x & 31), 32}, rec, gait, k, P.max_iter);
+          if ((int)(threadIdx.x >> 5) == aw) {
+            const mpc::WarpT<PK> wx{(int)(threadIdx.x & 31), 32};
+            if (wc) mpc::active_set_warm(wx, rec, k, wc, P.warm_shift);
+            mpc::active_set(wx, rec, gait, k, P.max_iter);
+          }
         } else {
+          if (wc) mpc::active_set_warm(cx, rec, k, wc, P.warm_shift);
           mpc::active_set(cx, rec, gait, k, P.max_iter);
         }
         __syncthreads();
       } else {
+        if (wc) mpc::active_set_warm(cx, rec, k, wc, P.warm_shift);
         mpc::active_set(cx, rec, gait, k, P.max_iter);
       }
+      if (wc && k.sc->status != mpc::STATUS_RETRY_BIG) mpc::active_set_store(cx, k, wc);
     }
     if (clk && threadIdx.x == 0) clk[3] = clock64();
     const int code = k.sc->status;
@@ -384,9 +394,13 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
         const mpc::Work kg = mpc::carve(P.L, fast, nullptr, cur ^ 1);
         const float* recp = (const float*)(recbuf + (size_t)(cur ^ 1) * P.stride);
         const unsigned char* gaitp = (const unsigned char*)recp + 4 * (MPC_REC_TRAJ + 12 * P.h);
+        int* const wc =
+            P.warm_cache ? P.warm_cache + (size_t)(P.warm_ids ? P.warm_ids[prev_b] : prev_b) * mpc::kWarmStride : nullptr;
+        if (wc) mpc::active_set_warm(wx, recp, kg, wc, P.warm_shift);
         mpc::active_set(wx, recp, gaitp, kg, P.max_iter);
         gsync();
         const int code = kg.sc->status;
+        if (wc && code != mpc::STATUS_RETRY_BIG) mpc::active_set_store(wx, kg, wc);
         if (code == mpc::STATUS_RETRY_BIG && P.retry_list) {
           if (tid == 0) {
             const int slot = atomicAdd(P.retry_count, 1);
@@ -506,6 +520,9 @@ struct mpc_batch {
   unsigned** peer_flags_dev = nullptr;  // [kSlots][kMaxPeers]
   long long* phase_clk = nullptr;
   int ctas_per_sm_limit = 0;
+  int* warm_cache = nullptr;        // warm start: device cache, robot ids, gait shift
+  const int* warm_ids = nullptr;
+  int warm_shift = 1;
   int sweep = MPC_SWEEP_DEFAULT;  // inversion of the register-resident classes: 0 FMA tiles, 1 DMMA grouped sweep
   int debug_stop = 0;
   bool no_host_classify = false;  // env MPC_NO_HOST_CLASSIFY: batches of one take the general path too
@@ -732,6 +749,9 @@ void fill_params(const mpc_batch* eng, int slot, SolveParams& P, const void* rec
   P.warp_mode = 1;
   P.phase_clk = eng->phase_clk;
   P.debug_stop = eng->debug_stop;
+  P.warm_cache = eng->warm_cache;
+  P.warm_ids = eng->warm_ids;
+  P.warm_shift = eng->warm_shift;
   P.n_peers = eng->n_peers;
   P.rank_offset = eng->rank_offset;
   for (int q = 0; q < kMaxPeers; q++)
@@ -1272,6 +1292,16 @@ int mpc_batch_set_sweep_variant(mpc_batch_t* eng, int variant) {
   return MPC_OK;
 }
 int mpc_batch_sweep_variant(const mpc_batch_t* eng) { return eng ? eng->sweep : -1; }
+
+int mpc_batch_warm_stride(void) { return mpc::kWarmStride; }
+
+int mpc_batch_set_warm_start(mpc_batch_t* eng, int* cache_dev, const int* robot_ids_dev, int shift) {
+  if (!eng || shift < 0) return MPC_E_ARG;
+  eng->warm_cache = cache_dev;
+  eng->warm_ids = cache_dev ? robot_ids_dev : nullptr;
+  eng->warm_shift = shift;
+  return MPC_OK;
+}
 
 int mpc_batch_set_max_iterations(mpc_batch_t* eng, int max_iter) {
   if (!eng || max_iter < 1) return MPC_E_ARG;

@@ -28,7 +28,7 @@ BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_creat
                  "mpc_batch_assemble_device", "mpc_batch_build_records_device", "mpc_batch_solve_ticks_device",
                  "mpc_batch_gait_state_device", "mpc_batch_leg_commands_device",
                  "mpc_batch_set_gather_peers", "mpc_batch_gather_alloc", "mpc_batch_gather_connect",
-                 "mpc_batch_gather_buffer", "mpc_batch_gather_buffer_slot", "mpc_batch_gather_sync", "mpc_batch_gather_sync_slot", "mpc_batch_set_max_iterations", "mpc_batch_set_sweep_variant", "mpc_batch_sweep_variant", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
+                 "mpc_batch_gather_buffer", "mpc_batch_gather_buffer_slot", "mpc_batch_gather_sync", "mpc_batch_gather_sync_slot", "mpc_batch_set_max_iterations", "mpc_batch_set_warm_start", "mpc_batch_warm_stride", "mpc_batch_set_sweep_variant", "mpc_batch_sweep_variant", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
                  "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
                  "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_class_kernel_ms", "mpc_batch_timing_mark",
                  "mpc_batch_timing_collect", "mpc_batch_host_buffers", "mpc_batch_device_buffers",
@@ -92,6 +92,7 @@ def lib():
     L.mpc_batch_gather_buffer.argtypes = [vp]
     L.mpc_batch_gather_buffer.restype = vp
     L.mpc_batch_set_max_iterations.argtypes = [vp, i32]
+    L.mpc_batch_set_warm_start.argtypes = [vp, vp, vp, i32]
     L.mpc_batch_set_sweep_variant.argtypes = [vp, i32]
     L.mpc_batch_sweep_variant.argtypes = [vp]
     L.mpc_batch_set_timing.argtypes = [vp, i32]
@@ -174,6 +175,20 @@ class MpcBatch:
     # ---- configuration ------------------------------------------------------------------
     def set_max_iterations(self, n):
         self._check(self._L.mpc_batch_set_max_iterations(self._h, int(n)), "set_max_iterations")
+
+    def new_warm_cache(self, robots):
+        """Zeroed device cache for `robots` robots (cuda int32 [robots, stride])."""
+        torch = _torch()
+        return torch.zeros((int(robots), int(self._L.mpc_batch_warm_stride())), dtype=torch.int32,
+                           device=torch.device("cuda", self.device))
+
+    def set_warm_start(self, cache, robot_ids=None, shift=1):
+        """Warm start across ticks: cache from new_warm_cache() (None: off), robot_ids cuda int32 [B]
+        (None: problem index), shift = horizon steps the gait advanced since the cached solve."""
+        self._warm_keep = (cache, robot_ids)
+        self._check(self._L.mpc_batch_set_warm_start(self._h, cache.data_ptr() if cache is not None else None,
+                                                     robot_ids.data_ptr() if robot_ids is not None else None,
+                                                     int(shift)), "set_warm_start")
 
     def set_sweep_variant(self, variant):
         """0 / "fma": rank-1 sweep on the FP64 FMA pipe; 1 / "mma": grouped sweep on the FP64 tensor pipe (DMMA)."""

@@ -96,3 +96,19 @@ def emu_leg_commands(legs, forces):
     L.emu_leg_commands(ctypes.c_void_p(legs.ctypes.data), ctypes.c_void_p(forces.ctypes.data), B,
                        ctypes.c_void_p(f_ff.ctypes.data), ctypes.c_void_p(tau.ctypes.data))
     return f_ff, tau
+
+
+def emu_solve_warm(rec, h, cache, shift=1, nv_cap=0, m_cap=0, max_iter=100000):
+    """Host build of the kernel body with the warm start: cache int32 [B, 128] is read and rewritten in place."""
+    L = emu_lib()
+    rec = np.ascontiguousarray(rec, np.uint8)
+    B = rec.shape[0]
+    assert cache.dtype == np.int32 and cache.shape == (B, L.emu_warm_stride()) and cache.flags.c_contiguous
+    f = np.zeros((B, 12), np.float32)
+    sol = np.zeros((B, 12 * h))
+    info = np.zeros((B, 4), np.int32)
+    vp = ctypes.c_void_p
+    rc = L.emu_solve_batch_warm(vp(rec.ctypes.data), B, h, nv_cap, m_cap, max_iter, vp(f.ctypes.data),
+                                vp(sol.ctypes.data), vp(info.ctypes.data), vp(cache.ctypes.data), int(shift))
+    assert rc == 0, rc
+    return dict(forces=f, sol=sol, nv=info[:, 0], m=info[:, 1], iters=info[:, 2], status=info[:, 3])

@@ -23,7 +23,8 @@ static int g_dbg_nv = 0, g_dbg_m = 0;
 //   info [batch*4]: nv, active-set size at exit, iterations, status code.
 template <bool PK>
 static int emu_solve_batch_t(const void* records, int batch, int h, int nv_cap, int m_cap, int max_iter, float* forces,
-                             double* solution, int* info, double* H_out, double* g_out) {
+                             double* solution, int* info, double* H_out, double* g_out, int* warm_cache = nullptr,
+                             int warm_shift = 0) {
   using namespace mpc;
   if (nv_cap <= 0) nv_cap = 12 * h;
   if (m_cap <= 0) m_cap = nv_cap;
@@ -68,6 +69,7 @@ static int emu_solve_batch_t(const void* records, int batch, int h, int nv_cap, 
       }
       if (k.sc->status == MPC_STATUS_OPTIMAL) {
         active_set_init(cx, rec, gait, k);
+        if (warm_cache) active_set_warm(cx, rec, k, warm_cache + (size_t)b * kWarmStride, warm_shift);
         active_set(cx, rec, gait, k, max_iter);
       }
     }
@@ -75,6 +77,10 @@ static int emu_solve_batch_t(const void* records, int batch, int h, int nv_cap, 
     g_dbg_W.assign(k.W, k.W + g_dbg_m); g_dbg_u.assign(k.u, k.u + g_dbg_m);
     g_dbg_minv.resize((size_t)g_dbg_nv * g_dbg_nv);
     for (int i = 0; i < g_dbg_nv; i++) for (int j = 0; j < g_dbg_nv; j++) g_dbg_minv[(size_t)i * g_dbg_nv + j] = k.Hm[hix(k.ld, i, j)];
+    if (warm_cache) {
+      if (k.sc->status != MPC_STATUS_OPTIMAL) k.sc->m = 0;
+      active_set_store(cx, k, warm_cache + (size_t)b * kWarmStride);
+    }
     int32_t st = 0;
     scatter(cx, k, forces + 12 * b, solution ? solution + (size_t)NU * b : nullptr, &st);
     if (info) {
@@ -104,6 +110,14 @@ int emu_solve_batch(const void* records, int batch, int h, int nv_cap, int m_cap
   return packed ? emu_solve_batch_t<true>(records, batch, h, nv_cap, m_cap, max_iter, forces, solution, info, H_out, g_out)
                 : emu_solve_batch_t<false>(records, batch, h, nv_cap, m_cap, max_iter, forces, solution, info, H_out, g_out);
 }
+
+// Warm start: warm_cache [batch][kWarmStride] ints, read before and rewritten after every solve.
+int emu_solve_batch_warm(const void* records, int batch, int h, int nv_cap, int m_cap, int max_iter, float* forces,
+                         double* solution, int* info, int* warm_cache, int warm_shift) {
+  return emu_solve_batch_t<false>(records, batch, h, nv_cap, m_cap, max_iter, forces, solution, info, nullptr, nullptr,
+                                  warm_cache, warm_shift);
+}
+int emu_warm_stride(void) { return mpc::kWarmStride; }
 
 // Host build of the device-side record builder (csrc/mpc_ticks.h), one robot at a time.
 void emu_build_records(const float* ticks, int batch, int h, unsigned char* records, float* state_out) {

@@ -545,3 +545,37 @@ def test_gait_state_and_leg_commands_on_device(oracle, cuda_engine_factory):
     assert np.array_equal(f_ff.cpu().numpy().view(np.int32), fo.view(np.int32))
     assert np.array_equal(tau.cpu().numpy().view(np.int32), to.view(np.int32))
     assert np.abs(fo).max() > 1.0
+
+
+def test_warm_start_in_a_closed_loop_rollout(cuda_engine_factory):
+    """SURVEY 8f row N3 on the GPU: robots rolled out in closed loop on the MPC's own model (rollout.Rollout), every
+    tick solved cold and warm (device-resident per-robot working-set cache, robots permuted inside the batch through
+    robot ids).  The warm solve returns the cold optimum to 1e-9 at every tick and needs fewer working-set changes."""
+    from quadruped_ctrl_b200 import rollout as RO
+    for gait, h, B, ticks, kw in (("trotting", 10, 384, 100, dict(mu=0.15, f_max=52.0)),
+                                  ("walking", 10, 192, 40, dict(v_cmd=0.3, f_max=34.0, mu=0.2))):
+        ro = RO.Rollout(B, h, gait, 5, **kw)
+        eng = cuda_engine_factory(h, B)
+        cache = eng.new_warm_cache(B)
+        perm = torch.from_numpy(np.random.default_rng(1).permutation(B).astype(np.int32)).cuda()
+        it_c, it_w, worst = [], [], 0.0
+        for t in range(ticks):
+            rec = ro.records()
+            d = torch.from_numpy(rec).cuda()
+            eng.set_warm_start(None)
+            fc, sc_, stc = eng.solve_device(d, want_solution=True)
+            # the batch in another order: robot ids tie every problem to its own cache entry
+            eng.set_warm_start(cache, robot_ids=perm, shift=1)
+            fw, sw, stw = eng.solve_device(d[perm.long()].contiguous(), want_solution=True)
+            torch.cuda.synchronize()
+            stc, stw = stc.cpu().numpy(), stw.cpu().numpy()
+            assert (E.status_code(stc) == 0).all() and (E.status_code(stw) == 0).all()
+            worst = max(worst, rel(sw.cpu().numpy(), sc_.cpu().numpy()[perm.cpu().numpy()]).max())
+            it_c.append(E.status_iterations(stc).mean())
+            it_w.append(E.status_iterations(stw).mean())
+            ro.advance(fc.cpu().numpy())
+        eng.set_warm_start(None)
+        print("\n[%s h=%d, %d robots x %d ticks] working-set additions per solve: cold %.2f, warm %.2f; max |warm - cold| %.1e"
+              % (gait, h, B, ticks, np.mean(it_c[5:]), np.mean(it_w[5:]), worst))
+        assert worst < 1e-9
+        assert np.mean(it_w[5:]) < 0.9 * np.mean(it_c[5:])
