@@ -275,7 +275,7 @@ int mpc_batch_gather_sync_slot(mpc_batch_t* eng, int slot, void* cuda_stream);
  *   0  symmetric sweep with one rank-1 update per pivot on the FP64 FMA pipe (invert_spd_tiles)
  *   1  grouped symmetric sweep, rank-8 updates / panel / pivot block as DMMA.8x8x4 on the FP64 tensor pipe
  *      (invert_spd_mma) -- the "tensor-core path" of BASELINE config 5
- * Both hold 1e-9 against the fp64 oracle; the results differ in the last bits.  Environment MPC_SWEEP=fma|mma sets
+ * Both hold 1e-9 against the reference solver on the fp64-assembled QP; the results differ in the last bits.  Environment MPC_SWEEP=fma|mma sets
  * the default of new engines. */
 int mpc_batch_set_sweep_variant(mpc_batch_t* eng, int variant);
 int mpc_batch_sweep_variant(const mpc_batch_t* eng);

@@ -66,6 +66,7 @@ struct Layout {
   int big_in_fast;  // 1: Hm and T are carved from `fast`; 0: from the global slab
   int pipe;         // 1: two problems in flight per CTA (see make_layout): disjoint assembly / active-set regions
   int off_scal2, off_ints2, off_gi, off_mom;  // pipe: second per-problem set, active-set region, moment sums
+  int off_wr;       // wrench-space class: its scratch vectors (0: none)
   // byte offsets into `fast`
   int off_scal, off_g, off_x, off_ints, off_union, off_red, off_Hm, off_T;
   int fast_bytes;
@@ -95,10 +96,14 @@ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 // the other warps assemble problem n+1 (phases P0..P9) -- so the assembly scratch and the active-set scratch are
 // disjoint instead of a union, the moment sums get their own place (H^{-1} of problem n is still being read) and the
 // small per-problem state (scalars, stance lists) exists twice.
-inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npad = 0, int packed = -1, int pipe = 0) {
+// wrench: the wrench-space class -- Hm holds a 6h x 6h matrix (not nv_cap x nv_cap) and the workspace carries the
+// scratch vectors of wr_apply().
+inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npad = 0, int packed = -1, int pipe = 0,
+                          int wrench = 0) {
   if (packed < 0) packed = 0;
   Layout L;
   L.pipe = pipe;
+  L.off_wr = 0;
   L.off_scal2 = L.off_ints2 = L.off_gi = L.off_mom = 0;
   L.h = h;
   L.nv_cap = nv_cap;
@@ -123,7 +128,9 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
   int gi = L.ck_len + 1 + 4 * h + (m_cap + 1) * 6;  // ck (16-byte aligned), ub, Wca, Wcz, w, r, u, tcol
   int un = kAsmDoubles(h);
   int t_doubles = m_cap * L.ldT;
-  int hm_doubles = packed ? nv_cap * (nv_cap + 1) / 2 : nv_cap * L.ld;
+  const int hm_n = wrench ? 6 * h : nv_cap;  // dimension of the matrix held in Hm
+  if (wrench) L.ld = packed ? -1 : (hm_n | 1);
+  int hm_doubles = packed ? hm_n * (hm_n + 1) / 2 : hm_n * L.ld;
   if (hm_doubles < 3 * 12 * h) hm_doubles = 3 * 12 * h;  // the assembly parks its moment sums there
   if (npad > 0 && hm_doubles < mma_panel_doubles(npad)) hm_doubles = mma_panel_doubles(npad);  // panel of the DMMA sweep
   if (big_in_fast) gi += t_doubles;
@@ -141,6 +148,10 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
   } else {
     if (gi > un) un = gi;
     o += 8 * un;
+  }
+  if (wrench) {  // wy [6h], wt [2][6h], wv, wz [nv_cap], rcat [24h], rleg [12], dblk [36*h]
+    L.off_wr = o;
+    o += 8 * (3 * 6 * h + 2 * nv_cap + 24 * h + 12 + 36 * h);
   }
   L.off_red = o;
   o += 8 * kRedDoubles;
@@ -164,6 +175,10 @@ struct Work {
   // active-set view of the union
   double *ck, *ub, *Wca, *Wcz, *w, *r, *u, *tcol;
   double* red;
+  // wrench-space class: scratch of wr_apply (wy, wt: 6h; wv, wz: nv), per-row coefficients by catalogue index (rcat),
+  // foot positions relative to the COM (rleg[leg][axis]), the 6x6 blocks D_s = sum_legs G G' (dblk), 1/(2 alpha)
+  double *wy, *wt, *wv, *wz, *rcat, *rleg, *dblk;
+  double i2a;
   int ld, ldT, nv_cap, m_cap, h;
   long long* clk;  // optional per-problem clock stamps (profiling aid), slots 8..23
 };
@@ -214,6 +229,17 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab, int set = 0) {
   k.u = k.r + (L.m_cap + 1);
   k.tcol = k.u + (L.m_cap + 1);
   k.red = (double*)(fast + L.off_red);
+  k.wy = k.wt = k.wv = k.wz = k.rcat = k.rleg = k.dblk = nullptr;
+  k.i2a = 0.0;
+  if (L.off_wr) {
+    k.wy = (double*)(fast + L.off_wr);
+    k.wt = k.wy + 6 * L.h;
+    k.wv = k.wt + 12 * L.h;
+    k.wz = k.wv + L.nv_cap;
+    k.rcat = k.wz + L.nv_cap;
+    k.rleg = k.rcat + 24 * L.h;
+    k.dblk = k.rleg + 12;
+  }
   k.mom = L.pipe ? (double*)(fast + L.off_mom) : k.Hm;
   k.ld = L.ld;
   k.ldT = L.ldT;
@@ -233,8 +259,11 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab, int set = 0) {
 // (the kernel is instruction-fetch heavy); 4 for the catch-all class, whose H^{-1} / T live in an L2-resident slab and
 // whose loops are chains of dependent-latency loads -- unrolling issues the loads of four steps before the first
 // FMA (same summation order, so the same bits).
-template <bool PK, int UNR = 1>
+// kWrench (compile time): H^{-1} is not stored; the active set works through the rank-6h structure of the Hessian
+// (see "wrench-space class" below).
+template <bool PK, int UNR = 1, bool WR = false>
 struct CtaT {
+  static constexpr bool kWrench = WR;
   static constexpr bool kOneWarp = false;
   static constexpr bool kPacked = PK;
   static constexpr int kUnroll = UNR;
@@ -245,6 +274,7 @@ struct CtaT {
 // reductions are shuffles only.
 template <bool PK>
 struct WarpT {
+  static constexpr bool kWrench = false;
   static constexpr bool kOneWarp = true;
   static constexpr bool kPacked = PK;
   static constexpr int kUnroll = 1;
@@ -256,6 +286,7 @@ struct WarpT {
 // current one.
 template <int BAR, int NTP, bool PK = false>
 struct PartT {
+  static constexpr bool kWrench = false;
   static constexpr bool kOneWarp = false;
   static constexpr bool kPacked = PK;
   static constexpr int kUnroll = 1;
@@ -265,8 +296,9 @@ struct PartT {
 using Cta = CtaT<false>;
 using Warp = WarpT<false>;
 #endif
-template <bool PK>
+template <bool PK, bool WR = false>
 struct OneThreadT {
+  static constexpr bool kWrench = WR;
   static constexpr bool kOneWarp = false;
   static constexpr bool kPacked = PK;
   static constexpr int kUnroll = 1;
@@ -715,7 +747,7 @@ MPC_HD void assemble(const Cx& cx, const float* rec, const unsigned char* gait, 
 // d-1 as in the register-resident version); the pivot row is gathered from row p (j <= p) and column p
 // (i > p); the result is mirrored, negated and the 2 taken off the diagonal in one final pass.
 template <class Cx>
-MPC_HD void invert_spd(const Cx& cx, const Work& k) {
+MPC_HD void invert_spd(const Cx& cx, const Work& k, int n_in = -1) {
   // Pivots are taken in groups of K = kSweepGroup so that the matrix (L2-resident in the catch-all class) is read
   // and written once per GROUP instead of once per pivot.  This is NOT the block sweep ruled out above: nothing is
   // inverted blockwise.  (A) the K pivot rows are gathered into fast memory; (B) they are swept against each other
@@ -726,7 +758,7 @@ MPC_HD void invert_spd(const Cx& cx, const Work& k) {
   // per pivot, so the result is bit-identical to it; only the traffic drops by K.
   constexpr int K = kSweepGroup;
   Scalars* sc = k.sc;
-  const int nv = sc->nv, ld = k.ld;
+  const int nv = n_in >= 0 ? n_in : sc->nv, ld = k.ld;  // n_in: the matrix in Hm is n_in x n_in (wrench-space class)
   double* Hm = k.Hm;
   double* S = k.ck;                       // [K][nv_cap] snapshots of the pivot rows
   double* U = k.ck + K * k.nv_cap;        // [K][nv_cap] -snapshot/d
@@ -886,13 +918,13 @@ __host__ __device__ constexpr bool sweep_block_kept(int i, int j2) { return 2 * 
 // gradient g.  It is never pivoted, so the sweep turns it into H^{-1} g and the unconstrained optimum
 // x = -H^{-1} g comes out of the inversion for free (no matrix-vector product afterwards).
 template <int GR, int R, int GC, int C, bool kPacked>
-__device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid, bool with_g) {
+__device__ __forceinline__ void invert_spd_tiles(const Work& k, int tid, bool with_g, int n_in = -1) {
   constexpr int NVP = GR * R;
   constexpr int BUF = NVP + 2;
   static_assert(GC * C == NVP && C % 2 == 0 && 32 % GC == 0, "tile grid must cover the padded matrix");
   static_assert((2 * GC) % GR == 0 || GR % (2 * GC) == 0, "super-block indices of a row slot must be compile-time");
   Scalars* sc = k.sc;
-  const int nv = sc->nv, ld = k.ld;
+  const int nv = n_in >= 0 ? n_in : sc->nv, ld = k.ld;  // n_in: the matrix in Hm is n_in x n_in (wrench-space class)
   double* Hm = k.Hm;
   const int tr = tid / GC, tc = tid % GC, lane = tid & 31;
   const bool gaug = with_g && nv < NVP;
@@ -1085,12 +1117,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // NT threads in the CTA, of which the first NWS warps sweep (the others only meet the barriers).
 template <int NT, int NWS, int NB, bool kPacked>
-__device__ __forceinline__ void invert_spd_mma(const Work& k, int tid, bool with_g) {
+__device__ __forceinline__ void invert_spd_mma(const Work& k, int tid, bool with_g, int n_in = -1) {
   constexpr int NVP = 8 * NB, RW = NB / NWS, HB = NB / 2, NSLOT = HB + 1, NCOL = RW - 1 + NSLOT;
   constexpr int LDP = NVP + 4, KG = 8;  // = mma_panel_ld(NVP), kMmaGroup (host-side constexpr functions)
   static_assert(NB % NWS == 0 && HB % 2 == 0 && NWS * 32 <= NT && (NWS & (NWS - 1)) == 0, "block rows per warp");
   Scalars* sc = k.sc;
-  const int nv = sc->nv, ld = k.ld;
+  const int nv = n_in >= 0 ? n_in : sc->nv, ld = k.ld;  // n_in: the matrix in Hm is n_in x n_in (wrench-space class)
   double* Hm = k.Hm;
   const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
   const bool gaug = with_g && nv < NVP;
@@ -1306,6 +1338,242 @@ __device__ __forceinline__ void invert_spd_mma(const Work& k, int tid, bool with
 #endif
 
 // ---------------------------------------------------------------------------
+// Wrench-space class (problems with more reduced variables than 6h, e.g. three or four stance legs).
+//
+// Every column of B_c factors through the 6-dimensional wrench of its foot: B_c[:, leg] = Bw * G_leg with
+// G_leg = [[r_leg]x ; I3] (torque r x f and force f; ct_ss_mats, SolverMPC.cpp:247-253) and Bw = [0; I_world^{-1}; I/m].
+// Hence  B_qp(reduced) = Psi * G  with Psi the 13h x 6h horizon response to unit wrenches and G block-diagonal
+// (one 6x3 block per stance pair, all pairs of a step in the same block row), and
+//     H = 2 (alpha I + G' K G),   K = Psi' S Psi   (6h x 6h, the condensed Hessian of the wrench problem)
+// has rank <= 6h above the alpha floor.  By the matrix-inversion lemma
+//     H^{-1} = 1/(2 alpha) [ I - G' M G ],   M = (alpha K^{-1} + D)^{-1},   D = G G' (block diagonal, 6x6 per step),
+// so two inversions of size 6h (120 at h = 20, where the reduced QP has up to 240 variables) replace one of size nv,
+// they fit the register-resident sweep of the nv <= 128 class, and M fits in shared memory where H^{-1} (231 KB
+// packed at nv = 240) does not.  H^{-1} is never formed: the active set applies it (wr_apply: two block-sparse
+// products with G and one 6h x 6h matrix-vector product) to the dense vectors it needs.
+// Verified against the dense route in numpy (|H - 2(alpha I + G'KG)| 6e-16 relative on BASELINE config 3) and
+// by the parity tests against the reference solver.
+// ---------------------------------------------------------------------------
+// K, the condensed Hessian of the wrench problem (before the factor 2), into Hm (6h x 6h); the foot positions into
+// rleg; D_s = sum over the stance legs of step s of G G' into dblk; 1/(2 alpha).  Runs after assemble_front.
+template <class Cx>
+MPC_HD void assemble_K(const Cx& cx, const float* rec, const Work& k) {
+  const int h = k.h;
+  double* Bw = k.M;            // 13 x 6 (the 12x12 tables of assemble_front are not needed by this class)
+  double* Cw = k.M + 96;       // C0w, C1w, C2w: 3 x (13 x 6)
+  double* Mw = Cw + 3 * 78;    // six 6 x 6 tables
+  const double dt = (double)rec[MPC_REC_DT], xd = (double)rec[MPC_REC_XDRAG];
+  const int na = (xd != 0.0) ? 3 : 2;
+  MPC_FOR(i, 78) Bw[i] = 0.0;
+  MPC_FOR(i, 12) k.rleg[i] = (double)rec[MPC_REC_R + (i % 3) * 4 + i / 3];  // rleg[leg*3 + axis] = r[axis*4 + leg]
+  cx.sync();
+  MPC_ONE {
+    const double yaw = (double)rec[MPC_REC_YAW];
+    const double yc = cos(yaw), ys = sin(yaw);
+    const double R[3][3] = {{yc, -ys, 0}, {ys, yc, 0}, {0, 0, 1}};
+    const double Ib[3] = {(double)rec[MPC_REC_IBODY], (double)rec[MPC_REC_IBODY + 1], (double)rec[MPC_REC_IBODY + 2]};
+    double Iw[3][3];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double acc = 0;
+        for (int q = 0; q < 3; q++) acc += (R[i][q] * Ib[q]) * R[j][q];
+        Iw[i][j] = acc;
+      }
+    const double det = Iw[0][0] * (Iw[1][1] * Iw[2][2] - Iw[1][2] * Iw[2][1]) -
+                       Iw[0][1] * (Iw[1][0] * Iw[2][2] - Iw[1][2] * Iw[2][0]) +
+                       Iw[0][2] * (Iw[1][0] * Iw[2][1] - Iw[1][1] * Iw[2][0]);
+    const double rdet = 1.0 / det;
+    Bw[6 * 6 + 0] = (Iw[1][1] * Iw[2][2] - Iw[1][2] * Iw[2][1]) * rdet;
+    Bw[6 * 6 + 1] = (Iw[0][2] * Iw[2][1] - Iw[0][1] * Iw[2][2]) * rdet;
+    Bw[6 * 6 + 2] = (Iw[0][1] * Iw[1][2] - Iw[0][2] * Iw[1][1]) * rdet;
+    Bw[7 * 6 + 0] = (Iw[1][2] * Iw[2][0] - Iw[1][0] * Iw[2][2]) * rdet;
+    Bw[7 * 6 + 1] = (Iw[0][0] * Iw[2][2] - Iw[0][2] * Iw[2][0]) * rdet;
+    Bw[7 * 6 + 2] = (Iw[0][2] * Iw[1][0] - Iw[0][0] * Iw[1][2]) * rdet;
+    Bw[8 * 6 + 0] = (Iw[1][0] * Iw[2][1] - Iw[1][1] * Iw[2][0]) * rdet;
+    Bw[8 * 6 + 1] = (Iw[0][1] * Iw[2][0] - Iw[0][0] * Iw[2][1]) * rdet;
+    Bw[8 * 6 + 2] = (Iw[0][0] * Iw[1][1] - Iw[0][1] * Iw[1][0]) * rdet;
+    const double minv = 1.0 / (double)rec[MPC_REC_MASS];
+    for (int i = 0; i < 3; i++) Bw[(9 + i) * 6 + 3 + i] = minv;
+    k.red[32] = yc;
+    k.red[33] = ys;
+  }
+  cx.sync();
+  const double yc = k.red[32], ys = k.red[33];
+  MPC_FOR(e, 78) {  // C0w = B_d for unit wrenches (exact cubic, as in assemble_front)
+    const int i = e / 6, j = e - 6 * i;
+    Cw[e] = dt * Bw[e] + (dt * dt / 2.0) * apply_A(Bw, 6, i, j, yc, ys, xd) + (dt * dt * dt / 6.0) * apply_A2(Bw, 6, i, j, xd);
+  }
+  cx.sync();
+  MPC_FOR(e, 78) {
+    const int i = e / 6, j = e - 6 * i;
+    Cw[78 + e] = dt * apply_A(Cw, 6, i, j, yc, ys, xd);
+    Cw[156 + e] = (dt * dt / 2.0) * apply_A2(Cw, 6, i, j, xd);
+  }
+  cx.sync();
+  MPC_FOR(e, 6 * 36) {  // tables Mw_ab = C_aw' Q C_bw, a <= b, order 00 01 02 11 12 22
+    const int tb = e / 36, ij = e - 36 * tb, i = ij / 6, j = ij - 6 * i;
+    const int a = tb < 3 ? 0 : (tb < 5 ? 1 : 2), b = tb < 3 ? tb : (tb < 5 ? tb - 2 : 2);
+    double acc = 0.0;
+    if (b < na)
+      for (int q = 0; q < 12; q++) acc += ((double)rec[MPC_REC_WEIGHTS + q] * Cw[78 * a + q * 6 + i]) * Cw[78 * b + q * 6 + j];
+    Mw[e] = acc;
+  }
+  MPC_FOR(e, 36 * h) {  // D_s = sum_{stance legs of step s} G G',  G = [[r]x ; I]
+    const int s = e / 36, ij = e - 36 * s, i = ij / 6, j = ij - 6 * i;
+    double acc = 0.0;
+    for (int l = 0; l < 4; l++) {
+      if (k.posk[4 * s + l] < 0) continue;
+      const double rx = k.rleg[3 * l], ry = k.rleg[3 * l + 1], rz = k.rleg[3 * l + 2];
+      const double cm[3][3] = {{0, -rz, ry}, {rz, 0, -rx}, {-ry, rx, 0}};
+      // G row i: i < 3 -> cm[i][.], else unit vector e_{i-3}
+      double d = 0.0;
+      for (int q = 0; q < 3; q++) {
+        const double gi = i < 3 ? cm[i][q] : (i - 3 == q ? 1.0 : 0.0);
+        const double gj = j < 3 ? cm[j][q] : (j - 3 == q ? 1.0 : 0.0);
+        d += gi * gj;
+      }
+      acc += d;
+    }
+    k.dblk[e] = acc;
+  }
+  cx.sync();
+  // K blocks, i >= j:  K[(i,.),(j,.)] = sum_{pa,pb} s_{pa,pb}(i,j) Mw_{pa,pb}  with the power sums of assemble_front
+  const int nblk = h * (h + 1) / 2;
+  MPC_FOR(e, nblk * 36) {
+    const int blk = e / 36, ij = e - 36 * blk, ci = ij / 6, cj = ij - 6 * ci;
+    int i = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= blk) i++;
+    while (i * (i + 1) / 2 > blk) i--;
+    const int j = blk - i * (i + 1) / 2;
+    const double d = (double)(i - j);
+    const double* P = k.psum + 5 * (h - 1 - i);
+    const double P0 = P[0], P1 = P[1], P2 = P[2], P3 = P[3], P4 = P[4];
+    double sm[3][3];
+    sm[0][0] = P0;  sm[0][1] = P1 + d * P0;  sm[0][2] = P2 + 2.0 * d * P1 + d * d * P0;
+    sm[1][0] = P1;  sm[1][1] = P2 + d * P1;  sm[1][2] = P3 + 2.0 * d * P2 + d * d * P1;
+    sm[2][0] = P2;  sm[2][1] = P3 + d * P2;  sm[2][2] = P4 + 2.0 * d * P3 + d * d * P2;
+    double acc = 0.0;
+    for (int pa = 0; pa < na; pa++)
+      for (int pb = 0; pb < na; pb++) {
+        const int lo = pa < pb ? pa : pb, hi = pa < pb ? pb : pa;
+        const int tb = lo * 3 - (lo * (lo - 1)) / 2 + (hi - lo);
+        acc += sm[pa][pb] * Mw[tb * 36 + (pa <= pb ? ci * 6 + cj : cj * 6 + ci)];
+      }
+    const int r_ = 6 * i + ci, c_ = 6 * j + cj;
+    if (Cx::kPacked) {
+      if (r_ >= c_) k.Hm[tri_index(r_, c_)] = acc;
+    } else {
+      k.Hm[r_ * k.ld + c_] = acc;
+      k.Hm[c_ * k.ld + r_] = acc;
+    }
+  }
+  cx.sync();
+}
+
+// Hm <- alpha * Hm + D (block diagonal), between the two inversions: K^{-1} -> alpha K^{-1} + D.
+template <class Cx>
+MPC_HD void wr_form_second(const Cx& cx, const float* rec, const Work& k) {
+  const int n = 6 * k.h;
+  const double alpha = (double)rec[MPC_REC_ALPHA];
+  MPC_FOR(e, n * n) {
+    const int i = e / n, j = e - i * n;
+    if (j > i) continue;
+    const double dd = (i / 6 == j / 6) ? k.dblk[36 * (i / 6) + 6 * (i % 6) + (j % 6)] : 0.0;
+    const double v = alpha * k.Hm[hixT<Cx::kPacked>(k.ld, i, j)] + dd;
+    k.Hm[hixT<Cx::kPacked>(k.ld, i, j)] = v;
+    if (!Cx::kPacked && i != j) k.Hm[j * k.ld + i] = v;
+  }
+  cx.sync();
+}
+
+// z = H^{-1} v = 1/(2 alpha) (v - G' M G v) for dense v, z of length nv (v == z allowed).  Uses wy, wt.
+template <class Cx>
+MPC_HD void wr_apply(const Cx& cx, const Work& k, const double* v, double* z) {
+  const int h = k.h, n = 6 * h, nv = k.sc->nv;
+  MPC_FOR(e, n) {  // wy = G v: per step, sum over its stance legs of [r x v_j ; v_j]
+    const int s = e / 6, c = e - 6 * s;
+    double acc = 0.0;
+    for (int l = 0; l < 4; l++) {
+      const int j = k.posk[4 * s + l];
+      if (j < 0) continue;
+      const double vx = v[3 * j], vy = v[3 * j + 1], vz = v[3 * j + 2];
+      const double rx = k.rleg[3 * l], ry = k.rleg[3 * l + 1], rz = k.rleg[3 * l + 2];
+      double t;
+      switch (c) {
+        case 0: t = ry * vz - rz * vy; break;
+        case 1: t = rz * vx - rx * vz; break;
+        case 2: t = rx * vy - ry * vx; break;
+        case 3: t = vx; break;
+        case 4: t = vy; break;
+        default: t = vz; break;
+      }
+      acc += t;
+    }
+    k.wy[e] = acc;
+  }
+  cx.sync();
+  // wt = M wy.  wy is block sparse (only the steps the working set touches carry a wrench), so all-zero blocks are
+  // skipped; with enough threads two of them share a row (even / odd steps, partial sums in wt[0..n) and wt[n..2n)).
+  // Packed storage: M(i, j) for j <= i is the contiguous run of row i, for j > i a walk down column i.
+  const int parts = (cx.nt >= 2 * n) ? 2 : 1;
+#pragma unroll 1
+  for (int e = cx.tid; e < n * parts; e += cx.nt) {
+    const int part = e >= n ? 1 : 0, i = e - part * n;
+    const int ti = Cx::kPacked ? i * (i + 1) / 2 : i * k.ld;
+    double a0 = 0, a1 = 0;
+#pragma unroll 1
+    for (int s = part; s < h; s += parts) {
+      const double* y = k.wy + 6 * s;
+      const double y0 = y[0], y1 = y[1], y2 = y[2], y3 = y[3], y4 = y[4], y5 = y[5];
+      if (y0 == 0.0 && y1 == 0.0 && y2 == 0.0 && y3 == 0.0 && y4 == 0.0 && y5 == 0.0) continue;
+      const int j0 = 6 * s;
+      double m[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        const int j = j0 + c;
+        m[c] = k.Hm[(!Cx::kPacked || j <= i) ? ti + j : j * (j + 1) / 2 + i];
+      }
+      a0 += m[0] * y0; a1 += m[1] * y1; a0 += m[2] * y2; a1 += m[3] * y3; a0 += m[4] * y4; a1 += m[5] * y5;
+    }
+    k.wt[part * n + i] = a0 + a1;
+  }
+  cx.sync();
+  const double i2a = k.i2a;
+  MPC_FOR(i, nv) {  // z = (v - G' wt) / (2 alpha);  G_l' t = t_force - r x t_torque
+    const int j = i / 3, c = i - 3 * j;
+    const int kk = k.stance[j], s = kk >> 2, l = kk & 3;
+    double t[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) t[q] = k.wt[6 * s + q] + (parts == 2 ? k.wt[n + 6 * s + q] : 0.0);
+    const double rx = k.rleg[3 * l], ry = k.rleg[3 * l + 1], rz = k.rleg[3 * l + 2];
+    double cr;
+    switch (c) {
+      case 0: cr = ry * t[2] - rz * t[1]; break;
+      case 1: cr = rz * t[0] - rx * t[2]; break;
+      default: cr = rx * t[1] - ry * t[0]; break;
+    }
+    z[i] = i2a * (v[i] - (t[3 + c] - cr));
+  }
+  cx.sync();
+}
+
+// wv = sum of catalogue rows weighted by rcat (dense N c), for wr_apply.  rcat[6j + t] = coefficient of row t of pair j.
+template <class Cx>
+MPC_HD void wr_rows_to_dense(const Cx& cx, const Work& k, double mu_inv) {
+  const int nv = k.sc->nv;
+  MPC_FOR(i, nv) {
+    const int j = i / 3, c = i - 3 * j;
+    const double* rc = k.rcat + 6 * j;
+    double v;
+    if (c == 0) v = (rc[0] - rc[1]) * mu_inv;
+    else if (c == 1) v = (rc[2] - rc[3]) * mu_inv;
+    else v = ((rc[0] + rc[1]) + (rc[2] + rc[3])) + (rc[4] - rc[5]);
+    k.wv[i] = v;
+  }
+  cx.sync();
+}
+
+// ---------------------------------------------------------------------------
 // Stage 3: Goldfarb-Idnani dual active-set iterations on the explicit inverse.
 //   x  = -Minv g (unconstrained optimum), working set W empty, duals u = 0;
 //   repeat: pick the most violated row p; move along z = Minv(n_p - N r),
@@ -1322,7 +1590,12 @@ MPC_HD void active_set_init(const Cx& cx, const float* rec, const unsigned char*
   Scalars* sc = k.sc;
   const int nv = sc->nv, ld = k.ld, ns = sc->ns;
   const double* Hm = k.Hm;
-  if (!have_x) MPC_FOR(i, nv) {  // four independent partial sums: the chain is latency-, not throughput-bound
+  if constexpr (Cx::kWrench) {  // x = -H^{-1} g through the rank structure
+    wr_apply(cx, k, k.g, k.x);
+    MPC_FOR(i, nv) k.x[i] = -k.x[i];
+    cx.sync();
+  }
+  if (!Cx::kWrench && !have_x) MPC_FOR(i, nv) {  // four independent partial sums: the chain is latency-, not throughput-bound
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     int j = 0;
 #pragma unroll 1
@@ -1383,17 +1656,29 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
     cx.sync();
     MPC_ONE { sc->iters++; sc->up = 0.0; }
     cx.sync();
+    if constexpr (Cx::kWrench) {  // zp = H^{-1} n_p, kept in g (free once x0 exists) while p is being added
+      MPC_FOR(c, 6 * ns) k.rcat[c] = (c == p) ? 1.0 : 0.0;
+      cx.sync();
+      wr_rows_to_dense(cx, k, mu_inv);
+      wr_apply(cx, k, k.wv, k.g);
+    }
     // ---- inner loop: partial steps drop blocking rows until p can be added ----
     bool fail = false;
     for (;;) {
       const int m = sc->m;
       // w_a = n_a' Minv n_p,  vnp = n_p' Minv n_p
-      MPC_FOR(a, m) {
-        Row ra;
-        ra.ia = k.Wia[a]; ra.iz = k.Wiz[a]; ra.ca = k.Wca[a]; ra.cz = k.Wcz[a];
-        k.w[a] = row_minv_row<Cx::kPacked>(Hm, ld, ra, rp);
+      double vnp;
+      if constexpr (Cx::kWrench) {
+        MPC_FOR(a, m) k.w[a] = k.Wca[a] * k.g[k.Wia[a]] + k.Wcz[a] * k.g[k.Wiz[a]];
+        vnp = rp.ca * k.g[rp.ia] + rp.cz * k.g[rp.iz];
+      } else {
+        MPC_FOR(a, m) {
+          Row ra;
+          ra.ia = k.Wia[a]; ra.iz = k.Wiz[a]; ra.ca = k.Wca[a]; ra.cz = k.Wcz[a];
+          k.w[a] = row_minv_row<Cx::kPacked>(Hm, ld, ra, rp);
+        }
+        vnp = row_minv_row<Cx::kPacked>(Hm, ld, rp, rp);
       }
-      const double vnp = row_minv_row<Cx::kPacked>(Hm, ld, rp, rp);
       cx.sync();
       // r = T w   (T symmetric: walk columns for contiguous reads)
       MPC_FOR(a, m) {
@@ -1429,7 +1714,15 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       // x += t * Minv (n_p - N r): every row touches <= 2 variables, so z is a combination of at most 2(m+1)
       // rows of Minv.  Applied in the (numerically) dependent case too: there z is only round-off-small, not
       // zero, and x and u must move with the same (r, t) for stationarity x = -Minv (g - N u) to survive.
-      {
+      if constexpr (Cx::kWrench) {  // z = H^{-1} (n_p - N r) through the rank structure
+        MPC_FOR(c, 6 * ns) k.rcat[c] = (c == p) ? 1.0 : 0.0;
+        cx.sync();
+        MPC_FOR(a, m) k.rcat[k.W[a]] = -k.r[a];
+        cx.sync();
+        wr_rows_to_dense(cx, k, mu_inv);
+        wr_apply(cx, k, k.wv, k.wz);
+        MPC_FOR(i, nv) k.x[i] += t * k.wz[i];
+      } else {
         MPC_FOR(i, nv) {
           double acc0 = rp.cz * Hm[hixT<Cx::kPacked>(ld, rp.iz, i)], acc1 = rp.ca * Hm[hixT<Cx::kPacked>(ld, rp.ia, i)];
 #pragma unroll(Cx::kUnroll)
@@ -1544,6 +1837,15 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
         k.r[a] = acc;
       }
       cx.sync();
+      if constexpr (Cx::kWrench) {
+        MPC_FOR(c, 6 * ns) k.rcat[c] = 0.0;
+        cx.sync();
+        MPC_FOR(a, m) k.rcat[k.W[a]] = k.r[a];
+        cx.sync();
+        wr_rows_to_dense(cx, k, mu_inv);
+        wr_apply(cx, k, k.wv, k.wz);
+        MPC_FOR(i, nv) k.x[i] += k.wz[i];
+      } else
       MPC_FOR(i, nv) {
         double acc0 = 0, acc1 = 0;
 #pragma unroll(Cx::kUnroll)

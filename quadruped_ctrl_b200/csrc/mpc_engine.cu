@@ -456,6 +456,89 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
   }
 }
 
+// ---- wrench-space class: problems with more reduced variables than the register-resident classes hold (nv > 128)
+// at horizons with 6h <= 128.  H = 2 (alpha I + G'KG) with K of size 6h (mpc_core.h, "wrench-space class"): two
+// register-resident inversions of size 6h instead of one of size nv in an L2 slab, and the active set applies
+// H^{-1} = (I - G'MG) / (2 alpha) from shared memory.  One problem per CTA at a time, 256 threads.
+// SW as above: which register-resident inversion runs.
+template <int MINB, bool PROF, int SW>
+__global__ void __launch_bounds__(256, MINB) mpc_solve_wrench_kernel(const __grid_constant__ SolveParams P) {
+  extern __shared__ __align__(128) char smem[];
+  const int count = P.count ? *P.count : P.batch;
+  if ((int)blockIdx.x >= count) return;
+  uint64_t* bar = (uint64_t*)smem;
+  char* recbuf = smem + 16;
+  char* fast = recbuf + 2 * P.stride;
+  const int tid = (int)threadIdx.x;
+  const mpc::CtaT<true, 1, true> cx{tid, 256};
+  mpc::Work k = mpc::carve(P.L, fast, nullptr);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t rec_bytes = (uint32_t)P.stride;
+  int item = blockIdx.x;
+  if (tid == 0) {
+    const int b0 = P.list ? P.list[item] : item;
+    mbar_expect_tx(&bar[0], rec_bytes);
+    tma_bulk_g2s(recbuf, P.records + P.stride * b0, rec_bytes, &bar[0]);
+  }
+  const int n = 6 * P.h;
+  for (int it = 0; item < count; item += gridDim.x, it++) {
+    const int cur = it & 1;
+    const int next = item + gridDim.x;
+    if (tid == 0 && next < count) {
+      const int bn = P.list ? P.list[next] : next;
+      mbar_expect_tx(&bar[cur ^ 1], rec_bytes);
+      tma_bulk_g2s(recbuf + (size_t)(cur ^ 1) * P.stride, P.records + P.stride * bn, rec_bytes, &bar[cur ^ 1]);
+    }
+    mbar_wait(&bar[cur], (uint32_t)((it >> 1) & 1));
+    const int b = P.list ? P.list[item] : item;
+    const float* rec = (const float*)(recbuf + (size_t)cur * P.stride);
+    const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
+    k.i2a = 0.5 / (double)rec[MPC_REC_ALPHA];
+    mpc::assemble_front(cx, rec, gait, k);
+    auto invert = [&]() {
+      if constexpr (SW == 1) mpc::invert_spd_mma<256, 8, 16, true>(k, tid, false, n);
+      else mpc::invert_spd_tiles<16, 8, 16, 8, true>(k, tid, false, n);
+    };
+    if (k.sc->status == MPC_STATUS_OPTIMAL) {
+      mpc::assemble_K(cx, rec, k);
+      invert();
+    }
+    if (k.sc->status == MPC_STATUS_OPTIMAL) {
+      mpc::wr_form_second(cx, rec, k);
+      invert();
+    }
+    if constexpr (PROF) {
+      if (P.debug_stop != 0) { __syncthreads(); continue; }
+    }
+    if (k.sc->status == MPC_STATUS_OPTIMAL) {
+      mpc::active_set_init(cx, rec, gait, k);
+      mpc::active_set(cx, rec, gait, k, P.max_iter);
+    }
+    const int code = k.sc->status;
+    if (code == mpc::STATUS_RETRY_BIG && P.retry_list) {
+      if (tid == 0) {
+        const int slot = atomicAdd(P.retry_count, 1);
+        P.retry_list[slot] = b;
+      }
+    } else {
+      if (code == mpc::STATUS_RETRY_BIG && tid == 0) k.sc->status = MPC_STATUS_MAX_ITER;
+      __syncthreads();
+      mpc::scatter(cx, k, P.forces + (size_t)12 * b, P.solution ? P.solution + (size_t)12 * P.h * b : nullptr,
+                   P.status ? P.status + b : nullptr);
+      if (P.n_peers > 0) {
+        __syncwarp();
+        peer_store_forces(P, b, tid);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 struct ClassCfg {
   int nv_cap, m_cap, in_fast, threads, grid, variant;
   size_t smem;
@@ -586,7 +669,7 @@ struct DeviceGuard {
 #define MPC_V64_C 8
 #endif
 #define MPC_V64_SHAPE MPC_V64_NT, MPC_V64_GR, MPC_V64_R, MPC_V64_GC, MPC_V64_C
-enum { V_64 = 0, V_96, V_128, V_GENERIC, V_COUNT };
+enum { V_64 = 0, V_96, V_128, V_GENERIC, V_WRENCH, V_COUNT };
 #define MPC_VARIANT_CALL2(v, PROF, SW, EXPR)                                                                  \
   switch (v) {                                                                                               \
     case V_64: { auto kern = mpc_solve_kernel<MPC_V64_SHAPE, MPC_MINB0, false, PROF, SW>; EXPR; } break;      \
@@ -615,8 +698,15 @@ enum { V_64 = 0, V_96, V_128, V_GENERIC, V_COUNT };
   }
 #define MPC_PIPE_CALL(v, sw, EXPR) \
   if (sw) { MPC_PIPE_CALL2(v, 1, EXPR) } else { MPC_PIPE_CALL2(v, 0, EXPR) }
-const int kVariantThreads[V_COUNT] = {MPC_V64_NT, 256, 256, 256};
-const int kVariantPad[V_COUNT] = {64, 96, 128, 0};
+const int kVariantThreads[V_COUNT] = {MPC_V64_NT, 256, 256, 256, 256};
+const int kVariantPad[V_COUNT] = {64, 96, 128, 0, 128};
+#ifndef MPC_MINBW  // wrench-space class: CTAs per SM it is compiled for
+#define MPC_MINBW 2
+#endif
+#define MPC_WRENCH_CALL(prof, sw, EXPR)                                                          \
+  if (prof) { auto kern = mpc_solve_wrench_kernel<MPC_MINBW, true, 0>; EXPR; }                   \
+  else if (sw) { auto kern = mpc_solve_wrench_kernel<MPC_MINBW, false, 1>; EXPR; }               \
+  else { auto kern = mpc_solve_wrench_kernel<MPC_MINBW, false, 0>; EXPR; }
 
 int configure_kernel(mpc_batch* eng, ClassCfg& c) {
   // the attribute is per kernel instantiation: raise it to the device limit
@@ -627,6 +717,12 @@ int configure_kernel(mpc_batch* eng, ClassCfg& c) {
     for (int sw = 1; sw >= 0; sw--) {
       if (prof && sw) continue;
       int o = 0;
+      if (c.variant == V_WRENCH) {
+        MPC_WRENCH_CALL(prof, sw, {
+          CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, c.threads, c.smem));
+        });
+      } else
       MPC_VARIANT_CALL(c.variant, prof, sw, {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, c.threads, c.smem));
@@ -714,6 +810,33 @@ int build_classes(mpc_batch* eng) {
     }
     eng->classes.push_back(c);
   }
+  // wrench-space class: nv > 128 at horizons with 6h <= 128 (see mpc_solve_wrench_kernel).  Its working-set tile is
+  // the largest that keeps two CTAs per SM; a larger working set is re-queued to the catch-all like everywhere else.
+  if (nv_max > 128 && 6 * h <= 128 && !getenv("MPC_NO_WRENCH")) {
+    int sm_smem = 0;
+    CK(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, eng->device));
+    const size_t budget = (size_t)sm_smem / MPC_MINBW - 1024;
+    ClassCfg c;
+    c.nv_cap = nv_max;
+    c.variant = V_WRENCH;
+    c.threads = 256;
+    c.in_fast = 1;
+    c.m_cap = 0;
+    for (int m = 120; m >= 16; m -= 4) {
+      const mpc::Layout Lw = mpc::make_layout(h, nv_max, m, 1, kVariantPad[V_WRENCH], 1, 0, 1);
+      const size_t need = 16 + 2 * eng->stride + Lw.fast_bytes;
+      if (need > budget || (int)need > max_smem) continue;
+      c.m_cap = m;
+      c.L = Lw;
+      c.smem = need;
+      break;
+    }
+    if (c.m_cap > 0) {
+      int rc = configure_kernel(eng, c);
+      if (rc) return rc;
+      eng->classes.push_back(c);
+    }
+  }
   // catch-all: full-size problem and working set in a per-CTA global slab (L2 resident)
   ClassCfg big;
   big.nv_cap = nv_max;
@@ -768,7 +891,11 @@ int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int gr
     CK(cudaGetLastError());
     return MPC_OK;
   }
-  MPC_VARIANT_CALL(c.variant, prof, eng->sweep, (kern<<<grid, c.threads, c.smem, st>>>(P)));
+  if (c.variant == V_WRENCH) {
+    MPC_WRENCH_CALL(prof, eng->sweep, (kern<<<grid, c.threads, c.smem, st>>>(P)));
+  } else {
+    MPC_VARIANT_CALL(c.variant, prof, eng->sweep, (kern<<<grid, c.threads, c.smem, st>>>(P)));
+  }
   eng->launches++;
   CK(cudaGetLastError());
   return MPC_OK;
@@ -795,7 +922,7 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
     P.L = c.L;
     P.warp_mode = c.variant == V_64 ? 1 : 0;
     P.slab = c.in_fast ? nullptr : S.slab;
-    return launch_solve(eng, c, P, std::min(c.grid, batch), st);
+    return launch_solve(eng, c, P, std::min(c.grid, batch), st);  // (the wrench class: a tile overflow comes back as MAX_ITER)
   }
   // class counters are double-buffered by solve parity: this solve's classify kernel zeroes the other set
   int* counts = S.counts + (S.parity ? kMaxClasses : 0);
@@ -808,7 +935,9 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
   const bool time_all = eng->timed && eng->timed_class < 0;
   if (time_all) CK(cudaEventRecord(eng->ev0, st));
   for (int ci = 0; ci < nc; ci++) {
-    const ClassCfg& c = eng->classes[ci];
+    // the assemble-only parity entry writes the reduced QP itself out: the wrench-space class never forms it, so its
+    // problems go through the catch-all kernel there
+    const ClassCfg& c = (H_out && eng->classes[ci].variant == V_WRENCH) ? eng->classes.back() : eng->classes[ci];
     SolveParams P;
     fill_params(eng, slot, P, records, batch, forces, solution, status);
     P.list = S.lists + (size_t)ci * eng->max_batch;

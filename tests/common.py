@@ -112,3 +112,18 @@ def emu_solve_warm(rec, h, cache, shift=1, nv_cap=0, m_cap=0, max_iter=100000):
                                 vp(sol.ctypes.data), vp(info.ctypes.data), vp(cache.ctypes.data), int(shift))
     assert rc == 0, rc
     return dict(forces=f, sol=sol, nv=info[:, 0], m=info[:, 1], iters=info[:, 2], status=info[:, 3])
+
+
+def emu_solve_wrench(rec, h, m_cap=0, max_iter=100000):
+    """Host build of the wrench-space class (H^{-1} through the rank-6h structure of the Hessian)."""
+    L = emu_lib()
+    rec = np.ascontiguousarray(rec, np.uint8)
+    B = rec.shape[0]
+    f = np.zeros((B, 12), np.float32)
+    sol = np.zeros((B, 12 * h))
+    info = np.zeros((B, 4), np.int32)
+    vp = ctypes.c_void_p
+    rc = L.emu_solve_batch_wrench(vp(rec.ctypes.data), B, h, m_cap, max_iter, vp(f.ctypes.data), vp(sol.ctypes.data),
+                                  vp(info.ctypes.data))
+    assert rc == 0, rc
+    return dict(forces=f, sol=sol, nv=info[:, 0], m=info[:, 1], iters=info[:, 2], status=info[:, 3])

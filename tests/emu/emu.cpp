@@ -111,6 +111,49 @@ int emu_solve_batch(const void* records, int batch, int h, int nv_cap, int m_cap
                 : emu_solve_batch_t<false>(records, batch, h, nv_cap, m_cap, max_iter, forces, solution, info, H_out, g_out);
 }
 
+// Wrench-space class (mpc_core.h): the same problems through H^{-1} = (I - G'MG)/(2 alpha), one emulated thread,
+// full storage of the 6h x 6h matrix, generic sweep for the two inversions.
+int emu_solve_batch_wrench(const void* records, int batch, int h, int m_cap, int max_iter, float* forces, double* solution,
+                           int* info) {
+  using namespace mpc;
+  const int nv_cap = 12 * h;
+  if (m_cap <= 0) m_cap = nv_cap;
+  const Layout L = make_layout(h, nv_cap, m_cap, 1, 0, 0, 0, 1);
+  std::vector<char> fast(L.fast_bytes + 64);
+  const size_t stride = ((size_t)(4 * (MPC_REC_TRAJ + 12 * h) + 4 * h) + 15) / 16 * 16;
+  OneThreadT<false, true> cx{0, 1};
+  const int NU = 12 * h;
+  for (int b = 0; b < batch; b++) {
+    memset(fast.data(), 0xCD, fast.size());
+    Work k = carve(L, fast.data(), nullptr);
+    const float* rec = (const float*)((const char*)records + stride * b);
+    const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * h);
+    k.i2a = 0.5 / (double)rec[MPC_REC_ALPHA];
+    assemble_front(cx, rec, gait, k);
+    if (k.sc->status == MPC_STATUS_OPTIMAL) {
+      assemble_K(cx, rec, k);
+      invert_spd(cx, k, 6 * h);
+      if (k.sc->status == MPC_STATUS_OPTIMAL) {
+        wr_form_second(cx, rec, k);
+        invert_spd(cx, k, 6 * h);
+      }
+      if (k.sc->status == MPC_STATUS_OPTIMAL) {
+        active_set_init(cx, rec, gait, k);
+        active_set(cx, rec, gait, k, max_iter);
+      }
+    }
+    int32_t st = 0;
+    scatter(cx, k, forces + 12 * b, solution ? solution + (size_t)NU * b : nullptr, &st);
+    if (info) {
+      info[4 * b + 0] = k.sc->nv;
+      info[4 * b + 1] = k.sc->m;
+      info[4 * b + 2] = k.sc->iters;
+      info[4 * b + 3] = k.sc->status;
+    }
+  }
+  return 0;
+}
+
 // Warm start: warm_cache [batch][kWarmStride] ints, read before and rewritten after every solve.
 int emu_solve_batch_warm(const void* records, int batch, int h, int nv_cap, int m_cap, int max_iter, float* forces,
                          double* solution, int* info, int* warm_cache, int warm_shift) {

@@ -218,3 +218,27 @@ def test_unpiped_layout_regions_are_inside_the_workspace():
         R, fb = _regions(10, 60, 33, 64, packed, 0, 0)
         for name, (lo, hi) in R.items():
             assert 0 <= lo <= hi <= fb, (name, lo, hi, fb)
+
+
+def test_wrench_space_class_matches_the_dense_route(oracle):
+    """The wrench-space class (H^{-1} = (I - G'MG)/(2 alpha), two inversions of size 6h instead of one of size nv;
+    host build of the same source the CUDA kernel runs) against the reference solver and the dense route:
+    same optimum for three- and four-stance problems at horizons 10, 16, 20, hard (many active rows) included."""
+    from quadruped_ctrl_b200 import records as R
+    from common import emu_solve_wrench
+    for name, h, B in (("four_stance", 10, 6), ("four_stance", 16, 4), ("config3", 20, 40)):
+        rec = W.four_stance(B, h, 3) if name == "four_stance" else W.config3(B, h, 7)
+        o = oracle.solve_batch(rec, h, 64)
+        wr = emu_solve_wrench(rec, h)
+        ok = o["rc"] == 0
+        assert (wr["status"] == 0).all()
+        assert rel(wr["sol"], o["sol"])[ok].max() < 1e-9
+    rec = W.four_stance(6, 20, 5)
+    rec.view(np.float32)[:, R.REC_FMAX] = 7.0       # most fz rows saturate: > 100 working-set changes
+    port = oracle.solve_batch(rec, 20, 64, "port")
+    wr = emu_solve_wrench(rec, 20)
+    assert (wr["status"] == 0).all() and wr["iters"].mean() > 100
+    assert rel(wr["sol"], port["sol"]).max() < 1e-8
+    # a working-set tile that is too small is reported for re-queueing, not silently truncated
+    wr = emu_solve_wrench(rec, 20, m_cap=16)
+    assert (wr["status"] == 0x40).all()
