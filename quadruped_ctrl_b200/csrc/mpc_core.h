@@ -67,6 +67,7 @@ struct Layout {
   int pipe;         // 1: two problems in flight per CTA (see make_layout): disjoint assembly / active-set regions
   int off_scal2, off_ints2, off_gi, off_mom;  // pipe: second per-problem set, active-set region, moment sums
   int off_wr;       // wrench-space class: its scratch vectors (0: none)
+  int t_in_slab;    // wrench-space overflow class: T lives in the global slab although Hm is in fast memory
   // byte offsets into `fast`
   int off_scal, off_g, off_x, off_ints, off_union, off_red, off_Hm, off_T;
   int fast_bytes;
@@ -133,7 +134,8 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
   int hm_doubles = packed ? hm_n * (hm_n + 1) / 2 : hm_n * L.ld;
   if (hm_doubles < 3 * 12 * h) hm_doubles = 3 * 12 * h;  // the assembly parks its moment sums there
   if (npad > 0 && hm_doubles < mma_panel_doubles(npad)) hm_doubles = mma_panel_doubles(npad);  // panel of the DMMA sweep
-  if (big_in_fast) gi += t_doubles;
+  const bool t_in_slab = wrench == 2;  // wrench-space overflow class: M in fast memory, the working-set matrix T in the slab
+  if (big_in_fast && !t_in_slab) gi += t_doubles;
   if (pipe) {
     o += 8 * un;                 // assembly scratch
     L.off_mom = o;
@@ -163,6 +165,11 @@ inline Layout make_layout(int h, int nv_cap, int m_cap, int big_in_fast, int npa
   L.slab_Hm = 0;
   L.slab_T = (size_t)hm_doubles * 8;
   L.slab_bytes = big_in_fast ? 0 : ((size_t)(hm_doubles + t_doubles) * 8 + 255) / 256 * 256;
+  if (t_in_slab) {
+    L.slab_T = 0;
+    L.slab_bytes = ((size_t)t_doubles * 8 + 255) / 256 * 256;
+  }
+  L.t_in_slab = t_in_slab ? 1 : 0;
   return L;
 }
 
@@ -211,7 +218,10 @@ MPC_HD Work carve(const Layout& L, char* fast, char* slab, int set = 0) {
   k.qe = k.xs + 39;
   k.psum = k.qe + 12 * L.h;
   double* gi = L.pipe ? (double*)(fast + L.off_gi) : un;
-  if (L.big_in_fast) {
+  if (L.big_in_fast && L.t_in_slab) {
+    k.T = (double*)(slab + L.slab_T);
+    k.Hm = (double*)(fast + L.off_Hm);
+  } else if (L.big_in_fast) {
     k.T = gi;
     gi += L.m_cap * L.ldT;
     k.Hm = (double*)(fast + L.off_Hm);
@@ -1557,6 +1567,45 @@ MPC_HD void wr_apply(const Cx& cx, const Work& k, const double* v, double* z) {
   cx.sync();
 }
 
+// z = H^{-1} n for ONE catalogue row n (the row being added): its wrench image lives in a single step block, so the
+// product with M touches six columns and needs no scratch vector for G v.
+template <class Cx>
+MPC_HD void wr_apply_row(const Cx& cx, const Work& k, const Row& rp, double* z) {
+  const int h = k.h, n = 6 * h, nv = k.sc->nv;
+  const int jp = rp.iz / 3, kp = k.stance[jp], sp = kp >> 2, lp = kp & 3;
+  double nl[3] = {0.0, 0.0, rp.cz};
+  if (rp.ca != 0.0) nl[rp.ia - 3 * jp] = rp.ca;
+  const double rx = k.rleg[3 * lp], ry = k.rleg[3 * lp + 1], rz = k.rleg[3 * lp + 2];
+  const double q[6] = {ry * nl[2] - rz * nl[1], rz * nl[0] - rx * nl[2], rx * nl[1] - ry * nl[0], nl[0], nl[1], nl[2]};
+  MPC_FOR(i, n) {
+    const int ti = Cx::kPacked ? i * (i + 1) / 2 : i * k.ld;
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      const int j = 6 * sp + c;
+      acc += k.Hm[(!Cx::kPacked || j <= i) ? ti + j : j * (j + 1) / 2 + i] * q[c];
+    }
+    k.wt[i] = acc;
+  }
+  cx.sync();
+  const double i2a = k.i2a;
+  MPC_FOR(i, nv) {
+    const int j = i / 3, c = i - 3 * j;
+    const int kk = k.stance[j], s = kk >> 2, l = kk & 3;
+    const double* t = k.wt + 6 * s;
+    const double ax = k.rleg[3 * l], ay = k.rleg[3 * l + 1], az = k.rleg[3 * l + 2];
+    double cr;
+    switch (c) {
+      case 0: cr = ay * t[2] - az * t[1]; break;
+      case 1: cr = az * t[0] - ax * t[2]; break;
+      default: cr = ax * t[1] - ay * t[0]; break;
+    }
+    const double vi = (j == jp) ? nl[c] : 0.0;
+    z[i] = i2a * (vi - (t[3 + c] - cr));
+  }
+  cx.sync();
+}
+
 // wv = sum of catalogue rows weighted by rcat (dense N c), for wr_apply.  rcat[6j + t] = coefficient of row t of pair j.
 template <class Cx>
 MPC_HD void wr_rows_to_dense(const Cx& cx, const Work& k, double mu_inv) {
@@ -1593,6 +1642,7 @@ MPC_HD void active_set_init(const Cx& cx, const float* rec, const unsigned char*
   if constexpr (Cx::kWrench) {  // x = -H^{-1} g through the rank structure
     wr_apply(cx, k, k.g, k.x);
     MPC_FOR(i, nv) k.x[i] = -k.x[i];
+    MPC_FOR(c, 6 * ns) k.rcat[c] = 0.0;  // per-row coefficients: all zero between uses
     cx.sync();
   }
   if (!Cx::kWrench && !have_x) MPC_FOR(i, nv) {  // four independent partial sums: the chain is latency-, not throughput-bound
@@ -1656,12 +1706,7 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
     cx.sync();
     MPC_ONE { sc->iters++; sc->up = 0.0; }
     cx.sync();
-    if constexpr (Cx::kWrench) {  // zp = H^{-1} n_p, kept in g (free once x0 exists) while p is being added
-      MPC_FOR(c, 6 * ns) k.rcat[c] = (c == p) ? 1.0 : 0.0;
-      cx.sync();
-      wr_rows_to_dense(cx, k, mu_inv);
-      wr_apply(cx, k, k.wv, k.g);
-    }
+    if constexpr (Cx::kWrench) wr_apply_row(cx, k, rp, k.g);  // zp = H^{-1} n_p, kept in g (free once x0 exists)
     // ---- inner loop: partial steps drop blocking rows until p can be added ----
     bool fail = false;
     for (;;) {
@@ -1714,12 +1759,13 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       // x += t * Minv (n_p - N r): every row touches <= 2 variables, so z is a combination of at most 2(m+1)
       // rows of Minv.  Applied in the (numerically) dependent case too: there z is only round-off-small, not
       // zero, and x and u must move with the same (r, t) for stationarity x = -Minv (g - N u) to survive.
-      if constexpr (Cx::kWrench) {  // z = H^{-1} (n_p - N r) through the rank structure
-        MPC_FOR(c, 6 * ns) k.rcat[c] = (c == p) ? 1.0 : 0.0;
-        cx.sync();
+      if constexpr (Cx::kWrench) {  // z = H^{-1} (n_p - N r) through the rank structure; rcat is all zero between uses
         MPC_FOR(a, m) k.rcat[k.W[a]] = -k.r[a];
+        MPC_ONE k.rcat[p] = 1.0;
         cx.sync();
         wr_rows_to_dense(cx, k, mu_inv);
+        MPC_FOR(a, m) k.rcat[k.W[a]] = 0.0;
+        MPC_ONE k.rcat[p] = 0.0;
         wr_apply(cx, k, k.wv, k.wz);
         MPC_FOR(i, nv) k.x[i] += t * k.wz[i];
       } else {
@@ -1838,11 +1884,10 @@ MPC_HD void active_set(const Cx& cx, const float* rec, const unsigned char* gait
       }
       cx.sync();
       if constexpr (Cx::kWrench) {
-        MPC_FOR(c, 6 * ns) k.rcat[c] = 0.0;
-        cx.sync();
         MPC_FOR(a, m) k.rcat[k.W[a]] = k.r[a];
         cx.sync();
         wr_rows_to_dense(cx, k, mu_inv);
+        MPC_FOR(a, m) k.rcat[k.W[a]] = 0.0;
         wr_apply(cx, k, k.wv, k.wz);
         MPC_FOR(i, nv) k.x[i] += k.wz[i];
       } else

@@ -461,7 +461,8 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
 // register-resident inversions of size 6h instead of one of size nv in an L2 slab, and the active set applies
 // H^{-1} = (I - G'MG) / (2 alpha) from shared memory.  One problem per CTA at a time, 256 threads.
 // SW as above: which register-resident inversion runs.
-template <int MINB, bool PROF, int SW>
+// UNR: unroll factor of the active set's loops over the working set (4 for the overflow class, whose T lives in L2).
+template <int MINB, bool PROF, int SW, int UNR = 1>
 __global__ void __launch_bounds__(256, MINB) mpc_solve_wrench_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) char smem[];
   const int count = P.count ? *P.count : P.batch;
@@ -470,8 +471,8 @@ __global__ void __launch_bounds__(256, MINB) mpc_solve_wrench_kernel(const __gri
   char* recbuf = smem + 16;
   char* fast = recbuf + 2 * P.stride;
   const int tid = (int)threadIdx.x;
-  const mpc::CtaT<true, 1, true> cx{tid, 256};
-  mpc::Work k = mpc::carve(P.L, fast, nullptr);
+  const mpc::CtaT<true, UNR, true> cx{tid, 256};
+  mpc::Work k = mpc::carve(P.L, fast, P.slab ? P.slab + (size_t)blockIdx.x * P.L.slab_bytes : nullptr);
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -583,6 +584,8 @@ struct mpc_batch {
   } s[kSlots];
   int* caps_dev = nullptr;
   std::vector<ClassCfg> classes;
+  ClassCfg dense_big;        // the dense catch-all configuration (last class, unless wrench-space classes replace it)
+  bool has_wrench = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // timing ring: event pairs around every class kernel of the last kRing solves (no sync while recording)
   std::vector<cudaEvent_t> ring0, ring1;
@@ -703,8 +706,9 @@ const int kVariantPad[V_COUNT] = {64, 96, 128, 0, 128};
 #ifndef MPC_MINBW  // wrench-space class: CTAs per SM it is compiled for
 #define MPC_MINBW 2
 #endif
-#define MPC_WRENCH_CALL(prof, sw, EXPR)                                                          \
+#define MPC_WRENCH_CALL(prof, sw, big, EXPR)                                                     \
   if (prof) { auto kern = mpc_solve_wrench_kernel<MPC_MINBW, true, 0>; EXPR; }                   \
+  else if (big) { auto kern = mpc_solve_wrench_kernel<MPC_MINBW, false, 0, 4>; EXPR; }           \
   else if (sw) { auto kern = mpc_solve_wrench_kernel<MPC_MINBW, false, 1>; EXPR; }               \
   else { auto kern = mpc_solve_wrench_kernel<MPC_MINBW, false, 0>; EXPR; }
 
@@ -718,7 +722,7 @@ int configure_kernel(mpc_batch* eng, ClassCfg& c) {
       if (prof && sw) continue;
       int o = 0;
       if (c.variant == V_WRENCH) {
-        MPC_WRENCH_CALL(prof, sw, {
+        MPC_WRENCH_CALL(prof, sw, !c.in_fast, {
           CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
           CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, c.threads, c.smem));
         });
@@ -835,6 +839,18 @@ int build_classes(mpc_batch* eng) {
       int rc = configure_kernel(eng, c);
       if (rc) return rc;
       eng->classes.push_back(c);
+      // ... and its own catch-all: the same kernel with a working set of any size, the working-set matrix T in a
+      // per-CTA global slab (L2 resident).  With it the dense catch-all below (a 12h x 12h inversion in L2) is
+      // not needed at this horizon at all.
+      ClassCfg o = c;
+      o.m_cap = nv_max;
+      o.in_fast = 0;
+      o.L = mpc::make_layout(h, nv_max, nv_max, 1, kVariantPad[V_WRENCH], 1, 0, 2);
+      o.smem = 16 + 2 * eng->stride + o.L.fast_bytes;
+      rc = configure_kernel(eng, o);
+      if (rc) return rc;
+      eng->classes.push_back(o);
+      eng->has_wrench = true;
     }
   }
   // catch-all: full-size problem and working set in a per-CTA global slab (L2 resident)
@@ -850,7 +866,8 @@ int build_classes(mpc_batch* eng) {
   if (rc) return rc;
   if (const char* e = getenv("MPC_BIG_CTAS")) big.grid = std::min(big.grid, atoi(e) * eng->sms); else
   big.grid = std::min(big.grid, 2 * eng->sms);  // two slabs per SM: more loads in flight, slabs still mostly L2-resident
-  eng->classes.push_back(big);
+  eng->dense_big = big;  // with wrench-space classes: only the assemble-only parity entry still uses it
+  if (!eng->has_wrench) eng->classes.push_back(big);
   if ((int)eng->classes.size() > kMaxClasses) {
     eng->err = "too many classes";
     return MPC_E_ARG;
@@ -892,7 +909,7 @@ int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int gr
     return MPC_OK;
   }
   if (c.variant == V_WRENCH) {
-    MPC_WRENCH_CALL(prof, eng->sweep, (kern<<<grid, c.threads, c.smem, st>>>(P)));
+    MPC_WRENCH_CALL(prof, eng->sweep, !c.in_fast, (kern<<<grid, c.threads, c.smem, st>>>(P)));
   } else {
     MPC_VARIANT_CALL(c.variant, prof, eng->sweep, (kern<<<grid, c.threads, c.smem, st>>>(P)));
   }
@@ -937,7 +954,7 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
   for (int ci = 0; ci < nc; ci++) {
     // the assemble-only parity entry writes the reduced QP itself out: the wrench-space class never forms it, so its
     // problems go through the catch-all kernel there
-    const ClassCfg& c = (H_out && eng->classes[ci].variant == V_WRENCH) ? eng->classes.back() : eng->classes[ci];
+    const ClassCfg& c = (H_out && eng->classes[ci].variant == V_WRENCH) ? eng->dense_big : eng->classes[ci];
     SolveParams P;
     fill_params(eng, slot, P, records, batch, forces, solution, status);
     P.list = S.lists + (size_t)ci * eng->max_batch;
@@ -984,7 +1001,10 @@ int ensure_slot(mpc_batch* eng, int q) {
     }                                                                                    \
   } while (0)
   const size_t B = (size_t)eng->max_batch, NU = 12 * (size_t)eng->h;
-  const ClassCfg& big = eng->classes.back();
+  // the slab serves the last class (dense catch-all or wrench-space overflow class) and the assemble-only entry
+  const ClassCfg& lastc = eng->classes.back();
+  const size_t slab_bytes = std::max(lastc.L.slab_bytes * (size_t)std::min<long long>(lastc.grid, eng->max_batch),
+                                     eng->dense_big.L.slab_bytes * (size_t)std::min<long long>(eng->dense_big.grid, eng->max_batch));
   cudaStream_t st = nullptr;
   CKS(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CKS(cudaMalloc(&S.rec_dev, B * eng->stride));
@@ -1004,7 +1024,7 @@ int ensure_slot(mpc_batch* eng, int q) {
   CKS(cudaMalloc(&S.lists, sizeof(int) * kMaxClasses * B));
   CKS(cudaMalloc(&S.counts, sizeof(int) * 2 * kMaxClasses));
   CKS(cudaMemset(S.counts, 0, sizeof(int) * 2 * kMaxClasses));
-  CKS(cudaMalloc(&S.slab, big.L.slab_bytes * (size_t)std::min<long long>(big.grid, eng->max_batch)));
+  CKS(cudaMalloc(&S.slab, slab_bytes));
   S.stream = st;  // last: marks the slot as complete
 #undef CKS
   return MPC_OK;
@@ -1212,6 +1232,11 @@ static int submit_host_impl(mpc_batch_t* eng, int slot, const void* records_host
   if (rc) return rc;
   if (S.out_bytes <= 8192) {  // small engine (the legacy single-robot one): one copy brings everything back
     CK(cudaMemcpyAsync(S.out_pin, S.out_dev, S.out_bytes, cudaMemcpyDeviceToHost, S.stream));
+    return MPC_OK;
+  }
+  if (batch == eng->max_batch && !want_solution) {  // forces | status are one contiguous block: one copy
+    const size_t bytes_out = (size_t)((char*)S.status_dev - S.out_dev) + (size_t)batch * sizeof(int32_t);
+    CK(cudaMemcpyAsync(S.out_pin, S.out_dev, bytes_out, cudaMemcpyDeviceToHost, S.stream));
     return MPC_OK;
   }
   CK(cudaMemcpyAsync(S.forces_pin, S.forces_dev, (size_t)batch * 12 * sizeof(float), cudaMemcpyDeviceToHost, S.stream));
