@@ -570,7 +570,7 @@ def run_ours(args):
     # i-2.  Every step's inputs come from pinned host memory and its forces + status are read back inside the timed
     # region; at N>1 the gather takes the slot's device forces (no second upload).
     pinned_sets = [torch.from_numpy(s).pin_memory() for s in host_sets[:min(8, n_sets)]]
-    nslots = E.SLOTS
+    nslots = max(2, min(args.e2e_slots, E.SLOTS))
     depth = nslots - 1
     out_f = [eng.host_buffers(q)[1] for q in range(nslots)]
     out_s = [eng.host_buffers(q)[3] for q in range(nslots)]
@@ -606,6 +606,35 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = (1.0 - e2e_bad[0] / float(B * args.steps)) * job * args.steps / float(t.item())
+    # ---- the same from TICK records (SURVEY 8f N1 + N2 on the host path): 272 bytes per robot cross the bus and the
+    #      problem records are built on the device.  Trot configs, N = 1 (synthetic trot ticks of the same shape). ----
+    e2e_ticks = None
+    if world == 1 and args.config in (2, 4):
+        tick_gen = W.config2_ticks if args.config == 2 else W.config4_ticks
+        tick_sets = [torch.from_numpy(tick_gen(B, h, cfg["seed"] + i)).pin_memory() for i in range(4)]
+        tick_bad = [0]
+
+        def ticks_run(n):
+            for i in range(n):
+                eng.submit_host_ticks(i % nslots, tick_sets[i % len(tick_sets)].numpy(), zero_copy=True)
+                if i >= depth:
+                    q = (i - depth) % nslots
+                    eng.wait_host(q)
+                    tick_bad[0] += int((out_s[q][:B] & 0xff != 0).sum())
+            for j in range(max(0, n - depth), n):
+                eng.wait_host(j % nslots)
+                tick_bad[0] += int((out_s[j % nslots][:B] & 0xff != 0).sum())
+            torch.cuda.synchronize()
+
+        ticks_run(max(args.warmup, 8))
+        tick_bad[0] = 0
+        t0 = time.perf_counter()
+        ticks_run(args.steps)
+        dt_ticks = time.perf_counter() - t0
+        e2e_ticks = {"value": (1.0 - tick_bad[0] / float(B * args.steps)) * B * args.steps / dt_ticks, "unit": UNIT,
+                     "h2d_bytes_per_step": B * 272, "d2h_bytes_per_step": B * 48 + B * 4 + B * 16,
+                     "api": "mpc_batch_submit_host_ticks / mpc_batch_wait_host: tick records in, problem records built "
+                            "on the device (workloads.config%d_ticks: the same seeded problems as tick records)" % args.config}
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -657,6 +686,8 @@ def run_ours(args):
         }
         if gather_ok is not None:
             line["gather_ok"] = gather_ok
+        if e2e_ticks is not None:
+            line["e2e_ticks"] = e2e_ticks
         if world == 1 and not args.no_cpu:
             v, info = cpu_reference_leg(host_sets[0][:4096], h, target_seconds=1.5 * (os.cpu_count() or 1))
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
@@ -678,6 +709,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the config's batch size")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight on the device-resident path (<= 3)")
+    ap.add_argument("--e2e-slots", type=int, default=6, help="scratch slots the end-to-end leg rotates over (<= 6)")
     ap.add_argument("--sweep", default=os.environ.get("MPC_SWEEP", "fma"), choices=["fma", "mma"],
                     help="inversion of the register-resident classes: FP64 FMA pipe or FP64 tensor pipe (DMMA)")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],

@@ -173,7 +173,7 @@ int mpc_batch_solve_device(mpc_batch_t* eng, const void* records_dev, int batch,
                            float* forces_dev, double* solution_dev,
                            int32_t* status_dev, void* cuda_stream);
 
-#define MPC_BATCH_SLOTS 3
+#define MPC_BATCH_SLOTS 6
 /* The same on scratch slot `slot` (0 .. MPC_BATCH_SLOTS-1).  Device-resident solves of one engine may overlap when they
  * use different slots and different streams: the tail of one batch then shares the GPU with the head of the
  * next (independent batches; nothing is exchanged between them). */
@@ -204,6 +204,22 @@ int mpc_batch_submit_host_pinned(mpc_batch_t* eng, int slot, const void* records
                                  int want_solution);
 int mpc_batch_wait_host(mpc_batch_t* eng, int slot, float* forces_host, double* solution_host,
                         int32_t* status_host);
+/* Both submit entries classify the batch on the host while they stage it: when every problem falls into one size
+ * class (one gait, one horizon -- the usual batch) the slot runs ONE kernel launch (no classify kernel, no index
+ * lists, no empty-class launches).  Mixed batches take the general path.  Results are identical either way. */
+
+/* The same from TICK records (layout above; SURVEY 8f N1 + N2): MPC_TICK_STRIDE = 272 bytes per robot cross the
+ * bus instead of the problem record (720 bytes at h = 10); the problem records are built on the device into the
+ * slot's own buffer.  zero_copy != 0: `ticks_host` is page-locked (checked) and stays untouched until
+ * mpc_batch_wait_host(slot); otherwise it is copied before the call returns.  Collect with mpc_batch_wait_host.
+ * mpc_batch_host_state: the slot's pinned [max_batch*4] fp32 controller state written back by the tick builder
+ * (world_position_desired x, y after the clamp, next x_comp_integral, 0 -- see mpc_batch_build_records_device),
+ * valid after wait_host, and the slot's own pinned tick buffer (filling it in place skips the staging copy). */
+int mpc_batch_submit_host_ticks(mpc_batch_t* eng, int slot, const void* ticks_host, int batch,
+                                int want_solution, int zero_copy);
+int mpc_batch_host_state(mpc_batch_t* eng, int slot, float** state_host, void** ticks_pinned);
+/* MPC_BATCH_SLOTS of the library that is loaded. */
+int mpc_batch_slots(void);
 
 /* Builds problem records from tick records on the device (one thread per robot), asynchronously on
  * `cuda_stream`.  records_dev [batch * mpc_record_stride(h)].  state_out_dev (optional, [batch*4] fp32)

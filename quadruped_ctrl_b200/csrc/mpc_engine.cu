@@ -34,6 +34,7 @@ constexpr int kMaxPeers = 8;
 constexpr int kSlots = MPC_BATCH_SLOTS;  // scratch slots per engine: that many batches can be in flight
 constexpr int kMaxClasses = 6;
 constexpr int kRing = 256;
+constexpr int kHostClassifyMax = 8192;  // largest batch the host entries classify themselves (see host_classify_records)
 
 #ifndef MPC_SWEEP_DEFAULT
 #define MPC_SWEEP_DEFAULT 0
@@ -580,7 +581,13 @@ struct mpc_batch {
     char* slab = nullptr;   // per-CTA global workspace of the catch-all class
     int pending_batch = 0;
     bool pending_solution = false;
-    int pending_single_class = -1;  // >= 0: the pending solve was host-classified (batch of one)
+    int pending_single_class = -1;  // >= 0: the pending solve was host-classified (every problem in that class)
+    // tick entry of the host path (allocated on first use): tick records in, controller state out
+    char* tick_dev = nullptr;
+    char* tick_pin = nullptr;
+    float* state_dev = nullptr;
+    float* state_pin = nullptr;
+    bool pending_state = false;
   } s[kSlots];
   int* caps_dev = nullptr;
   std::vector<ClassCfg> classes;
@@ -923,6 +930,97 @@ int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int gr
 // single-robot tick -- where launch overhead, not the solve, is most of the latency.  A working set that outgrows the
 // class's tile cannot be re-queued on this path; it comes back as MAX_ITER with few iterations and the host entry
 // repeats the solve on the general path.
+
+// Host-side classification (the host entries have the records in host memory): the size class every problem of the
+// batch falls into, or -1 when the batch is mixed (or host classification is off).  A uniform batch -- the usual case:
+// one gait, one horizon -- then needs no classify kernel, no index lists and no empty-class launches: ONE kernel
+// launch per batch.  The rule is mpc_classify_kernel's (the reference's near-zero test on gait * f_max,
+// SolverMPC.cpp:441-469); the scan stops at the first problem that disagrees.
+int class_of_nv(const mpc_batch* eng, int nv) {
+  int c = 0;
+  while (c < (int)eng->classes.size() - 1 && nv > eng->classes[c].nv_cap) c++;
+  return c;
+}
+// number of non-zero bytes among the first n bytes at p (eight at a time)
+inline int count_nonzero_bytes(const unsigned char* p, int n) {
+  int cnt = 0, q = 0;
+  for (; q + 8 <= n; q += 8) {
+    uint64_t x;
+    memcpy(&x, p + q, 8);
+    const uint64_t m = ((x & 0x7f7f7f7f7f7f7f7full) + 0x7f7f7f7f7f7f7f7full) | x;  // bit 7 of a byte set <=> byte != 0
+    cnt += __builtin_popcountll(m & 0x8080808080808080ull);
+  }
+  for (; q < n; q++) cnt += p[q] != 0;
+  return cnt;
+}
+inline bool near_zero_ub(float ub) { return (double)ub < 0.01 && (double)ub > -0.01; }
+int host_classify_records(const mpc_batch* eng, const void* records_host, int batch) {
+  if (eng->no_host_classify || eng->phase_clk || eng->debug_stop || eng->timed) return -1;  // (kernel timing is per class list)
+  // Worth it for small and medium batches only (a launch and a few microseconds of device time per batch saved); the
+  // scan itself is bound by host-memory latency -- two cache lines per record, prefetched a few records ahead
+  if (batch > kHostClassifyMax) return -1;
+  const size_t go = mpc_record_gait_offset(eng->h);
+  const int nb = 4 * eng->h;
+  int single = -1;
+  for (int b = 0; b < batch; b++) {
+    const char* base = (const char*)records_host + eng->stride * (size_t)b;
+    if (b + 12 < batch) {
+      const char* ahead = base + eng->stride * 12;
+      __builtin_prefetch(ahead + 4 * MPC_REC_FMAX);
+      __builtin_prefetch(ahead + go);
+      __builtin_prefetch(ahead + go + nb - 1);
+    }
+    const float fmax = ((const float*)base)[MPC_REC_FMAX];
+    const unsigned char* gait = (const unsigned char*)base + go;
+    int ns;
+    if (!near_zero_ub(1.0f * fmax) && fmax > 0.f) {
+      ns = count_nonzero_bytes(gait, nb);  // gait * f_max >= f_max for every non-zero table entry: all of them count
+    } else {  // tiny, negative or non-finite f_max: the test entry by entry, as the kernels do it
+      ns = 0;
+      for (int q = 0; q < nb; q++) ns += !near_zero_ub((float)gait[q] * fmax);
+    }
+    const int c = class_of_nv(eng, 3 * ns);
+    if (single < 0) single = c;
+    else if (c != single) return -1;
+  }
+  return single;
+}
+// The same from tick records: the contact table is a function of the gait definition (Gait.cpp:142-166, as in
+// build_record_from_tick).  With every offset inside [0, h) the h table rows run through every phase of the cycle
+// exactly once, so leg j is in stance in min(duration_j, h) of them whatever the iteration is.
+int host_classify_ticks(const mpc_batch* eng, const void* ticks_host, int batch) {
+  if (eng->no_host_classify || eng->phase_clk || eng->debug_stop || eng->timed) return -1;
+  if (batch > kHostClassifyMax) return -1;
+  const int h = eng->h;
+  int single = -1;
+  for (int b = 0; b < batch; b++) {
+    const float* tick = (const float*)ticks_host + (size_t)MPC_TICK_WORDS * b;
+    const int32_t* ti = (const int32_t*)tick;
+    int ns = 0;
+    if (!near_zero_ub(1.0f * tick[MPC_TICK_FMAX])) {
+      bool regular = ti[MPC_TICK_ITERATION] >= 0;  // (a negative iteration breaks the modulo of the table rows)
+      for (int j = 0; j < 4; j++) regular = regular && ti[MPC_TICK_OFFSETS + j] >= 0 && ti[MPC_TICK_OFFSETS + j] < h;
+      if (regular) {
+        for (int j = 0; j < 4; j++) ns += std::min(std::max(ti[MPC_TICK_DURATIONS + j], 0), h);
+      } else {
+        const int it0 = ti[MPC_TICK_ITERATION];
+        for (int i = 0; i < h; i++) {
+          const int iter = (i + it0 + 1) % h;
+          for (int j = 0; j < 4; j++) {
+            int progress = iter - ti[MPC_TICK_OFFSETS + j];
+            if (progress < 0) progress += h;
+            ns += progress < ti[MPC_TICK_DURATIONS + j];
+          }
+        }
+      }
+    }
+    const int c = class_of_nv(eng, 3 * ns);
+    if (single < 0) single = c;
+    else if (c != single) return -1;
+  }
+  return single;
+}
+
 int ensure_slot(mpc_batch* eng, int q);
 
 int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, float* forces, double* solution,
@@ -939,7 +1037,10 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
     P.L = c.L;
     P.warp_mode = c.variant == V_64 ? 1 : 0;
     P.slab = c.in_fast ? nullptr : S.slab;
-    return launch_solve(eng, c, P, std::min(c.grid, batch), st);  // (the wrench class: a tile overflow comes back as MAX_ITER)
+    const bool piped = c.pipe && !eng->phase_clk && !eng->debug_stop;
+    int grid = std::min(piped ? c.pipe_grid : c.grid, batch);
+    if (eng->ctas_per_sm_limit > 0) grid = std::min(grid, eng->ctas_per_sm_limit * eng->sms);
+    return launch_solve(eng, c, P, grid, st);  // a working-set tile overflow comes back as MAX_ITER (see wait_host)
   }
   // class counters are double-buffered by solve parity: this solve's classify kernel zeroes the other set
   int* counts = S.counts + (S.parity ? kMaxClasses : 0);
@@ -1122,6 +1223,10 @@ void mpc_batch_destroy(mpc_batch_t* eng) {
     cudaFree(S.out_dev);
     cudaFreeHost(S.rec_pin);
     cudaFreeHost(S.out_pin);
+    cudaFree(S.tick_dev);
+    cudaFreeHost(S.tick_pin);
+    cudaFree(S.state_dev);
+    cudaFreeHost(S.state_pin);
     cudaFree(S.lists);
     cudaFree(S.counts);
     cudaFree(S.slab);
@@ -1195,6 +1300,7 @@ static int submit_host_impl(mpc_batch_t* eng, int slot, const void* records_host
   mpc_batch::Slot& S = eng->s[slot];
   S.pending_batch = batch;
   S.pending_solution = want_solution != 0;
+  S.pending_state = false;
   if (batch == 0) return MPC_OK;
   const size_t NU = 12 * (size_t)eng->h;
   // The records are COPIED before this call returns (staged into the slot's pinned buffer chunk by chunk, chunk c's
@@ -1213,19 +1319,7 @@ static int submit_host_impl(mpc_batch_t* eng, int slot, const void* records_host
       CK(cudaMemcpyAsync(S.rec_dev + off, S.rec_pin + off, n, cudaMemcpyHostToDevice, S.stream));
     }
   }
-  int single = -1;
-  if (batch == 1 && !eng->no_host_classify && !eng->phase_clk && !eng->debug_stop) {
-    // the reference's near-zero test on gait * f_max (SolverMPC.cpp:441-469), as in mpc_classify_kernel
-    const float* rec = (const float*)records_host;
-    const unsigned char* gait = (const unsigned char*)records_host + mpc_record_gait_offset(eng->h);
-    int ns = 0;
-    for (int q = 0; q < 4 * eng->h; q++) {
-      const float ub = (float)gait[q] * rec[MPC_REC_FMAX];
-      ns += !((double)ub < 0.01 && (double)ub > -0.01);
-    }
-    single = 0;
-    while (single < (int)eng->classes.size() - 1 && 3 * ns > eng->classes[single].nv_cap) single++;
-  }
+  const int single = host_classify_records(eng, records_host, batch);  // uniform batch: one launch, no classify kernel
   S.pending_single_class = single;
   int rc = solve_on_stream(eng, slot, S.rec_dev, batch, S.forces_dev, want_solution ? S.sol_dev : nullptr, S.status_dev,
                            S.stream, nullptr, nullptr, nullptr, single);
@@ -1262,18 +1356,24 @@ int mpc_batch_wait_host(mpc_batch_t* eng, int slot, float* forces_host, double* 
   ON_DEVICE(eng);
   CK(cudaStreamSynchronize(S.stream));
   const size_t NU = 12 * (size_t)eng->h;
-  if (S.pending_single_class >= 0 && S.pending_single_class < (int)eng->classes.size() - 1 && batch == 1 &&
-      (S.status_pin[0] & 0xff) == MPC_STATUS_MAX_ITER && (S.status_pin[0] >> 8) < eng->max_iter) {
-    // host-classified solve whose working set outgrew its class's tile: once more on the general path (re-queue)
-    S.pending_single_class = -1;
-    int rc = solve_on_stream(eng, slot, S.rec_dev, 1, S.forces_dev, S.pending_solution ? S.sol_dev : nullptr,
-                             S.status_dev, S.stream, nullptr, nullptr, nullptr);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(S.forces_pin, S.forces_dev, 12 * sizeof(float), cudaMemcpyDeviceToHost, S.stream));
-    if (S.pending_solution)
-      CK(cudaMemcpyAsync(S.sol_pin, S.sol_dev, NU * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
-    CK(cudaMemcpyAsync(S.status_pin, S.status_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, S.stream));
-    CK(cudaStreamSynchronize(S.stream));
+  if (S.pending_single_class >= 0 && S.pending_single_class < (int)eng->classes.size() - 1) {
+    // host-classified solve: a problem whose working set outgrew its class's tile could not be re-queued on that path
+    // and came back as MAX_ITER short of the iteration cap -- the batch goes through the general path once more
+    // (never on the BASELINE workloads; the tiles hold 17..27 rows)
+    bool overflow = false;
+    for (int b = 0; b < batch && !overflow; b++)
+      overflow = (S.status_pin[b] & 0xff) == MPC_STATUS_MAX_ITER && (S.status_pin[b] >> 8) < eng->max_iter;
+    if (overflow) {
+      S.pending_single_class = -1;
+      int rc = solve_on_stream(eng, slot, S.rec_dev, batch, S.forces_dev, S.pending_solution ? S.sol_dev : nullptr,
+                               S.status_dev, S.stream, nullptr, nullptr, nullptr);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(S.forces_pin, S.forces_dev, (size_t)batch * 12 * sizeof(float), cudaMemcpyDeviceToHost, S.stream));
+      if (S.pending_solution)
+        CK(cudaMemcpyAsync(S.sol_pin, S.sol_dev, (size_t)batch * NU * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+      CK(cudaMemcpyAsync(S.status_pin, S.status_dev, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, S.stream));
+      CK(cudaStreamSynchronize(S.stream));
+    }
   }
   if (forces_host && forces_host != S.forces_pin) memcpy(forces_host, S.forces_pin, (size_t)batch * 12 * sizeof(float));
   if (solution_host && solution_host != S.sol_pin)
@@ -1282,6 +1382,89 @@ int mpc_batch_wait_host(mpc_batch_t* eng, int slot, float* forces_host, double* 
   S.pending_batch = 0;
   return MPC_OK;
 }
+
+// Host entry from TICK records (SURVEY 8f N1 + N2 on the host path): 272 bytes per robot cross the bus instead of the
+// 720-byte problem record (h = 10); the records are built on the device (mpc_build_records_kernel) into the slot's
+// own buffer and never exist in host memory.  The controller state the reference writes back at this point
+// (world_position_desired after the clamp, next x_comp_integral) comes back with the forces: mpc_batch_host_state.
+int mpc_batch_submit_host_ticks(mpc_batch_t* eng, int slot, const void* ticks_host, int batch, int want_solution,
+                                int zero_copy) {
+  if (!eng) return MPC_E_ARG;
+  if (slot < 0 || slot >= kSlots || !ticks_host || batch < 0 || batch > eng->max_batch) {
+    eng->err = "mpc_batch_submit_host_ticks: bad argument";
+    return MPC_E_ARG;
+  }
+  if (zero_copy) {
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, ticks_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) {
+      cudaGetLastError();
+      eng->err = "mpc_batch_submit_host_ticks: zero_copy asks for page-locked tick records";
+      return MPC_E_ARG;
+    }
+  }
+  ON_DEVICE(eng);
+  if (int rc = ensure_slot(eng, slot)) return rc;
+  mpc_batch::Slot& S = eng->s[slot];
+  if (!S.tick_dev) {
+    const size_t B = (size_t)eng->max_batch;
+    CK(cudaMalloc(&S.tick_dev, B * MPC_TICK_STRIDE));
+    CK(cudaMallocHost(&S.tick_pin, B * MPC_TICK_STRIDE));
+    CK(cudaMalloc(&S.state_dev, B * 4 * sizeof(float)));
+    CK(cudaMallocHost(&S.state_pin, B * 4 * sizeof(float)));
+  }
+  S.pending_batch = batch;
+  S.pending_solution = want_solution != 0;
+  S.pending_state = true;
+  if (batch == 0) return MPC_OK;
+  const size_t bytes = (size_t)batch * MPC_TICK_STRIDE;
+  const void* src = ticks_host;
+  if (!zero_copy && ticks_host != (const void*)S.tick_pin) {
+    memcpy(S.tick_pin, ticks_host, bytes);  // the caller may reuse its buffer at once
+    src = S.tick_pin;
+  }
+  CK(cudaMemcpyAsync(S.tick_dev, src, bytes, cudaMemcpyHostToDevice, S.stream));
+  mpc_build_records_kernel<<<(batch + 127) / 128, 128, 0, S.stream>>>((const float*)S.tick_dev, batch, eng->h, S.rec_dev,
+                                                                     eng->stride, S.state_dev);
+  eng->launches++;
+  CK(cudaGetLastError());
+  const int single = host_classify_ticks(eng, ticks_host, batch);
+  S.pending_single_class = single;
+  int rc = solve_on_stream(eng, slot, S.rec_dev, batch, S.forces_dev, want_solution ? S.sol_dev : nullptr, S.status_dev,
+                           S.stream, nullptr, nullptr, nullptr, single);
+  if (rc) return rc;
+  const size_t NU = 12 * (size_t)eng->h;
+  if (batch == eng->max_batch && !want_solution) {  // forces | status are one contiguous block: one copy
+    const size_t bytes_out = (size_t)((char*)S.status_dev - S.out_dev) + (size_t)batch * sizeof(int32_t);
+    CK(cudaMemcpyAsync(S.out_pin, S.out_dev, bytes_out, cudaMemcpyDeviceToHost, S.stream));
+  } else {
+    CK(cudaMemcpyAsync(S.forces_pin, S.forces_dev, (size_t)batch * 12 * sizeof(float), cudaMemcpyDeviceToHost, S.stream));
+    if (want_solution)
+      CK(cudaMemcpyAsync(S.sol_pin, S.sol_dev, (size_t)batch * NU * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaMemcpyAsync(S.status_pin, S.status_dev, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, S.stream));
+  }
+  CK(cudaMemcpyAsync(S.state_pin, S.state_dev, (size_t)batch * 4 * sizeof(float), cudaMemcpyDeviceToHost, S.stream));
+  return MPC_OK;
+}
+
+int mpc_batch_host_state(mpc_batch_t* eng, int slot, float** state_host, void** ticks_pinned) {
+  if (!eng || slot < 0 || slot >= kSlots) return MPC_E_ARG;
+  mpc_batch::Slot& S = eng->s[slot];
+  if (!S.tick_dev) {  // allocate the tick-side buffers so that a caller can fill the slot's own pinned tick buffer
+    ON_DEVICE(eng);
+    if (int rc = ensure_slot(eng, slot)) return rc;
+    const size_t B = (size_t)eng->max_batch;
+    CK(cudaMalloc(&S.tick_dev, B * MPC_TICK_STRIDE));
+    CK(cudaMallocHost(&S.tick_pin, B * MPC_TICK_STRIDE));
+    CK(cudaMalloc(&S.state_dev, B * 4 * sizeof(float)));
+    CK(cudaMallocHost(&S.state_pin, B * 4 * sizeof(float)));
+  }
+  if (state_host) *state_host = S.state_pin;
+  if (ticks_pinned) *ticks_pinned = S.tick_pin;
+  return MPC_OK;
+}
+
+int mpc_batch_slots(void) { return kSlots; }
 
 int mpc_batch_solve_host(mpc_batch_t* eng, const void* records_host, int batch, float* forces_host,
                          double* solution_host, int32_t* status_host) {

@@ -19,12 +19,13 @@ LIB_PATH = os.environ.get("MPC_LIB_PATH") or os.path.join(_HERE, "libquadruped_m
 _LIB = None
 
 MPC_OK, MPC_E_ARG, MPC_E_CUDA, MPC_E_NOMEM, MPC_E_NODEVICE = 0, -1, -2, -3, -4
-SLOTS = 3  # MPC_BATCH_SLOTS of include/mpc_batch.h: scratch slots per engine (batches that can be in flight)
+SLOTS = 6  # MPC_BATCH_SLOTS of include/mpc_batch.h: scratch slots per engine (batches that can be in flight)
 STATUS_OPTIMAL, STATUS_MAX_ITER, STATUS_BAD_INPUT, STATUS_NOT_PD, STATUS_NO_STANCE = 0, 1, 2, 3, 4
 
 # every symbol include/mpc_batch.h and include/convexMPC_interface.h declare
 BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_create", "mpc_batch_destroy",
                  "mpc_batch_solve_device", "mpc_batch_solve_device_slot", "mpc_batch_solve_host", "mpc_batch_submit_host", "mpc_batch_submit_host_pinned", "mpc_batch_wait_host",
+                 "mpc_batch_submit_host_ticks", "mpc_batch_host_state", "mpc_batch_slots",
                  "mpc_batch_assemble_device", "mpc_batch_build_records_device", "mpc_batch_solve_ticks_device",
                  "mpc_batch_gait_state_device", "mpc_batch_leg_commands_device",
                  "mpc_batch_set_gather_peers", "mpc_batch_gather_alloc", "mpc_batch_gather_connect",
@@ -80,6 +81,10 @@ def lib():
     L.mpc_batch_submit_host.argtypes = [vp, i32, vp, i32, i32]
     L.mpc_batch_submit_host_pinned.argtypes = [vp, i32, vp, i32, i32]
     L.mpc_batch_wait_host.argtypes = [vp, i32, vp, vp, vp]
+    L.mpc_batch_submit_host_ticks.argtypes = [vp, i32, vp, i32, i32, i32]
+    L.mpc_batch_host_state.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    if L.mpc_batch_slots() != SLOTS:
+        raise MpcError("engine.SLOTS (%d) does not match the library's MPC_BATCH_SLOTS (%d)" % (SLOTS, L.mpc_batch_slots()))
     L.mpc_batch_assemble_device.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.mpc_batch_build_records_device.argtypes = [vp, vp, i32, vp, vp, vp]
     L.mpc_batch_solve_ticks_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
@@ -369,6 +374,29 @@ class MpcBatch:
         fn = self._L.mpc_batch_submit_host_pinned if zero_copy else self._L.mpc_batch_submit_host
         rc = fn(self._h, int(slot), records.ctypes.data, records.shape[0], int(bool(want_solution)))
         self._check(rc, "mpc_batch_submit_host")
+
+    def submit_host_ticks(self, slot, ticks, want_solution=False, zero_copy=False):
+        """The host entry from tick records (numpy [B, 68] of 32-bit words, ticks.pack_ticks): 272 bytes per robot
+        cross the bus, the problem records are built on the device.  Collect with wait_host(slot); the controller
+        state written back by the builder is host_state(slot)[:B] afterwards."""
+        ticks = np.ascontiguousarray(ticks)
+        assert ticks.itemsize * ticks.shape[1] == 272
+        rc = self._L.mpc_batch_submit_host_ticks(self._h, int(slot), ticks.ctypes.data, ticks.shape[0],
+                                                 int(bool(want_solution)), int(bool(zero_copy)))
+        self._check(rc, "mpc_batch_submit_host_ticks")
+
+    def host_state(self, slot=0):
+        """(state [max_batch, 4] f32, ticks [max_batch, 68] f32): the slot's pinned controller-state output of the tick
+        entry and its own pinned tick buffer."""
+        ps, pt = ctypes.c_void_p(), ctypes.c_void_p()
+        self._check(self._L.mpc_batch_host_state(self._h, int(slot), ctypes.byref(ps), ctypes.byref(pt)), "host_state")
+        B = self.max_batch
+
+        def view(p, nbytes, shape):
+            buf = (ctypes.c_char * nbytes).from_address(p.value)
+            return np.frombuffer(buf, dtype=np.float32).reshape(shape)
+
+        return view(ps, B * 16, (B, 4)), view(pt, B * 272, (B, 68))
 
     def wait_host(self, slot, out_forces=None, out_solution=None, out_status=None):
         """Waits for slot `slot` and copies its results into the given numpy arrays (None: left in the slot's

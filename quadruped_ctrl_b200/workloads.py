@@ -182,6 +182,31 @@ def four_stance(batch=256, horizon=10, seed=777):
     return _pack(h, roll, pitch, yaw, p, v, w, feet, traj, gait)
 
 
+def _trot_ticks(batch, horizon, seed, stairs):
+    """config2 / config4 as TICK records (include/mpc_batch.h): the same seeded states, footholds, command and gait
+    phase, with the feet given in the WORLD frame -- the records the engine builds from them on the device equal
+    config2(...) / config4(...) up to the fp32 rounding of (foot + p) - p, gait tables byte for byte."""
+    from . import ticks as T
+    rng = np.random.default_rng(seed)
+    h = horizon
+    roll, pitch, yaw, p, v, w, feet, v_nom = _states(rng, batch)
+    if stairs:
+        feet[:, :, 2] += rng.choice(np.array([0.0, 0.02, 0.04, 0.06, 0.08]), (batch, 4))
+        feet[:, :, 0] += rng.uniform(-0.05, 0.05, (batch, 4))
+    phase = rng.integers(0, h, batch)
+    q = rpy_to_quat(roll, pitch, yaw)
+    return T.pack_ticks(p, v, q, w, feet + p[:, None, :], yaw, p[:, :2], yaw, np.zeros(batch), v_nom[:, :2],
+                        (0, h // 2, h // 2, 0), (h // 2,) * 4, phase, body_height=BODY_HEIGHT)
+
+
+def config2_ticks(batch=4096, horizon=10, seed=1234):
+    return _trot_ticks(batch, horizon, seed, False)
+
+
+def config4_ticks(batch=65536, horizon=10, seed=3456):
+    return _trot_ticks(batch, horizon, seed, True)
+
+
 CONFIGS = {"config1": config1, "config2": config2, "config3": config3, "config4": config4, "config5": config5,
            "four_stance": four_stance}
 HORIZONS = {"config1": 10, "config2": 10, "config3": 20, "config4": 10, "config5": 16, "four_stance": 10}

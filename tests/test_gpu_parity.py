@@ -475,6 +475,60 @@ def test_host_entry_copies_before_returning_unless_zero_copy_is_requested(cuda_e
     assert (E.status_code(st1) == E.STATUS_OPTIMAL).all()
 
 
+def test_uniform_host_batch_is_one_launch_and_identical(cuda_engine_factory):
+    """The host entries classify the batch while they stage it: a uniform batch (one size class) runs ONE kernel
+    launch -- no classify kernel, no empty-class launches -- and gives the bytes of the general path; a mixed batch
+    takes the general path (classify + one launch per class)."""
+    h, B = 10, 1024
+    eng = cuda_engine_factory(h, B)
+    nc = len(eng.classes())
+    rec = W.config2(B, h, 777)
+    fd, sd, std = eng.solve_device(torch.from_numpy(rec).cuda(), want_solution=True)   # general path
+    torch.cuda.synchronize()
+    l0 = eng.kernel_launches()
+    f1, s1, st1 = eng.solve_host(rec, want_solution=True)
+    assert eng.kernel_launches() - l0 == 1
+    assert np.array_equal(f1, fd.cpu().numpy()) and np.array_equal(s1, sd.cpu().numpy())
+    assert np.array_equal(st1, std.cpu().numpy())
+    mixed = np.concatenate([W.config2(B // 2, h, 778), W.CONFIGS["four_stance"](B // 2, seed=779)])
+    fd, sd, std = eng.solve_device(torch.from_numpy(mixed).cuda(), want_solution=True)
+    torch.cuda.synchronize()
+    l0 = eng.kernel_launches()
+    f2, s2, st2 = eng.solve_host(mixed, want_solution=True)
+    assert eng.kernel_launches() - l0 == 1 + nc
+    assert np.array_equal(f2, fd.cpu().numpy()) and np.array_equal(s2, sd.cpu().numpy())
+    assert (E.status_code(st1) == E.STATUS_OPTIMAL).all() and (E.status_code(st2) == E.STATUS_OPTIMAL).all()
+
+
+def test_host_tick_entry_matches_device_tick_entry(oracle, cuda_engine_factory):
+    """mpc_batch_submit_host_ticks: 272-byte tick records from host memory (staged or zero-copy), records built on the
+    device -- the forces, solution, status and the controller state written back equal the device tick entry's and the
+    oracle's record builder, bit for bit; uniform batches are two launches (builder + one solve kernel)."""
+    from quadruped_ctrl_b200 import ticks as T
+    for h, mixed, B in ((10, False, 1000), (16, True, 300)):
+        tk = T.synth_ticks(B, h, 21 + h, mixed_gaits=mixed)
+        _, st_o = oracle.build_records(tk, h)
+        eng = cuda_engine_factory(h, B)
+        f1, s1, c1, st1 = eng.solve_ticks_device(torch.from_numpy(tk).cuda(), want_solution=True)
+        torch.cuda.synchronize()
+        pinned = torch.from_numpy(tk.copy()).pin_memory()
+        for slot, zero_copy, src in ((0, False, tk), (E.SLOTS - 1, True, pinned.numpy())):
+            l0 = eng.kernel_launches()
+            eng.submit_host_ticks(slot, src, want_solution=True, zero_copy=zero_copy)
+            f = np.empty((B, 12), np.float32)
+            s = np.empty((B, 12 * h), np.float64)
+            c = np.empty(B, np.int32)
+            eng.wait_host(slot, f, s, c)
+            if not mixed:
+                assert eng.kernel_launches() - l0 == 2
+            assert np.array_equal(f, f1.cpu().numpy()) and np.array_equal(s, s1.cpu().numpy())
+            assert np.array_equal(c, c1.cpu().numpy())
+            assert np.array_equal(eng.host_state(slot)[0][:B], st_o)
+        with pytest.raises(E.MpcError):
+            eng.submit_host_ticks(0, tk, zero_copy=True)   # pageable memory cannot be read in place
+        assert (E.status_code(c1.cpu().numpy()) == E.STATUS_OPTIMAL).all()
+
+
 def test_device_record_builder_is_byte_exact(oracle, cuda_engine_factory):
     """SURVEY 8f N1 + N2: records built on the device from tick records equal the oracle's restatement of the
     reference's host code (ConvexMPCLocomotion.cpp:498-640, Gait.cpp:142-166) byte for byte, and solving the

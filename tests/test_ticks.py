@@ -97,3 +97,21 @@ def test_x_drag_integrator_threshold_is_the_reference_double_compare(oracle):
     assert np.array_equal(rec_o, rec_e) and np.array_equal(st_o, st_e)
     moved = st_o[:, 2] != np.float32(0.125)
     assert moved.tolist() == [True, True, False, False, True, False, True, True]
+
+
+def test_trot_tick_workloads_rebuild_the_record_workloads():
+    """workloads.config2_ticks / config4_ticks (the bench's e2e_ticks leg) describe the problems of config2 / config4:
+    records built from them (oracle restatement of the reference's host code) equal the packed records up to the fp32
+    rounding of the COM-relative feet, the gait tables byte for byte."""
+    from quadruped_ctrl_b200 import records as R
+    from quadruped_ctrl_b200 import workloads as W
+    from oracle import oracle as O
+    h = 10
+    for ticks_fn, rec_fn, seed in ((W.config2_ticks, W.config2, 1234), (W.config4_ticks, W.config4, 3456)):
+        rec_t, _ = O.build_records(ticks_fn(256, h, seed), h)
+        rec = rec_fn(256, h, seed)
+        go = R.gait_offset(h) if hasattr(R, "gait_offset") else 4 * (48 + 12 * h)
+        assert np.array_equal(rec_t[:, go:go + 4 * h], rec[:, go:go + 4 * h])
+        a = rec_t[:, :go].copy().view(np.float32)
+        b = rec[:, :go].copy().view(np.float32)
+        assert np.abs(a - b).max() < 1e-6

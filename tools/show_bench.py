@@ -17,6 +17,8 @@ for path in sys.argv[1:]:
         print("   value %.3f M/s  serial %s  e2e %.3f M/s  ms/step %.3f  n_gpus %d  launches %s  ok %s gather %s" % (
             d["value"] / 1e6, "%.3f" % (d["serial"]["value"] / 1e6) if "serial" in d else "-", d["e2e"]["value"] / 1e6,
             d["ms_per_step"], d["n_gpus"], d.get("gpu_launches"), d.get("results_ok"), d.get("gather_ok")))
+        if "e2e_ticks" in d:
+            print("   e2e from tick records %.3f M/s (%d B/robot up)" % (d["e2e_ticks"]["value"] / 1e6, 272))
         if r:
             print("   kernel: %s  %.3f ms  frac %.2e  classes alone %s  per class %s" % (
                 r.get("kernel"), r.get("kernel_ms", 0), r.get("frac", 0),
