@@ -296,6 +296,17 @@ int mpc_batch_gather_sync_slot(mpc_batch_t* eng, int slot, void* cuda_stream);
 int mpc_batch_set_sweep_variant(mpc_batch_t* eng, int variant);
 int mpc_batch_sweep_variant(const mpc_batch_t* eng);
 
+/* Solver of the size classes with nv <= 128 (selectable per engine, any time):
+ *   0  explicit inverse of the reduced condensed Hessian (symmetric sweep in registers) + dual active set on it
+ *   1  Riccati sweeps (default): the condensed Hessian is never formed; the gains of the horizon's Riccati recursion
+ *      are factored once per problem and every H^{-1} product of the dual active-set method is one backward and one
+ *      forward sweep over the horizon (csrc/mpc_riccati.h), one warp per problem
+ * Both end at the same KKT point (1e-9 against the reference solver on the fp64-assembled QP is asserted for
+ * either; they differ in the last bits).  The warm start, the phase-clock and the assemble-only entries always use
+ * solver 0.  Environment MPC_SOLVER=riccati|inverse sets the default of new engines. */
+int mpc_batch_set_solver(mpc_batch_t* eng, int solver);
+int mpc_batch_solver(const mpc_batch_t* eng);
+
 /* Warm start across MPC ticks (the reference cold-starts every solve, SolverMPC.cpp:529).
  * cache_dev: device memory, [robots][mpc_batch_warm_stride()] int32, zero-initialised by the caller once; the engine
  * reads a robot's entry before its solve and rewrites it afterwards (the optimal working set as (step, leg, row)

@@ -27,6 +27,7 @@
 #include "mpc_core.h"
 #include "mpc_ticks.h"
 #include "mpc_legs.h"
+#include "mpc_riccati.h"
 
 namespace {
 
@@ -38,6 +39,9 @@ constexpr int kHostClassifyMax = 8192;  // largest batch the host entries classi
 
 #ifndef MPC_SWEEP_DEFAULT
 #define MPC_SWEEP_DEFAULT 0
+#endif
+#ifndef MPC_SOLVER_DEFAULT
+#define MPC_SOLVER_DEFAULT 1
 #endif
 
 struct SolveParams {
@@ -53,6 +57,7 @@ struct SolveParams {
   int* retry_count;
   char* slab;
   mpc::Layout L;
+  mpc::RicLayout RL;  // workspace of the Riccati solver (mpc_solve_riccati_kernel)
   int max_iter;
   int warp_mode;
   float* peers[kMaxPeers];
@@ -541,6 +546,67 @@ __global__ void __launch_bounds__(256, MINB) mpc_solve_wrench_kernel(const __gri
   }
 }
 
+// ---- Riccati solver (csrc/mpc_riccati.h): ONE WARP PER PROBLEM ------------------------------------------------
+// No condensed Hessian and no inversion: the gains of the horizon's Riccati recursion are factored once and every
+// H^{-1} product the dual active-set method asks for is a backward + forward sweep over the horizon.  A CTA is one
+// warp (__syncwarp only); the persistent grid keeps as many warps per SM as the per-problem workspace allows.  Records
+// are staged by TMA bulk copies, double buffered, exactly as in mpc_solve_kernel.
+__global__ void __launch_bounds__(32) mpc_solve_riccati_kernel(const __grid_constant__ SolveParams P) {
+  extern __shared__ __align__(128) char smem[];
+  const int count = P.count ? *P.count : P.batch;
+  if ((int)blockIdx.x >= count) return;
+  uint64_t* bar = (uint64_t*)smem;
+  char* recbuf = smem + 16;
+  char* fast = recbuf + 2 * P.stride;
+  const int lane = (int)threadIdx.x;
+  const mpc::WarpT<false> cx{lane, 32};
+  const mpc::RicWork k = mpc::ric_carve(P.RL, fast);
+  if (lane == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint32_t rec_bytes = (uint32_t)P.stride;
+  int item = blockIdx.x;
+  if (lane == 0) {
+    const int b0 = P.list ? P.list[item] : item;
+    mbar_expect_tx(&bar[0], rec_bytes);
+    tma_bulk_g2s(recbuf, P.records + P.stride * b0, rec_bytes, &bar[0]);
+  }
+  for (int it = 0; item < count; item += gridDim.x, it++) {
+    const int cur = it & 1;
+    const int next = item + gridDim.x;
+    if (lane == 0 && next < count) {  // buffer cur^1 was released by the __syncwarp that ended the last pass
+      const int bn = P.list ? P.list[next] : next;
+      mbar_expect_tx(&bar[cur ^ 1], rec_bytes);
+      tma_bulk_g2s(recbuf + (size_t)(cur ^ 1) * P.stride, P.records + P.stride * bn, rec_bytes, &bar[cur ^ 1]);
+    }
+    mbar_wait(&bar[cur], (uint32_t)((it >> 1) & 1));
+    const int b = P.list ? P.list[item] : item;
+    const float* rec = (const float*)(recbuf + (size_t)cur * P.stride);
+    const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
+    const int code = mpc::ric_solve_problem(cx, rec, gait, k, P.max_iter);
+    __syncwarp();
+    if (code == mpc::STATUS_RETRY_BIG && P.retry_list) {
+      if (lane == 0) {
+        const int slot = atomicAdd(P.retry_count, 1);
+        P.retry_list[slot] = b;
+      }
+    } else {
+      if (code == mpc::STATUS_RETRY_BIG && lane == 0) k.sc->status = MPC_STATUS_MAX_ITER;
+      __syncwarp();
+      mpc::ric_scatter(cx, k, P.forces + (size_t)12 * b, P.solution ? P.solution + (size_t)12 * P.h * b : nullptr,
+                       P.status ? P.status + b : nullptr);
+      if (P.n_peers > 0) {
+        __syncwarp();  // lanes 0..11 wrote the forces, lanes 0..2 read them back four at a time
+        peer_store_forces(P, b, lane);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 struct ClassCfg {
   int nv_cap, m_cap, in_fast, threads, grid, variant;
   size_t smem;
@@ -551,6 +617,12 @@ struct ClassCfg {
   int pipe_m_cap = 0, pipe_grid = 0;
   size_t pipe_smem = 0;
   mpc::Layout pipe_L;
+  // Riccati solver (mpc_solve_riccati_kernel, one warp per problem): used instead of the class's inverse-based kernel
+  // when the engine's solver is 1, except by the profiling / assemble-only / warm-start entries
+  bool ric = false;
+  int ric_m_cap = 0, ric_grid = 0;
+  size_t ric_smem = 0;
+  mpc::RicLayout ric_L;
 };
 
 thread_local std::string g_err;
@@ -617,6 +689,7 @@ struct mpc_batch {
   const int* warm_ids = nullptr;
   int warm_shift = 1;
   int sweep = MPC_SWEEP_DEFAULT;  // inversion of the register-resident classes: 0 FMA tiles, 1 DMMA grouped sweep
+  int solver = MPC_SOLVER_DEFAULT;  // 0: explicit inverse of the condensed Hessian; 1: Riccati sweeps (mpc_riccati.h)
   int debug_stop = 0;
   bool no_host_classify = false;  // env MPC_NO_HOST_CLASSIFY: batches of one take the general path too
   void* peer_open[kMaxPeers] = {nullptr};
@@ -819,6 +892,27 @@ int build_classes(mpc_batch* eng) {
         break;
       }
     }
+    // Riccati variant of the class: working-set tile of MPC_RIC_MCAP columns (default 16 / 24 / 32 by class; a larger
+    // working set is re-queued to the last class like every tile overflow)
+    if (!getenv("MPC_NO_RICCATI")) {
+      int m = c.variant == V_64 ? 16 : c.variant == V_96 ? 24 : 32;
+      if (const char* e = getenv("MPC_RIC_MCAP")) m = std::max(4, atoi(e));
+      m = std::min(m, c.nv_cap);
+      const mpc::RicLayout Lr = mpc::make_ric_layout(h, c.nv_cap, m);
+      const size_t need = 16 + 2 * eng->stride + Lr.bytes;
+      if ((int)need <= max_smem) {
+        int o = 0;
+        CK(cudaFuncSetAttribute(mpc_solve_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, mpc_solve_riccati_kernel, 32, need));
+        if (o >= 1) {
+          c.ric = true;
+          c.ric_m_cap = m;
+          c.ric_L = Lr;
+          c.ric_smem = need;
+          c.ric_grid = o * eng->sms;
+        }
+      }
+    }
     eng->classes.push_back(c);
   }
   // wrench-space class: nv > 128 at horizons with 6h <= 128 (see mpc_solve_wrench_kernel).  Its working-set tile is
@@ -905,8 +999,21 @@ void fill_params(const mpc_batch* eng, int slot, SolveParams& P, const void* rec
     P.peers[q] = eng->peers[q] ? (float*)((char*)eng->peers[q] + eng->gather_slot_bytes * (size_t)slot) : nullptr;
 }
 
+// does this launch of class c go through the Riccati kernel?
+bool use_riccati(const mpc_batch* eng, const ClassCfg& c, bool assemble_only) {
+  return c.ric && eng->solver == 1 && !eng->phase_clk && !eng->debug_stop && !assemble_only && !eng->warm_cache;
+}
+
 int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int grid, cudaStream_t st) {
   const bool prof = P.phase_clk != nullptr || P.H_out != nullptr || P.debug_stop != 0;
+  if (use_riccati(eng, c, P.H_out != nullptr)) {
+    SolveParams Pr = P;
+    Pr.RL = c.ric_L;
+    mpc_solve_riccati_kernel<<<grid, 32, c.ric_smem, st>>>(Pr);
+    eng->launches++;
+    CK(cudaGetLastError());
+    return MPC_OK;
+  }
   if (c.pipe && !prof) {
     SolveParams Pp = P;
     Pp.L = c.pipe_L;
@@ -1038,7 +1145,7 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
     P.warp_mode = c.variant == V_64 ? 1 : 0;
     P.slab = c.in_fast ? nullptr : S.slab;
     const bool piped = c.pipe && !eng->phase_clk && !eng->debug_stop;
-    int grid = std::min(piped ? c.pipe_grid : c.grid, batch);
+    int grid = std::min(use_riccati(eng, c, false) ? c.ric_grid : piped ? c.pipe_grid : c.grid, batch);
     if (eng->ctas_per_sm_limit > 0) grid = std::min(grid, eng->ctas_per_sm_limit * eng->sms);
     return launch_solve(eng, c, P, grid, st);  // a working-set tile overflow comes back as MAX_ITER (see wait_host)
   }
@@ -1077,7 +1184,7 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
     const bool time_this = eng->timed && (eng->timed_class < 0 || eng->timed_class == ci);
     if (time_this) CK(cudaEventRecord(eng->ring0[ring], st));
     const bool piped = c.pipe && !eng->phase_clk && !H_out && !eng->debug_stop;
-    int grid = std::min(piped ? c.pipe_grid : c.grid, batch);
+    int grid = std::min(use_riccati(eng, c, H_out != nullptr) ? c.ric_grid : piped ? c.pipe_grid : c.grid, batch);
     if (eng->ctas_per_sm_limit > 0) grid = std::min(grid, eng->ctas_per_sm_limit * eng->sms);
     int rc = launch_solve(eng, c, P, grid, st);
     if (rc) return rc;
@@ -1185,6 +1292,7 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
   if (const char* ds = getenv("MPC_DEBUG_STOP")) eng->debug_stop = atoi(ds);
   eng->no_host_classify = getenv("MPC_NO_HOST_CLASSIFY") != nullptr;
   if (const char* sw = getenv("MPC_SWEEP")) eng->sweep = (sw[0] == 'm' || sw[0] == '1') ? 1 : 0;  // "mma" / "fma"
+  if (const char* sv = getenv("MPC_SOLVER")) eng->solver = (sv[0] == 'r' || sv[0] == '1') ? 1 : 0;  // "riccati" / "inverse"
   eng->device = device;
   eng->h = horizon;
   eng->max_batch = max_batch;
@@ -1630,6 +1738,13 @@ int mpc_batch_set_sweep_variant(mpc_batch_t* eng, int variant) {
 }
 int mpc_batch_sweep_variant(const mpc_batch_t* eng) { return eng ? eng->sweep : -1; }
 
+int mpc_batch_set_solver(mpc_batch_t* eng, int solver) {
+  if (!eng || solver < 0 || solver > 1) return MPC_E_ARG;
+  eng->solver = solver;
+  return MPC_OK;
+}
+int mpc_batch_solver(const mpc_batch_t* eng) { return eng ? eng->solver : -1; }
+
 int mpc_batch_warm_stride(void) { return mpc::kWarmStride; }
 
 int mpc_batch_set_warm_start(mpc_batch_t* eng, int* cache_dev, const int* robot_ids_dev, int shift) {
@@ -1753,6 +1868,10 @@ int mpc_batch_num_classes(const mpc_batch_t* eng) { return eng ? (int)eng->class
 int mpc_batch_class_info(const mpc_batch_t* eng, int idx, int* info) {
   if (!eng || idx < 0 || idx >= (int)eng->classes.size() || !info) return MPC_E_ARG;
   const ClassCfg& c = eng->classes[idx];
+  if (use_riccati(eng, c, false)) {  // what the production launches of this class use right now
+    info[0] = c.nv_cap; info[1] = c.ric_m_cap; info[2] = 32; info[3] = c.ric_grid; info[4] = (int)c.ric_smem; info[5] = 1;
+    return MPC_OK;
+  }
   info[0] = c.nv_cap; info[1] = c.pipe ? c.pipe_m_cap : c.m_cap; info[2] = c.threads;
   info[3] = c.pipe ? c.pipe_grid : c.grid; info[4] = (int)(c.pipe ? c.pipe_smem : c.smem); info[5] = c.in_fast;
   return MPC_OK;

@@ -1,0 +1,833 @@
+// Riccati solver of the convex-MPC QP: the same optimum as mpc_core.h's explicit-inverse route, without ever
+// forming the condensed Hessian.
+//
+// What it replaces in the reference is the same as mpc_core.h (SolverMPC.cpp:296-557: c2qp, qH / qg, swing-leg
+// elimination, qpOASES); what changes is the algebra.  The condensed QP of solve_mpc,
+//     min 1/2 u'Hu + g'u,   H = 2 (B_qp' S B_qp + alpha I),   g = 2 B_qp' S (A_qp x0 - X_d)   (SolverMPC.cpp:395-399)
+// is the finite-horizon LQ tracking problem
+//     min sum_{k=1..h} (x_k - xd_k)' Q (x_k - xd_k) + alpha sum_{k<h} |u_k|^2,   x_{k+1} = A_d x_k + B_k u_k + a
+// over the stance forces u_k of every horizon step (B_k = the stance columns of B_d; a = gravity's column of A_d).
+// A product H^{-1} v is therefore one backward and one forward sweep over the horizon with the gains of the
+// discrete Riccati recursion (12 x 12 state, at most 12 controls per step):
+//     S_k = alpha I + B_k' P_{k+1} B_k,  K_k = S_k^{-1} B_k' P_{k+1} A,  P_k = Q + A' P_{k+1} A - (B_k' P_{k+1} A)' K_k
+// -- O(h) work of 12 x 12 matrix products instead of the O((3 * stance)^3) inversion of the condensed Hessian, and
+// it only gets cheaper relative to that with longer horizons.  The Goldfarb-Idnani dual active-set method needs
+// exactly such products: x = -H^{-1} g once (its backward sweep rides along with the factorisation) and
+// d = H^{-1} n_p for every row p that enters the working set (n_p touches one stance foot of one step, so its
+// backward sweep starts at that step).  The columns Z = H^{-1} N of the working set are kept, the inverse Schur
+// complement T = (N'Z)^{-1} is bordered / down-dated exactly as in mpc_core.h's active_set, and a step direction is
+// z = d - Z r.  On the BASELINE workloads a problem changes its working set 2 (trot, horizon 10) to 14 times
+// (horizon 20, mixed gaits), so a solve is one factorisation and a handful of sweeps.
+//
+// Execution model: ONE WARP PER PROBLEM (no CTA barrier anywhere; __syncwarp only), written against the same tiny
+// execution context as mpc_core.h, so the single-thread host build of tests/emu/ runs the very same source.
+// Exactness: A_d = I + dt A + dt^2/2 A^2 and B_d = dt B + dt^2/2 AB + dt^3/6 A^2 B are exact (A^3 = 0, see
+// mpc_core.h); results agree with the reference's qpOASES on the fp64-assembled dense QP to ~1e-13 relative
+// (tests/test_riccati.py, tests/test_gpu_parity.py).
+#ifndef QUADRUPED_MPC_RICCATI_H
+#define QUADRUPED_MPC_RICCATI_H
+
+#include "mpc_core.h"
+
+namespace mpc {
+
+struct RicLayout {
+  int h, nv_cap, m_cap, ldT, ldz, gain_cap;
+  int off_sc, off_ints, off_dyn, off_Bd, off_gain, off_x, off_d, off_kap, off_vec, off_red, off_un;
+  int bytes;
+};
+
+// doubles a problem's gains can take: per step 12 n_k (K_k) + n_k (n_k + 1) / 2 (S_k^{-1}, packed), n_k <= 12
+constexpr int ric_gain_doubles(int nv_cap) { return 12 * nv_cap + (13 * nv_cap + 1) / 2; }
+constexpr int kRicDyn = 8 + 12 + 36 + 36 + 12;  // scalars, Q, column form of N, row form of N, x0
+constexpr int kRicVec = 6 * 12;                 // pv, pn, xv, xn, wv, pt
+
+inline RicLayout make_ric_layout(int h, int nv_cap, int m_cap) {
+  RicLayout L;
+  L.h = h;
+  L.nv_cap = nv_cap;
+  L.m_cap = m_cap;
+  L.ldT = m_cap | 1;
+  L.ldz = nv_cap;
+  L.gain_cap = ric_gain_doubles(nv_cap);
+  int o = 0;
+  L.off_sc = o;
+  o += (int)((sizeof(Scalars) + 15) / 16 * 16);
+  // ints: stance, posk, amask [4h each]; nk [h]; voff, koff [h+1 each]; bcol [nv_cap]; W, Wia, Wiz [m_cap+1 each];
+  // NcI, NrI [36 each]
+  L.off_ints = o;
+  o += 4 * (12 * h + h + 2 * (h + 1) + nv_cap + 3 * (m_cap + 1) + 72);
+  o = (o + 15) / 16 * 16;
+  L.off_dyn = o;
+  o += 8 * kRicDyn;
+  L.off_Bd = o;
+  o += 8 * 156;
+  L.off_gain = o;
+  o += 8 * L.gain_cap;
+  L.off_x = o;
+  o += 8 * nv_cap;
+  L.off_d = o;
+  o += 8 * nv_cap;
+  L.off_kap = o;
+  o += 8 * nv_cap;
+  L.off_vec = o;
+  o += 8 * kRicVec;
+  L.off_red = o;
+  o += 8 * kRedDoubles;
+  L.off_un = o;
+  // union: factorisation scratch (P, Y, M, G 144 each; S 78; scol 12; Bc 156) | active set (Z, T, six vectors, ub)
+  const int fac = 4 * 144 + 78 + 12 + 156;
+  const int as = nv_cap * m_cap + m_cap * L.ldT + 6 * (m_cap + 1) + 4 * h;
+  o += 8 * (fac > as ? fac : as);
+  L.bytes = (o + 15) / 16 * 16;
+  return L;
+}
+
+struct RicWork {
+  Scalars* sc;
+  int *stance, *posk, *amask, *nk, *voff, *koff, *bcol, *W, *Wia, *Wiz, *NcI, *NrI;
+  double *dyn, *Q, *NcV, *NrV, *x0, *Bd, *gain, *x, *d, *kap, *pv, *pn, *xv, *xn, *wv, *pt, *red;
+  double *P, *Y, *M, *G, *S, *scol, *Bc;              // factorisation view of the union
+  double *Z, *T, *w, *r, *u, *tcol, *Wca, *Wcz, *ub;  // active-set view
+  int h, nv_cap, m_cap, ldT, ldz;
+};
+// dyn[]: 0 dt, 1 cos(yaw), 2 sin(yaw), 3 x_drag, 4 alpha, 5 a[5], 6 a[11] (gravity's column of A_d times x0[12]),
+// 7 1/mu (float, as the reference forms it)
+
+MPC_HD RicWork ric_carve(const RicLayout& L, char* fast) {
+  RicWork k;
+  k.sc = (Scalars*)(fast + L.off_sc);
+  int* ip = (int*)(fast + L.off_ints);
+  k.stance = ip;
+  k.posk = ip + 4 * L.h;
+  k.amask = ip + 8 * L.h;
+  k.nk = ip + 12 * L.h;
+  k.voff = k.nk + L.h;
+  k.koff = k.voff + L.h + 1;
+  k.bcol = k.koff + L.h + 1;
+  k.W = k.bcol + L.nv_cap;
+  k.Wia = k.W + L.m_cap + 1;
+  k.Wiz = k.Wia + L.m_cap + 1;
+  k.NcI = k.Wiz + L.m_cap + 1;
+  k.NrI = k.NcI + 36;
+  k.dyn = (double*)(fast + L.off_dyn);
+  k.Q = k.dyn + 8;
+  k.NcV = k.Q + 12;
+  k.NrV = k.NcV + 36;
+  k.x0 = k.NrV + 36;
+  k.Bd = (double*)(fast + L.off_Bd);
+  k.gain = (double*)(fast + L.off_gain);
+  k.x = (double*)(fast + L.off_x);
+  k.d = (double*)(fast + L.off_d);
+  k.kap = (double*)(fast + L.off_kap);
+  k.pv = (double*)(fast + L.off_vec);
+  k.pn = k.pv + 12;
+  k.xv = k.pn + 12;
+  k.xn = k.xv + 12;
+  k.wv = k.xn + 12;
+  k.pt = k.wv + 12;
+  k.red = (double*)(fast + L.off_red);
+  double* un = (double*)(fast + L.off_un);
+  k.P = un;
+  k.Y = k.P + 144;
+  k.M = k.Y + 144;
+  k.G = k.M + 144;
+  k.S = k.G + 144;
+  k.scol = k.S + 78;
+  k.Bc = k.scol + 12;
+  k.Z = un;
+  k.T = k.Z + L.nv_cap * L.m_cap;
+  k.w = k.T + L.m_cap * L.ldT;
+  k.r = k.w + L.m_cap + 1;
+  k.u = k.r + L.m_cap + 1;
+  k.tcol = k.u + L.m_cap + 1;
+  k.Wca = k.tcol + L.m_cap + 1;
+  k.Wcz = k.Wca + L.m_cap + 1;
+  k.ub = k.Wcz + L.m_cap + 1;
+  k.h = L.h;
+  k.nv_cap = L.nv_cap;
+  k.m_cap = L.m_cap;
+  k.ldT = L.ldT;
+  k.ldz = L.ldz;
+  return k;
+}
+
+// e / n and the remainder for small non-negative e and 1 <= n <= 12 (a float reciprocal instead of an integer
+// division on the device; exact in this range)
+MPC_HD int ric_div(int e, int n) {
+#if defined(__CUDA_ARCH__)
+  return __float2int_rz(__fdividef((float)e + 0.5f, (float)n));
+#else
+  return e / n;
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// Set-up: input check, stance list, x0, exact discretisation (the P0-P3 phases of mpc_core.h's assemble_front with
+// the same formulas), the sparse tables of N = A_d - I, per-step offsets.  Returns through sc->status.
+// ---------------------------------------------------------------------------
+template <class Cx>
+MPC_HD void ric_setup(const Cx& cx, const float* rec, const unsigned char* gait, const RicWork& k) {
+  const int h = k.h;
+  Scalars* sc = k.sc;
+  double* B = k.Bc;  // 13 x 12 continuous-time B
+  int* flag = k.amask;
+  const float fmax = rec[MPC_REC_FMAX];
+  MPC_ONE {
+    sc->status = MPC_STATUS_OPTIMAL;
+    sc->m = 0;
+    sc->iters = 0;
+  }
+  MPC_FOR(kk, 4 * h) {  // SolverMPC.cpp:441-469: U_b(5k+4) = gait[k]*f_max "near zero" => eliminated
+    const float ub = (float)gait[kk] * fmax;
+    flag[kk] = ((double)ub < 0.01 && (double)ub > -0.01) ? 0 : 1;
+  }
+  MPC_FOR(i, 156) B[i] = 0.0;
+  MPC_FOR(i, 36) {
+    k.NcI[i] = 0; k.NrI[i] = 0;
+    k.NcV[i] = 0.0; k.NrV[i] = 0.0;
+  }
+  cx.sync();
+  MPC_FOR(i, MPC_REC_TRAJ + 12 * h)
+    if (!finite_f(rec[i])) sc->status = MPC_STATUS_BAD_INPUT;  // same value from every writer
+  MPC_ONE {
+    if (!(rec[MPC_REC_MU] > 0.f) || !(rec[MPC_REC_MASS] > 0.f) || !(rec[MPC_REC_DT] > 0.f) ||
+        !(rec[MPC_REC_IBODY] > 0.f) || !(rec[MPC_REC_IBODY + 1] > 0.f) || !(rec[MPC_REC_IBODY + 2] > 0.f) ||
+        !(fmax >= 0.f))
+      sc->status = MPC_STATUS_BAD_INPUT;
+  }
+  MPC_FOR(kk, 4 * h) {
+    int pos = 0;
+#pragma unroll 4
+    for (int q = 0; q < kk; q++) pos += flag[q];
+    if (flag[kk]) { k.stance[pos] = kk; k.posk[kk] = pos; }
+    else k.posk[kk] = -1;
+    if (kk == 4 * h - 1) { sc->ns = pos + flag[kk]; sc->nv = 3 * (pos + flag[kk]); }
+  }
+  {
+    // quat_to_rpy (SolverMPC.cpp:257-267), q = (w,x,y,z); x_0 = [rpy(2), rpy(1), rpy(0), ...] (:318); the
+    // transcendental groups on four lanes
+    const double qw = rec[MPC_REC_Q], qx = rec[MPC_REC_Q + 1], qy = rec[MPC_REC_Q + 2], qz = rec[MPC_REC_Q + 3];
+    const int l1 = cx.nt >= 4 ? 1 : 0, l2 = cx.nt >= 4 ? 2 : 0, l3 = cx.nt >= 4 ? 3 : 0;
+    if (cx.tid == 0) {
+      const double yaw = (double)rec[MPC_REC_YAW];
+      double sy, cy;
+      sincos(yaw, &sy, &cy);
+      k.dyn[1] = cy;
+      k.dyn[2] = sy;
+    }
+    if (cx.tid == l1) k.x0[2] = MPC_ATAN2(2. * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
+    if (cx.tid == l2) {
+      double as = -2. * (qx * qz - qw * qy);
+      if (!(as < .99999)) as = .99999;
+      k.x0[1] = asin(as);
+    }
+    if (cx.tid == l3) k.x0[0] = MPC_ATAN2(2. * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
+  }
+  cx.sync();
+  const double dt = (double)rec[MPC_REC_DT];
+  const double xd = (double)rec[MPC_REC_XDRAG];
+  const double yc = k.dyn[1], ys = k.dyn[2];
+  MPC_ONE {
+    if (sc->status == MPC_STATUS_OPTIMAL && sc->ns == 0) sc->status = MPC_STATUS_NO_STANCE;
+    for (int i = 0; i < 3; i++) {
+      k.x0[3 + i] = rec[MPC_REC_P + i];
+      k.x0[6 + i] = rec[MPC_REC_W + i];
+      k.x0[9 + i] = rec[MPC_REC_V + i];
+    }
+    const double grav = (double)-9.8f;  // x0[12] (SolverMPC.cpp:318)
+    k.dyn[0] = dt;
+    k.dyn[3] = xd;
+    k.dyn[4] = (double)rec[MPC_REC_ALPHA];
+    k.dyn[5] = (dt * dt / 2.0) * grav;  // A_d[5][12] = dt^2/2 (row 5 of A^2 carries e12), A_d[11][12] = dt
+    k.dyn[6] = dt * grav;
+    k.dyn[7] = (double)(1.0f / rec[MPC_REC_MU]);
+    // N = A_d - I = dt A + dt^2/2 A^2 (ct_ss_mats, SolverMPC.cpp:237-244; A^2 has row 5 = x_drag e9' + e12' only).
+    // Column form: entries (row, value) of column j; row form: entries (column, value) of row i; three slots each.
+    const double half = dt * dt / 2.0;
+    int* ci = k.NcI; double* cv = k.NcV; int* ri = k.NrI; double* rv = k.NrV;
+    ci[3 * 6 + 0] = 0; cv[3 * 6 + 0] = dt * yc;   ci[3 * 6 + 1] = 1; cv[3 * 6 + 1] = -dt * ys;
+    ci[3 * 7 + 0] = 0; cv[3 * 7 + 0] = dt * ys;   ci[3 * 7 + 1] = 1; cv[3 * 7 + 1] = dt * yc;
+    ci[3 * 8 + 0] = 2; cv[3 * 8 + 0] = dt;
+    ci[3 * 9 + 0] = 3; cv[3 * 9 + 0] = dt;        ci[3 * 9 + 1] = 5; cv[3 * 9 + 1] = half * xd;
+    ci[3 * 9 + 2] = 11; cv[3 * 9 + 2] = dt * xd;
+    ci[3 * 10 + 0] = 4; cv[3 * 10 + 0] = dt;
+    ci[3 * 11 + 0] = 5; cv[3 * 11 + 0] = dt;
+    ri[3 * 0 + 0] = 6; rv[3 * 0 + 0] = dt * yc;   ri[3 * 0 + 1] = 7; rv[3 * 0 + 1] = dt * ys;
+    ri[3 * 1 + 0] = 6; rv[3 * 1 + 0] = -dt * ys;  ri[3 * 1 + 1] = 7; rv[3 * 1 + 1] = dt * yc;
+    ri[3 * 2 + 0] = 8; rv[3 * 2 + 0] = dt;
+    ri[3 * 3 + 0] = 9; rv[3 * 3 + 0] = dt;
+    ri[3 * 4 + 0] = 10; rv[3 * 4 + 0] = dt;
+    ri[3 * 5 + 0] = 11; rv[3 * 5 + 0] = dt;       ri[3 * 5 + 1] = 9; rv[3 * 5 + 1] = half * xd;
+    ri[3 * 11 + 0] = 9; rv[3 * 11 + 0] = dt * xd;
+  }
+  MPC_FOR(i, 12) k.Q[i] = (double)rec[MPC_REC_WEIGHTS + i];
+  MPC_FOR(b, 4) {  // B_c per leg (ct_ss_mats, SolverMPC.cpp:235-254; cross_mat :226-233), as in mpc_core.h P2
+    const double R[3][3] = {{yc, -ys, 0}, {ys, yc, 0}, {0, 0, 1}};
+    const double Ib[3] = {(double)rec[MPC_REC_IBODY], (double)rec[MPC_REC_IBODY + 1], (double)rec[MPC_REC_IBODY + 2]};
+    double Iw[3][3];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double acc = 0;
+        for (int q = 0; q < 3; q++) acc += (R[i][q] * Ib[q]) * R[j][q];
+        Iw[i][j] = acc;
+      }
+    const double det = Iw[0][0] * (Iw[1][1] * Iw[2][2] - Iw[1][2] * Iw[2][1]) -
+                       Iw[0][1] * (Iw[1][0] * Iw[2][2] - Iw[1][2] * Iw[2][0]) +
+                       Iw[0][2] * (Iw[1][0] * Iw[2][1] - Iw[1][1] * Iw[2][0]);
+    const double rdet = 1.0 / det;
+    double Ii[3][3];
+    Ii[0][0] = (Iw[1][1] * Iw[2][2] - Iw[1][2] * Iw[2][1]) * rdet;
+    Ii[0][1] = (Iw[0][2] * Iw[2][1] - Iw[0][1] * Iw[2][2]) * rdet;
+    Ii[0][2] = (Iw[0][1] * Iw[1][2] - Iw[0][2] * Iw[1][1]) * rdet;
+    Ii[1][0] = (Iw[1][2] * Iw[2][0] - Iw[1][0] * Iw[2][2]) * rdet;
+    Ii[1][1] = (Iw[0][0] * Iw[2][2] - Iw[0][2] * Iw[2][0]) * rdet;
+    Ii[1][2] = (Iw[0][2] * Iw[1][0] - Iw[0][0] * Iw[1][2]) * rdet;
+    Ii[2][0] = (Iw[1][0] * Iw[2][1] - Iw[1][1] * Iw[2][0]) * rdet;
+    Ii[2][1] = (Iw[0][1] * Iw[2][0] - Iw[0][0] * Iw[2][1]) * rdet;
+    Ii[2][2] = (Iw[0][0] * Iw[1][1] - Iw[0][1] * Iw[1][0]) * rdet;
+    const double minv = 1.0 / (double)rec[MPC_REC_MASS];
+    const double rx = rec[MPC_REC_R + b], ry = rec[MPC_REC_R + 4 + b], rz = rec[MPC_REC_R + 8 + b];
+    const double cm[3][3] = {{0, -rz, ry}, {rz, 0, -rx}, {-ry, rx, 0}};
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) {
+        double acc = 0;
+        for (int q = 0; q < 3; q++) acc += Ii[i][q] * cm[q][j];
+        B[(6 + i) * 12 + b * 3 + j] = acc;
+      }
+      B[(9 + i) * 12 + b * 3 + i] = minv;
+    }
+  }
+  // per-step offsets: n_k = 3 * (stance legs of step k), voff = first reduced variable, koff = first gain double
+  MPC_ONE {
+    int v = 0, g = 0;
+    for (int s = 0; s < h; s++) {
+      const int n = 3 * (flag[4 * s] + flag[4 * s + 1] + flag[4 * s + 2] + flag[4 * s + 3]);
+      k.nk[s] = n;
+      k.voff[s] = v;
+      k.koff[s] = g;
+      v += n;
+      g += 12 * n + n * (n + 1) / 2;
+    }
+    k.voff[h] = v;
+    k.koff[h] = g;
+  }
+  cx.sync();
+  if (sc->status != MPC_STATUS_OPTIMAL) return;
+  // exact discretisation B_d = dt B + dt^2/2 AB + dt^3/6 A^2 B (c2qp, SolverMPC.cpp:87-101); row 12 is zero
+  MPC_FOR(e, 144) {
+    const int i = e / 12, j = e - 12 * i;
+    k.Bd[e] = dt * B[e] + (dt * dt / 2.0) * apply_A(B, 12, i, j, yc, ys, xd) +
+              (dt * dt * dt / 6.0) * apply_A2(B, 12, i, j, xd);
+  }
+  MPC_FOR(v, sc->nv) k.bcol[v] = (k.stance[v / 3] & 3) * 3 + (v % 3);
+  cx.sync();
+}
+
+// ---------------------------------------------------------------------------
+// Factorisation: backward Riccati recursion, gains K_k and S_k^{-1} of every step into k.gain, and -- riding along --
+// the backward sweep of the tracking problem itself (kap = S^{-1}(B'(p + P a)), the feed-forward of x = -H^{-1} g).
+// ---------------------------------------------------------------------------
+template <class Cx>
+MPC_HD void ric_factor(const Cx& cx, const float* rec, const RicWork& k) {
+  const int h = k.h;
+  Scalars* sc = k.sc;
+  double *P = k.P, *Y = k.Y, *M = k.M, *G = k.G, *S = k.S;
+  const double* Bd = k.Bd;
+  const double* Q = k.Q;
+  const double alpha = k.dyn[4], a5 = k.dyn[5], a11 = k.dyn[6];
+  // terminal cost of step h: P = Q, p = -Q xd_h
+  MPC_FOR(e, 144) {
+    const int i = e / 12, j = e - 12 * i;
+    P[e] = (i == j) ? Q[i] : 0.0;
+  }
+  MPC_FOR(i, 12) k.pv[i] = -Q[i] * (double)rec[MPC_REC_TRAJ + 12 * (h - 1) + i];
+  cx.sync();
+  bool bad = false;
+#pragma unroll 1
+  for (int s = h - 1; s >= 0; s--) {
+    const int n = k.nk[s], v0 = k.voff[s], ntri = n * (n + 1) / 2;
+    double* K = k.gain + k.koff[s];  // n x 12, row-major
+    double* Si = K + 12 * n;         // S^{-1}, packed lower triangle
+    const int* bc = k.bcol + v0;
+    // (1) pt = p + P a (a has two entries);  M = P B_k  (12 x n, leading dimension 12)
+    MPC_FOR(i, 12) k.pt[i] = k.pv[i] + a5 * P[i * 12 + 5] + a11 * P[i * 12 + 11];
+    MPC_FOR(e, 12 * n) {
+      const int i = ric_div(e, n), c = e - i * n, col = bc[c];
+      double a0 = 0, a1 = 0;
+#pragma unroll
+      for (int j = 0; j < 12; j += 2) {
+        a0 += P[i * 12 + j] * Bd[j * 12 + col];
+        a1 += P[i * 12 + j + 1] * Bd[(j + 1) * 12 + col];
+      }
+      M[i * 12 + c] = a0 + a1;
+    }
+    cx.sync();
+    // (2) S = alpha I + B_k' M (lower triangle, packed);  w = B_k' pt
+    MPC_FOR(e, n * n + n) {
+      if (e < n * n) {
+        const int a = ric_div(e, n), b = e - a * n;
+        if (a >= b) {
+          const int ca = bc[a];
+          double a0 = 0, a1 = 0;
+#pragma unroll
+          for (int i = 0; i < 12; i += 2) {
+            a0 += Bd[i * 12 + ca] * M[i * 12 + b];
+            a1 += Bd[(i + 1) * 12 + ca] * M[(i + 1) * 12 + b];
+          }
+          S[tri_index(a, b)] = (a0 + a1) + (a == b ? alpha : 0.0);
+        }
+      } else {
+        const int c = e - n * n, col = bc[c];
+        double a0 = 0, a1 = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i += 2) {
+          a0 += Bd[i * 12 + col] * k.pt[i];
+          a1 += Bd[(i + 1) * 12 + col] * k.pt[i + 1];
+        }
+        k.wv[c] = a0 + a1;
+      }
+    }
+    cx.sync();
+    // (3) S <- -S^{-1} by symmetric sweeps (SPD: no pivoting; a non-positive pivot = alpha <= 0 with zero weights)
+#pragma unroll 1
+    for (int p = 0; p < n; p++) {
+      MPC_FOR(a, n) k.scol[a] = S[tri_index(a, p)];
+      cx.sync();
+      const double dp = k.scol[p];
+      if (!(dp > 0.0) || !(dp < 1e300)) bad = true;  // uniform
+      const double dinv = 1.0 / dp;
+      MPC_FOR(e, n * n) {
+        const int a = ric_div(e, n), b = e - a * n;
+        if (a >= b) {
+          double v;
+          if (a == p && b == p) v = -dinv;
+          else if (a == p) v = k.scol[b] * dinv;
+          else if (b == p) v = k.scol[a] * dinv;
+          else v = S[tri_index(a, b)] - k.scol[a] * k.scol[b] * dinv;
+          S[tri_index(a, b)] = v;
+        }
+      }
+      cx.sync();
+    }
+    // (4) G = M' A = M' + M' N  (n x 12);  S^{-1} into the gains
+    MPC_FOR(e, ntri) Si[e] = -S[e];
+    MPC_FOR(e, 12 * n) {
+      const int c = e / 12, j = e - 12 * c;
+      double acc = M[j * 12 + c];
+#pragma unroll
+      for (int t = 0; t < 3; t++) acc += k.NcV[3 * j + t] * M[k.NcI[3 * j + t] * 12 + c];
+      G[e] = acc;
+    }
+    // Y = P A = P + P N
+    MPC_FOR(e, 144) {
+      const int i = e / 12, j = e - 12 * i;
+      double acc = P[e];
+#pragma unroll
+      for (int t = 0; t < 3; t++) acc += k.NcV[3 * j + t] * P[i * 12 + k.NcI[3 * j + t]];
+      Y[e] = acc;
+    }
+    cx.sync();
+    // (5) K = S^{-1} G;  kap = S^{-1} w
+    MPC_FOR(e, 12 * n + n) {
+      if (e < 12 * n) {
+        const int c = e / 12, j = e - 12 * c;
+        double acc = 0;
+#pragma unroll 1
+        for (int b = 0; b < n; b++) acc += Si[tri_index(c, b)] * G[b * 12 + j];
+        K[e] = acc;
+      } else {
+        const int c = e - 12 * n;
+        double acc = 0;
+#pragma unroll 1
+        for (int b = 0; b < n; b++) acc += Si[tri_index(c, b)] * k.wv[b];
+        k.kap[v0 + c] = acc;
+      }
+    }
+    cx.sync();
+    // (6) P <- Q + A'Y - G'K (lower triangle, mirrored);  p <- A' pt - G' kap - Q xd_s.  (Q and xd only for s >= 1:
+    //     x_0 is given, it carries no cost.)  Nothing here reads P or p.
+    MPC_FOR(e, 144 + 12) {
+      if (e < 144) {
+        const int i = e / 12, j = e - 12 * i;
+        if (i >= j) {
+          double acc = Y[e];
+#pragma unroll
+          for (int t = 0; t < 3; t++) acc += k.NcV[3 * i + t] * Y[k.NcI[3 * i + t] * 12 + j];
+          double g0 = 0, g1 = 0;
+          int c = 0;
+#pragma unroll 1
+          for (; c + 1 < n; c += 2) {
+            g0 += G[c * 12 + i] * K[c * 12 + j];
+            g1 += G[(c + 1) * 12 + i] * K[(c + 1) * 12 + j];
+          }
+          if (c < n) g0 += G[c * 12 + i] * K[c * 12 + j];
+          acc -= g0 + g1;
+          if (i == j && s >= 1) acc += Q[i];
+          P[i * 12 + j] = acc;
+          P[j * 12 + i] = acc;
+        }
+      } else {
+        const int j = e - 144;
+        double acc = k.pt[j];
+#pragma unroll
+        for (int t = 0; t < 3; t++) acc += k.NcV[3 * j + t] * k.pt[k.NcI[3 * j + t]];
+#pragma unroll 1
+        for (int c = 0; c < n; c++) acc -= G[c * 12 + j] * k.kap[v0 + c];
+        if (s >= 1) acc -= Q[j] * (double)rec[MPC_REC_TRAJ + 12 * (s - 1) + j];
+        k.pv[j] = acc;
+      }
+    }
+    cx.sync();
+  }
+  if (bad) {
+    MPC_ONE sc->status = MPC_STATUS_NOT_PD;
+    cx.sync();
+  }
+}
+
+// Forward sweep: u_k = -K_k x_k - kap_k, x_{k+1} = A x_k + B_k u_k (+ a when `affine`: the tracking problem; the
+// products H^{-1} v are homogeneous), from x_0 = xstart (nullptr: 0).  kap_k counts as zero for steps > last.
+template <class Cx>
+MPC_HD void ric_forward(const Cx& cx, const RicWork& k, const double* xstart, bool affine, int last, double* out) {
+  const int h = k.h;
+  double* xa = k.xv;
+  double* xb = k.xn;
+  MPC_FOR(i, 12) xa[i] = xstart ? xstart[i] : 0.0;
+  cx.sync();
+  const double a5 = affine ? k.dyn[5] : 0.0, a11 = affine ? k.dyn[6] : 0.0;
+#pragma unroll 1
+  for (int s = 0; s < h; s++) {
+    const int n = k.nk[s], v0 = k.voff[s];
+    const double* K = k.gain + k.koff[s];
+    MPC_FOR(c, n) {
+      double a0 = (s <= last) ? k.kap[v0 + c] : 0.0, a1 = 0;
+#pragma unroll
+      for (int j = 0; j < 12; j += 2) {
+        a0 += K[c * 12 + j] * xa[j];
+        a1 += K[c * 12 + j + 1] * xa[j + 1];
+      }
+      out[v0 + c] = -(a0 + a1);
+    }
+    cx.sync();
+    if (s == h - 1) break;  // the state after the last step is not needed
+    MPC_FOR(i, 12) {
+      double acc = xa[i];
+#pragma unroll
+      for (int t = 0; t < 3; t++) acc += k.NrV[3 * i + t] * xa[k.NrI[3 * i + t]];
+#pragma unroll 1
+      for (int c = 0; c < n; c++) acc += k.Bd[i * 12 + k.bcol[v0 + c]] * out[v0 + c];
+      if (i == 5) acc += a5;
+      if (i == 11) acc += a11;
+      xb[i] = acc;
+    }
+    cx.sync();
+    double* t = xa; xa = xb; xb = t;
+  }
+}
+
+// out = H^{-1} n for a catalogue row n = ca e_ia + cz e_iz (both variables belong to one stance foot of one step):
+// argmin 1/2 u'Hu - n'u.  The backward sweep starts at that step (the costate is zero behind it).
+template <class Cx>
+MPC_HD void ric_hinv_row(const Cx& cx, const RicWork& k, const Row& rp, double* out) {
+  const int kp = k.stance[rp.iz / 3] >> 2;
+  double* pa = k.pv;
+  double* pb = k.pn;
+  {
+    const int n = k.nk[kp], v0 = k.voff[kp];
+    const double* K = k.gain + k.koff[kp];
+    const double* Si = K + 12 * n;
+    // w = -n/2 on the variables of this step
+    MPC_FOR(c, n) k.wv[c] = -0.5 * ((v0 + c == rp.ia ? rp.ca : 0.0) + (v0 + c == rp.iz ? rp.cz : 0.0));
+    cx.sync();
+    MPC_FOR(e, n + 12) {
+      if (e < n) {
+        double acc = 0;
+#pragma unroll 1
+        for (int b = 0; b < n; b++) acc += Si[tri_index(e, b)] * k.wv[b];
+        k.kap[v0 + e] = acc;
+      } else {
+        const int j = e - n;
+        double acc = 0;
+#pragma unroll 1
+        for (int c = 0; c < n; c++) acc -= K[c * 12 + j] * k.wv[c];
+        pa[j] = acc;
+      }
+    }
+    cx.sync();
+  }
+#pragma unroll 1
+  for (int s = kp - 1; s >= 0; s--) {
+    const int n = k.nk[s], v0 = k.voff[s];
+    const double* K = k.gain + k.koff[s];
+    const double* Si = K + 12 * n;
+    MPC_FOR(c, n) {
+      const int col = k.bcol[v0 + c];
+      double a0 = 0, a1 = 0;
+#pragma unroll
+      for (int i = 0; i < 12; i += 2) {
+        a0 += k.Bd[i * 12 + col] * pa[i];
+        a1 += k.Bd[(i + 1) * 12 + col] * pa[i + 1];
+      }
+      k.wv[c] = a0 + a1;
+    }
+    cx.sync();
+    MPC_FOR(e, n + 12) {
+      if (e < n) {
+        double acc = 0;
+#pragma unroll 1
+        for (int b = 0; b < n; b++) acc += Si[tri_index(e, b)] * k.wv[b];
+        k.kap[v0 + e] = acc;
+      } else {
+        const int j = e - n;
+        double acc = pa[j];
+#pragma unroll
+        for (int t = 0; t < 3; t++) acc += k.NcV[3 * j + t] * pa[k.NcI[3 * j + t]];
+#pragma unroll 1
+        for (int c = 0; c < n; c++) acc -= K[c * 12 + j] * k.wv[c];
+        pb[j] = acc;
+      }
+    }
+    cx.sync();
+    double* t = pa; pa = pb; pb = t;
+  }
+  ric_forward(cx, k, nullptr, false, kp, out);
+}
+
+// ---------------------------------------------------------------------------
+// Goldfarb-Idnani dual active set with H^{-1} products from the Riccati sweeps.  Same selection rule, tolerances,
+// step rules and T updates as mpc_core.h's active_set; rows of H^{-1} are replaced by the stored columns
+// Z[:, a] = H^{-1} n_a of the working set and d = H^{-1} n_p of the entering row.
+// ---------------------------------------------------------------------------
+template <class Cx>
+MPC_HD void ric_active_set(const Cx& cx, const float* rec, const unsigned char* gait, const RicWork& k, int max_iter) {
+  Scalars* sc = k.sc;
+  const int nv = sc->nv, ns = sc->ns, ldT = k.ldT, ldz = k.ldz;
+  const double mu_inv = k.dyn[7];
+  double* T = k.T;
+  double* Z = k.Z;
+  double* d = k.d;
+  const double vtol = 1e-9;
+  MPC_FOR(j, ns) {
+    k.amask[j] = 0;
+    k.ub[j] = (double)((float)gait[k.stance[j]] * rec[MPC_REC_FMAX]);  // U_b(5k+4), a float product upstream
+  }
+  cx.sync();
+  for (;;) {
+    double best = -vtol;
+    int bidx = 0x7fffffff;
+    MPC_FOR(j, ns) {
+      const double fx = k.x[3 * j], fy = k.x[3 * j + 1], fz = k.x[3 * j + 2];
+      const int mask = k.amask[j];
+      const double sl[6] = {fx * mu_inv + fz, fz - fx * mu_inv, fy * mu_inv + fz, fz - fy * mu_inv, fz, k.ub[j] - fz};
+#pragma unroll
+      for (int t = 0; t < 6; t++)
+        if (!((mask >> t) & 1) && sl[t] < best) { best = sl[t]; bidx = 6 * j + t; }
+    }
+    block_argmin(cx, k.red, best, bidx);
+    if (bidx == 0x7fffffff) break;  // uniform
+    if (sc->iters >= max_iter) {
+      cx.sync();
+      MPC_ONE sc->status = MPC_STATUS_MAX_ITER;
+      cx.sync();
+      break;
+    }
+    if (sc->m >= k.m_cap) {  // no room for another column of Z: the problem goes to a class with a larger tile
+      cx.sync();
+      MPC_ONE sc->status = STATUS_RETRY_BIG;
+      cx.sync();
+      return;
+    }
+    const int p = bidx;
+    const Row rp = make_row(p, mu_inv);
+    const double bp = (p % 6 == 5) ? -k.ub[p / 6] : 0.0;
+    cx.sync();
+    MPC_ONE { sc->iters++; sc->up = 0.0; }
+    ric_hinv_row(cx, k, rp, d);  // (ends with a sync)
+    const double vnp = rp.ca * d[rp.ia] + rp.cz * d[rp.iz];
+    bool fail = false;
+    for (;;) {
+      const int m = sc->m;
+      MPC_FOR(a, m) k.w[a] = k.Wca[a] * d[k.Wia[a]] + k.Wcz[a] * d[k.Wiz[a]];  // n_a' H^{-1} n_p
+      cx.sync();
+      MPC_FOR(a, m) {
+        double acc = 0;
+#pragma unroll 1
+        for (int b = 0; b < m; b++) acc += T[b * ldT + a] * k.w[b];
+        k.r[a] = acc;
+      }
+      cx.sync();
+      double part = 0, tbest = 1e300;
+      int tidx = 0x7fffffff;
+      MPC_FOR(a, m) {
+        part += k.w[a] * k.r[a];
+        if (k.r[a] > 0.0) {
+          const double q = k.u[a] / k.r[a];
+          if (q < tbest) { tbest = q; tidx = a; }
+        }
+      }
+      double wr = 0.0;
+      if (m > 0) {  // uniform
+        wr = block_sum(cx, k.red, part);
+        block_argmin(cx, k.red, tbest, tidx);
+      }
+      const double znp = vnp - wr;
+      const bool dependent = !(znp > 1e-11 * vnp);
+      const double spc = rp.ca * k.x[rp.ia] + rp.cz * k.x[rp.iz] - bp;  // current slack of p (< 0)
+      const double t2 = dependent ? 1e300 : -spc / znp;
+      const double t1 = (tidx == 0x7fffffff) ? 1e300 : tbest;
+      const double t = t1 < t2 ? t1 : t2;
+      if (t >= 1e300) { fail = true; break; }
+      cx.sync();  // every thread has read x (slack of p) before anybody moves x
+      // x += t (d - Z r); applied in the dependent case too (x and u must move with the same (r, t))
+      MPC_FOR(i, nv) {
+        double acc0 = d[i], acc1 = 0;
+        int a = 0;
+#pragma unroll 1
+        for (; a + 1 < m; a += 2) {
+          acc0 -= k.r[a] * Z[a * ldz + i];
+          acc1 -= k.r[a + 1] * Z[(a + 1) * ldz + i];
+        }
+        if (a < m) acc0 -= k.r[a] * Z[a * ldz + i];
+        k.x[i] += t * (acc0 + acc1);
+      }
+      MPC_FOR(a, m) k.u[a] -= t * k.r[a];
+      cx.sync();
+      if (t2 <= t1) {
+        // ---- full step: p joins the working set; border T, keep d as its column of Z ----
+        const double dinv = 1.0 / znp;
+#pragma unroll 1
+        for (int e = cx.tid; e < m * m; e += cx.nt) {
+          const int a = e / m, b = e - a * m;
+          T[a * ldT + b] += k.r[a] * k.r[b] * dinv;
+        }
+        MPC_FOR(a, m) {
+          T[a * ldT + m] = -k.r[a] * dinv;
+          T[m * ldT + a] = -k.r[a] * dinv;
+        }
+        MPC_FOR(i, nv) Z[m * ldz + i] = d[i];
+        MPC_ONE {
+          T[m * ldT + m] = dinv;
+          k.W[m] = p;
+          k.Wia[m] = rp.ia; k.Wiz[m] = rp.iz; k.Wca[m] = rp.ca; k.Wcz[m] = rp.cz;
+          k.u[m] = sc->up + t;
+          k.amask[p / 6] |= 1 << (p % 6);
+          sc->m = m + 1;
+        }
+        cx.sync();
+        break;
+      }
+      // ---- partial step: row W[tidx] leaves; Schur-downdate T, move the last row / column into the hole ----
+      const int a0 = tidx, last = m - 1;
+      MPC_FOR(a, m) k.tcol[a] = T[a0 * ldT + a];
+      cx.sync();
+      const double taa_inv = 1.0 / k.tcol[a0];
+#pragma unroll 1
+      for (int e = cx.tid; e < m * m; e += cx.nt) {
+        const int a = e / m, b = e - a * m;
+        if (a != a0 && b != a0) T[a * ldT + b] -= k.tcol[a] * k.tcol[b] * taa_inv;
+      }
+      cx.sync();
+      if (a0 != last) {
+        MPC_FOR(b, last) {
+          if (b == a0) continue;
+          const double v = T[last * ldT + b];
+          T[a0 * ldT + b] = v;
+          T[b * ldT + a0] = v;
+        }
+        MPC_ONE T[a0 * ldT + a0] = T[last * ldT + last];
+        MPC_FOR(i, nv) Z[a0 * ldz + i] = Z[last * ldz + i];
+      }
+      cx.sync();
+      MPC_ONE {
+        sc->up += t;
+        const int cdrop = k.W[a0];
+        k.amask[cdrop / 6] &= ~(1 << (cdrop % 6));
+        if (a0 != last) {
+          k.W[a0] = k.W[last];
+          k.Wia[a0] = k.Wia[last]; k.Wiz[a0] = k.Wiz[last]; k.Wca[a0] = k.Wca[last]; k.Wcz[a0] = k.Wcz[last];
+          k.u[a0] = k.u[last];
+        }
+        sc->m = last;
+      }
+      cx.sync();
+    }
+    if (fail) {
+      cx.sync();
+      MPC_ONE sc->status = MPC_STATUS_MAX_ITER;
+      cx.sync();
+      break;
+    }
+  }
+  // ---- polish (as in mpc_core.h): restore the feasibility n_a'x = b_a of the working set when T has drifted ----
+  const int m = sc->m;
+  if (sc->status == MPC_STATUS_OPTIMAL && m > 0) {
+    for (int pass = 0; pass < 2; pass++) {
+      double worst = 0.0;
+      MPC_FOR(a, m) {
+        const double b = (k.W[a] % 6 == 5) ? -k.ub[k.W[a] / 6] : 0.0;
+        const double wa = b - (k.Wca[a] * k.x[k.Wia[a]] + k.Wcz[a] * k.x[k.Wiz[a]]);
+        k.w[a] = wa;
+        worst = fabs(wa) > worst ? fabs(wa) : worst;
+      }
+      {
+        double neg = -worst;
+        int who = cx.tid;
+        block_argmin(cx, k.red, neg, who);
+        if (!(-neg > 1e-12)) break;  // uniform
+      }
+      cx.sync();
+      MPC_FOR(a, m) {
+        double acc = 0;
+#pragma unroll 1
+        for (int b = 0; b < m; b++) acc += T[b * ldT + a] * k.w[b];
+        k.r[a] = acc;
+      }
+      cx.sync();
+      MPC_FOR(i, nv) {
+        double acc = 0;
+#pragma unroll 1
+        for (int a = 0; a < m; a++) acc += k.r[a] * Z[a * ldz + i];
+        k.x[i] += acc;
+      }
+      MPC_FOR(a, m) k.u[a] += k.r[a];
+      cx.sync();
+    }
+  }
+}
+
+// Outputs, as mpc_core.h's scatter (SolverMPC.cpp:545-557): eliminated variables are exactly 0; zeros on failure.
+template <class Cx>
+MPC_HD void ric_scatter(const Cx& cx, const RicWork& k, float* forces, double* solution, int32_t* status) {
+  const Scalars* sc = k.sc;
+  const int code = sc->status;
+  const bool ok = code == MPC_STATUS_OPTIMAL;
+  MPC_FOR(i, 12) {
+    const int pos = (code == MPC_STATUS_BAD_INPUT) ? -1 : k.posk[i / 3];
+    forces[i] = (ok && pos >= 0) ? (float)k.x[3 * pos + (i % 3)] : 0.f;
+  }
+  if (solution) {
+    MPC_FOR(i, 12 * k.h) {
+      const int pos = (code == MPC_STATUS_BAD_INPUT) ? -1 : k.posk[i / 3];
+      solution[i] = (ok && pos >= 0) ? k.x[3 * pos + (i % 3)] : 0.0;
+    }
+  }
+  MPC_ONE {
+    if (status) *status = (code & 0xff) | (sc->iters << 8);
+  }
+}
+
+// One problem, start to finish (everything but the outputs).  Returns the status code (uniform).
+template <class Cx>
+MPC_HD int ric_solve_problem(const Cx& cx, const float* rec, const unsigned char* gait, const RicWork& k, int max_iter) {
+  ric_setup(cx, rec, gait, k);
+  if (k.sc->status != MPC_STATUS_OPTIMAL) return k.sc->status;
+  ric_factor(cx, rec, k);
+  if (k.sc->status != MPC_STATUS_OPTIMAL) return k.sc->status;
+  ric_forward(cx, k, k.x0, true, k.h, k.x);  // x = -H^{-1} g
+  ric_active_set(cx, rec, gait, k, max_iter);
+  return k.sc->status;
+}
+
+}  // namespace mpc
+#endif

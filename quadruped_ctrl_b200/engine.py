@@ -46,7 +46,7 @@ class MpcError(RuntimeError):
 def build(force=False):
     """Compiles csrc/ for sm_100a into libquadruped_mpc_b200.so (nvcc cross-compiles without a GPU)."""
     src = os.path.join(_HERE, "csrc")
-    deps = [os.path.join(src, f) for f in ("mpc_engine.cu", "mpc_core.h", "mpc_ticks.h", "mpc_legs.h", "convexMPC_interface.cpp",
+    deps = [os.path.join(src, f) for f in ("mpc_engine.cu", "mpc_core.h", "mpc_riccati.h", "mpc_ticks.h", "mpc_legs.h", "convexMPC_interface.cpp",
                                            "Makefile")]
     deps += [os.path.join(_HERE, "..", "include", f) for f in ("mpc_batch.h", "convexMPC_interface.h")]
     stale = force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(map(os.path.getmtime, deps))

@@ -34,8 +34,10 @@ def emu_lib():
         core = os.path.join(ROOT, "quadruped_ctrl_b200", "csrc", "mpc_core.h")
         ticks = os.path.join(ROOT, "quadruped_ctrl_b200", "csrc", "mpc_ticks.h")
         legs = os.path.join(ROOT, "quadruped_ctrl_b200", "csrc", "mpc_legs.h")
+        ric = os.path.join(ROOT, "quadruped_ctrl_b200", "csrc", "mpc_riccati.h")
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core),
-                                                                 os.path.getmtime(ticks), os.path.getmtime(legs)):
+                                                                 os.path.getmtime(ticks), os.path.getmtime(legs),
+                                                                 os.path.getmtime(ric)):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Wno-unknown-pragmas", "-ffp-contract=off", "-fPIC", "-shared", src, "-o", so])
         _EMU = ctypes.CDLL(so)
     return _EMU
@@ -125,5 +127,20 @@ def emu_solve_wrench(rec, h, m_cap=0, max_iter=100000):
     vp = ctypes.c_void_p
     rc = L.emu_solve_batch_wrench(vp(rec.ctypes.data), B, h, m_cap, max_iter, vp(f.ctypes.data), vp(sol.ctypes.data),
                                   vp(info.ctypes.data))
+    assert rc == 0, rc
+    return dict(forces=f, sol=sol, nv=info[:, 0], m=info[:, 1], iters=info[:, 2], status=info[:, 3])
+
+
+def emu_solve_riccati(rec, h, nv_cap=0, m_cap=0, max_iter=100000):
+    """Host build of the Riccati solver (csrc/mpc_riccati.h): no condensed Hessian, H^{-1} products by sweeps."""
+    L = emu_lib()
+    rec = np.ascontiguousarray(rec, np.uint8)
+    B = rec.shape[0]
+    f = np.zeros((B, 12), np.float32)
+    sol = np.zeros((B, 12 * h))
+    info = np.zeros((B, 4), np.int32)
+    vp = ctypes.c_void_p
+    rc = L.emu_solve_batch_riccati(vp(rec.ctypes.data), B, h, nv_cap, m_cap, max_iter, vp(f.ctypes.data),
+                                   vp(sol.ctypes.data), vp(info.ctypes.data))
     assert rc == 0, rc
     return dict(forces=f, sol=sol, nv=info[:, 0], m=info[:, 1], iters=info[:, 2], status=info[:, 3])

@@ -12,6 +12,7 @@
 #include "../../quadruped_ctrl_b200/csrc/mpc_core.h"
 #include "../../quadruped_ctrl_b200/csrc/mpc_ticks.h"
 #include "../../quadruped_ctrl_b200/csrc/mpc_legs.h"
+#include "../../quadruped_ctrl_b200/csrc/mpc_riccati.h"
 
 static std::vector<double> g_dbg_u, g_dbg_minv;
 static std::vector<int> g_dbg_W;
@@ -144,6 +145,37 @@ int emu_solve_batch_wrench(const void* records, int batch, int h, int m_cap, int
     }
     int32_t st = 0;
     scatter(cx, k, forces + 12 * b, solution ? solution + (size_t)NU * b : nullptr, &st);
+    if (info) {
+      info[4 * b + 0] = k.sc->nv;
+      info[4 * b + 1] = k.sc->m;
+      info[4 * b + 2] = k.sc->iters;
+      info[4 * b + 3] = k.sc->status;
+    }
+  }
+  return 0;
+}
+
+// Riccati solver (csrc/mpc_riccati.h): the same problems without the condensed Hessian, one emulated thread.
+// info [batch*4]: nv, active-set size at exit, iterations, status code (STATUS_RETRY_BIG = 0x40 when m_cap is hit).
+int emu_solve_batch_riccati(const void* records, int batch, int h, int nv_cap, int m_cap, int max_iter, float* forces,
+                            double* solution, int* info) {
+  using namespace mpc;
+  if (nv_cap <= 0) nv_cap = 12 * h;
+  if (m_cap <= 0) m_cap = nv_cap;
+  const RicLayout L = make_ric_layout(h, nv_cap, m_cap);
+  std::vector<char> fast(L.bytes + 64);
+  const size_t stride = ((size_t)(4 * (MPC_REC_TRAJ + 12 * h) + 4 * h) + 15) / 16 * 16;
+  OneThreadT<false> cx{0, 1};
+  const int NU = 12 * h;
+  for (int b = 0; b < batch; b++) {
+    memset(fast.data(), 0xCD, fast.size());  // poison: nothing may rely on zeroed workspace
+    const RicWork k = ric_carve(L, fast.data());
+    const float* rec = (const float*)((const char*)records + stride * b);
+    const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * h);
+    ric_solve_problem(cx, rec, gait, k, max_iter);
+    if (k.sc->status == MPC_STATUS_OPTIMAL && k.sc->nv > nv_cap) return -1;
+    int32_t st = 0;
+    ric_scatter(cx, k, forces + 12 * b, solution ? solution + (size_t)NU * b : nullptr, &st);
     if (info) {
       info[4 * b + 0] = k.sc->nv;
       info[4 * b + 1] = k.sc->m;
