@@ -345,6 +345,7 @@ def run_config1(args):
     # device-resident figure: the same problem as a batch of one through the batched entry
     eng = E.MpcBatch(h, 1, 0)
     eng.set_sweep_variant(args.sweep)
+    eng.set_solver(args.solver)
     d = torch.from_numpy(rec[:1]).cuda()
     f = torch.empty((1, 12), dtype=torch.float32, device="cuda")
     st = torch.empty((1,), dtype=torch.int32, device="cuda")
@@ -378,7 +379,7 @@ def run_config1(args):
                    "note": "value: batch of one through mpc_batch_solve_device, back to back (launch-bound); e2e: %d "
                            "ticks through the legacy C interface from a C++ caller (tools/legacy_tick_bench.cpp)" % ticks,
                    "l2": "latency benchmark of a single problem: inputs are 720 bytes, L2 state is irrelevant",
-                   "sweep": args.sweep},
+                   "solver": args.solver, "sweep": args.sweep},
         "e2e": {"value": 1e6 / mean, "unit": UNIT, "h2d_bytes_per_step": R.record_stride(h),
                 "d2h_bytes_per_step": 12 * 4 + 4 + 12 * h * 8, "us_per_tick_median": med, "us_per_tick_p95": p95,
                 "api": "setup_problem / update_x_drag / update_solver_settings / update_problem_data_floats / "
@@ -438,6 +439,7 @@ def run_ours(args):
     gen = W.CONFIGS[cfg["key"]]
     eng = E.MpcBatch(h, B, local_rank)
     eng.set_sweep_variant(args.sweep)
+    eng.set_solver(args.solver)
     classes = eng.classes()
     stride = eng.stride
     # ---- synthetic inputs: distinct batches per rank, rotated so that every step reads cold (non-L2) inputs ----
@@ -661,7 +663,7 @@ def run_ours(args):
                        "collective": ("none (N=1)" if world == 1 else
                                       "peer stores from the solve kernel + device-side flag barrier (no NCCL on the path)" if peer else
                                       "all_gather_into_tensor of [N*B,12] fp32 forces on a communication stream of its own"),
-                       "sweep": eng.sweep_variant(), "classes": classes,
+                       "solver": eng.solver(), "sweep": eng.sweep_variant(), "classes": classes,
                        "problems_per_class": [int(x) for x in per_class]},
             "serial": {"value": serial_value, "unit": UNIT, "ms_per_batch": serial_ms / n_serial, "steps": n_serial,
                        "note": "one batch at a time on one stream (BASELINE configs are single batches)"},
@@ -712,6 +714,9 @@ def main():
     ap.add_argument("--e2e-slots", type=int, default=6, help="scratch slots the end-to-end leg rotates over (<= 6)")
     ap.add_argument("--sweep", default=os.environ.get("MPC_SWEEP", "fma"), choices=["fma", "mma"],
                     help="inversion of the register-resident classes: FP64 FMA pipe or FP64 tensor pipe (DMMA)")
+    ap.add_argument("--solver", default=os.environ.get("MPC_SOLVER", "riccati"), choices=["riccati", "inverse"],
+                    help="riccati: sweeps over the horizon, no condensed Hessian (default); inverse: explicit inverse of "
+                         "the reduced condensed Hessian")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
                     help="N>1: NCCL all-gather of the forces (default) or the kernel's fused peer-store epilogue")
     args = ap.parse_args()

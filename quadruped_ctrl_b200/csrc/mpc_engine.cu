@@ -58,6 +58,7 @@ struct SolveParams {
   char* slab;
   mpc::Layout L;
   mpc::RicLayout RL;  // workspace of the Riccati solver (mpc_solve_riccati_kernel)
+  int ric_generic;    // development switch (env MPC_RIC_GENERIC): the scalar generic factorisation instead of the DMMA one
   int max_iter;
   int warp_mode;
   float* peers[kMaxPeers];
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(32) mpc_solve_riccati_kernel(const __grid_cons
     const int b = P.list ? P.list[item] : item;
     const float* rec = (const float*)(recbuf + (size_t)cur * P.stride);
     const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
-    const int code = mpc::ric_solve_problem(cx, rec, gait, k, P.max_iter);
+    const int code = mpc::ric_solve_problem(cx, rec, gait, k, P.max_iter, P.ric_generic != 0);
     __syncwarp();
     if (code == mpc::STATUS_RETRY_BIG && P.retry_list) {
       if (lane == 0) {
@@ -691,6 +692,7 @@ struct mpc_batch {
   int sweep = MPC_SWEEP_DEFAULT;  // inversion of the register-resident classes: 0 FMA tiles, 1 DMMA grouped sweep
   int solver = MPC_SOLVER_DEFAULT;  // 0: explicit inverse of the condensed Hessian; 1: Riccati sweeps (mpc_riccati.h)
   int debug_stop = 0;
+  int ric_generic = 0;
   bool no_host_classify = false;  // env MPC_NO_HOST_CLASSIFY: batches of one take the general path too
   void* peer_open[kMaxPeers] = {nullptr};
   std::string err;
@@ -990,6 +992,7 @@ void fill_params(const mpc_batch* eng, int slot, SolveParams& P, const void* rec
   P.warp_mode = 1;
   P.phase_clk = eng->phase_clk;
   P.debug_stop = eng->debug_stop;
+  P.ric_generic = eng->ric_generic;
   P.warm_cache = eng->warm_cache;
   P.warm_ids = eng->warm_ids;
   P.warm_shift = eng->warm_shift;
@@ -1290,6 +1293,7 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
     }                                                                   \
   } while (0)
   if (const char* ds = getenv("MPC_DEBUG_STOP")) eng->debug_stop = atoi(ds);
+  if (const char* rg = getenv("MPC_RIC_GENERIC")) eng->ric_generic = atoi(rg);
   eng->no_host_classify = getenv("MPC_NO_HOST_CLASSIFY") != nullptr;
   if (const char* sw = getenv("MPC_SWEEP")) eng->sweep = (sw[0] == 'm' || sw[0] == '1') ? 1 : 0;  // "mma" / "fma"
   if (const char* sv = getenv("MPC_SOLVER")) eng->solver = (sv[0] == 'r' || sv[0] == '1') ? 1 : 0;  // "riccati" / "inverse"

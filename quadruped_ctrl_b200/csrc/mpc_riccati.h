@@ -38,7 +38,8 @@ struct RicLayout {
 };
 
 // doubles a problem's gains can take: per step 12 n_k (K_k) + n_k (n_k + 1) / 2 (S_k^{-1}, packed), n_k <= 12
-constexpr int ric_gain_doubles(int nv_cap) { return 12 * nv_cap + (13 * nv_cap + 1) / 2; }
+// (every step's block starts on an even offset: the DMMA factorisation stores two doubles at a time)
+constexpr int ric_gain_doubles(int nv_cap, int h) { return (12 * nv_cap + (13 * nv_cap + 1) / 2 + h + 1) / 2 * 2; }
 constexpr int kRicDyn = 8 + 12 + 36 + 36 + 12;  // scalars, Q, column form of N, row form of N, x0
 constexpr int kRicVec = 6 * 12;                 // pv, pn, xv, xn, wv, pt
 
@@ -49,7 +50,7 @@ inline RicLayout make_ric_layout(int h, int nv_cap, int m_cap) {
   L.m_cap = m_cap;
   L.ldT = m_cap | 1;
   L.ldz = nv_cap;
-  L.gain_cap = ric_gain_doubles(nv_cap);
+  L.gain_cap = ric_gain_doubles(nv_cap, h);
   int o = 0;
   L.off_sc = o;
   o += (int)((sizeof(Scalars) + 15) / 16 * 16);
@@ -75,8 +76,9 @@ inline RicLayout make_ric_layout(int h, int nv_cap, int m_cap) {
   L.off_red = o;
   o += 8 * kRedDoubles;
   L.off_un = o;
-  // union: factorisation scratch (P, Y, M, G 144 each; S 78; scol 12; Bc 156) | active set (Z, T, six vectors, ub)
-  const int fac = 4 * 144 + 78 + 12 + 156;
+  // union: factorisation scratch (P, Y, M 13 x 12 each; G, S 144; scol 2 x 16; Bc 156) | active set (Z, T, six
+  // vectors, ub)
+  const int fac = 3 * 156 + 2 * 144 + 32 + 156;
   const int as = nv_cap * m_cap + m_cap * L.ldT + 6 * (m_cap + 1) + 4 * h;
   o += 8 * (fac > as ? fac : as);
   L.bytes = (o + 15) / 16 * 16;
@@ -129,12 +131,12 @@ MPC_HD RicWork ric_carve(const RicLayout& L, char* fast) {
   k.red = (double*)(fast + L.off_red);
   double* un = (double*)(fast + L.off_un);
   k.P = un;
-  k.Y = k.P + 144;
-  k.M = k.Y + 144;
-  k.G = k.M + 144;
+  k.Y = k.P + 156;
+  k.M = k.Y + 156;
+  k.G = k.M + 156;
   k.S = k.G + 144;
-  k.scol = k.S + 78;
-  k.Bc = k.scol + 12;
+  k.scol = k.S + 144;
+  k.Bc = k.scol + 32;
   k.Z = un;
   k.T = k.Z + L.nv_cap * L.m_cap;
   k.w = k.T + L.m_cap * L.ldT;
@@ -307,7 +309,7 @@ MPC_HD void ric_setup(const Cx& cx, const float* rec, const unsigned char* gait,
       k.voff[s] = v;
       k.koff[s] = g;
       v += n;
-      g += 12 * n + n * (n + 1) / 2;
+      g += (12 * n + n * (n + 1) / 2 + 1) / 2 * 2;
     }
     k.voff[h] = v;
     k.koff[h] = g;
@@ -485,6 +487,306 @@ MPC_HD void ric_factor(const Cx& cx, const float* rec, const RicWork& k) {
     cx.sync();
   }
 }
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------
+// The same factorisation on the FP64 tensor pipe (device only): every product of a Riccati step is a handful of
+// DMMA.8x8x4 (mma.sync.m8n8k4.f64) on 8x8 tiles of the 12 x 12 state / 12 x n control blocks,
+//     M = P B_k        S = alpha I + B_k' M        G = M' A        K = S^{-1} G        Y = P A
+//     P <- Q + A'Y - G'K
+// 46 DMMAs per trot step instead of ~2400 scalar FMAs issued through shared-memory operands.  Fragment layout of
+// mma.m8n8k4.f64 (lane = 4*lr + lc): A[row lr][k lc], B[k lc][col lr], C[row lr][cols 2lc, 2lc+1].  All operands
+// are row-major with leading dimension 12 in shared memory: 12 = -4 (mod 16), so both fragment patterns
+// (rows by lr / k by lc, and k by lc / columns by lr) hit every 8-byte slot of a 128-byte wavefront exactly twice --
+// the minimum for 32 x 8 bytes.  Tiles are padded by predication: loads outside a matrix return 0, stores outside
+// are dropped.  The backward sweep of the tracking problem rides along in the padding: row 12 of P holds
+// pt' = (p + P a)', so row 12 of M = P B_k is w' = (B_k' pt)', row 12 of Y = P A is (A' pt)', column 12 of
+// K = S^{-1} [G | w] is kap, and row 12 of the new P comes out as (A' pt - K' w)'.
+// S (n <= 12, one or four tiles) is swept in registers, the pivot column broadcast through a double-buffered
+// 16-entry shared-memory line (one __syncwarp per pivot).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void ric_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// One backward step with NTU control tiles (0: no stance leg in this step, 1: n <= 6, 2: n = 9 or 12).
+template <int NTU>
+__device__ __forceinline__ bool ric_step_mma(const RicWork& k, const float* rec, int s, int lane, const double (&AB)[3][2]) {
+  constexpr int NT = NTU > 0 ? NTU : 1;  // array extents (unused when NTU == 0)
+  constexpr int KS = NTU == 2 ? 3 : 2;   // k-steps over the controls: 8 (n <= 6; rows 6, 7 of G are exact zeros) or 12
+  constexpr int KPAD = 4 * KS;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int n = k.nk[s], v0 = k.voff[s];
+  double *P = k.P, *Y = k.Y, *M = k.M, *G = k.G, *SF = k.S;  // SF: S^{-1}, full storage [KPAD x 12]
+  double* K = k.gain + k.koff[s];
+  double* Si = K + 12 * n;
+  const double* Bd = k.Bd;
+  bool bad = false;
+  int colB[NT];
+#pragma unroll
+  for (int tb = 0; tb < NT; tb++) {
+    const int c = 8 * tb + lr;
+    colB[tb] = (NTU > 0 && c < n) ? k.bcol[v0 + c] : -1;
+  }
+  // A fragments of P (rows 8t + lr <= 12, k = 4 s3 + lc): shared by M = P B and Y = P A
+  double pa[2][3];
+#pragma unroll
+  for (int t = 0; t < 2; t++)
+#pragma unroll
+    for (int s3 = 0; s3 < 3; s3++) pa[t][s3] = (8 * t + lr < 13) ? P[(8 * t + lr) * 12 + 4 * s3 + lc] : 0.0;
+  // ---- Y = P A (rows 0..12) ----
+  {
+    double y[2][2][2];
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        y[t][u][0] = y[t][u][1] = 0.0;
+#pragma unroll
+        for (int s3 = 0; s3 < 3; s3++) ric_dmma(y[t][u][0], y[t][u][1], pa[t][s3], AB[s3][u]);
+      }
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int r = 8 * t + lr, c = 8 * u + 2 * lc;
+        if (r < 13 && c < 12) *reinterpret_cast<double2*>(Y + r * 12 + c) = make_double2(y[t][u][0], y[t][u][1]);
+      }
+    __syncwarp();
+  }
+  if constexpr (NTU > 0) {
+    // ---- (1) M = P B_k (rows 0..12: row 12 is w') ----
+    double m[2][NT][2];
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+      for (int tb = 0; tb < NT; tb++) {
+        m[t][tb][0] = m[t][tb][1] = 0.0;
+#pragma unroll
+        for (int s3 = 0; s3 < 3; s3++) {
+          const double b = colB[tb] >= 0 ? Bd[(4 * s3 + lc) * 12 + colB[tb]] : 0.0;
+          ric_dmma(m[t][tb][0], m[t][tb][1], pa[t][s3], b);
+        }
+      }
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+      for (int tb = 0; tb < NT; tb++) {
+        const int r = 8 * t + lr, c = 8 * tb + 2 * lc;
+        if (r < 13 && c < 12) *reinterpret_cast<double2*>(M + r * 12 + c) = make_double2(m[t][tb][0], m[t][tb][1]);
+      }
+    __syncwarp();
+    // ---- (4) G = M' A (rows = controls < KPAD, columns = states) ----
+    {
+      double g[NT][2][2];
+#pragma unroll
+      for (int tc = 0; tc < NT; tc++) {
+        double ma[3];
+#pragma unroll
+        for (int s3 = 0; s3 < 3; s3++) ma[s3] = (8 * tc + lr < 12) ? M[(4 * s3 + lc) * 12 + 8 * tc + lr] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          g[tc][u][0] = g[tc][u][1] = 0.0;
+#pragma unroll
+          for (int s3 = 0; s3 < 3; s3++) ric_dmma(g[tc][u][0], g[tc][u][1], ma[s3], AB[s3][u]);
+          const int r = 8 * tc + lr, c = 8 * u + 2 * lc;
+          if (r < KPAD && c < 12) *reinterpret_cast<double2*>(G + r * 12 + c) = make_double2(g[tc][u][0], g[tc][u][1]);
+        }
+      }
+    }
+    // ---- (2) S = alpha I + B_k' M, all NTU x NTU tiles in registers ----
+    double sw[NT][NT][2];
+    {
+      const double alpha = k.dyn[4];
+#pragma unroll
+      for (int ta = 0; ta < NT; ta++)
+#pragma unroll
+        for (int tb = 0; tb < NT; tb++) {
+          sw[ta][tb][0] = (ta == tb && lr == 2 * lc) ? alpha : 0.0;
+          sw[ta][tb][1] = (ta == tb && lr == 2 * lc + 1) ? alpha : 0.0;
+#pragma unroll
+          for (int s3 = 0; s3 < 3; s3++) {
+            const double a = colB[ta] >= 0 ? Bd[(4 * s3 + lc) * 12 + colB[ta]] : 0.0;
+            const double b = (8 * tb + lr < 12) ? M[(4 * s3 + lc) * 12 + 8 * tb + lr] : 0.0;
+            ric_dmma(sw[ta][tb][0], sw[ta][tb][1], a, b);
+          }
+        }
+    }
+    // ---- (3) sweep: S <- -S^{-1}, pivots 0..n-1 (the padding keeps its alpha diagonal; it only ever meets the zero
+    //      rows of G) ----
+    double* scol = k.scol;  // [2][16]
+#pragma unroll 1
+    for (int p = 0; p < n; p++) {
+      double* cur = scol + 16 * (p & 1);
+      const int tp = p >> 3, pl = p & 7;
+#pragma unroll
+      for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int tb = 0; tb < NT; tb++)
+          if (tb == tp && lc == (pl >> 1)) cur[8 * t + lr] = (pl & 1) ? sw[t][tb][1] : sw[t][tb][0];
+      __syncwarp();
+      const double dp = cur[p];
+      const double dinv = fast_rcp(dp);
+      bad = bad || (unsigned)(__double2hiint(dinv) - 0x00100000) >= (unsigned)(0x7E37E43C - 0x00100000);
+#pragma unroll
+      for (int t = 0; t < NT; t++) {
+        const int r = 8 * t + lr;
+        const double cr = cur[r];
+#pragma unroll
+        for (int tb = 0; tb < NT; tb++) {
+          const double2 cc = *reinterpret_cast<const double2*>(cur + 8 * tb + 2 * lc);
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int c = 8 * tb + 2 * lc + e;
+            const double ccv = e ? cc.y : cc.x;
+            const double upd = fma(-cr * dinv, ccv, sw[t][tb][e]);
+            sw[t][tb][e] = (r == p) ? (c == p ? -dinv : ccv * dinv) : (c == p ? cr * dinv : upd);
+          }
+        }
+      }
+    }
+    // S^{-1} = -(swept): full copy for the K product, packed lower triangle into the gains
+#pragma unroll
+    for (int t = 0; t < NT; t++)
+#pragma unroll
+      for (int tb = 0; tb < NT; tb++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int r = 8 * t + lr, c = 8 * tb + 2 * lc + e;
+          const double v = -sw[t][tb][e];
+          if (r < KPAD && c < KPAD) SF[r * 12 + c] = (r < n && c < n) ? v : 0.0;
+          if (r < n && c <= r) Si[r * (r + 1) / 2 + c] = v;
+        }
+    __syncwarp();
+    // ---- (5) K = S^{-1} [G | w]: columns 0..11 the gain, column 12 kap ----
+    {
+#pragma unroll
+      for (int tc = 0; tc < NT; tc++) {
+        double sa[KS];
+#pragma unroll
+        for (int s2 = 0; s2 < KS; s2++) sa[s2] = (8 * tc + lr < KPAD) ? SF[(8 * tc + lr) * 12 + 4 * s2 + lc] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          double k0 = 0.0, k1 = 0.0;
+#pragma unroll
+          for (int s2 = 0; s2 < KS; s2++) {
+            const int cc = 4 * s2 + lc, j = 8 * u + lr;
+            const double b = j < 12 ? G[cc * 12 + j] : (j == 12 ? M[12 * 12 + cc] : 0.0);
+            ric_dmma(k0, k1, sa[s2], b);
+          }
+          const int r = 8 * tc + lr, c = 8 * u + 2 * lc;
+          if (r < n && c < 12) *reinterpret_cast<double2*>(K + r * 12 + c) = make_double2(k0, k1);
+          if (r < n && c == 12) k.kap[v0 + r] = k0;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // ---- (6) P <- Q + A'Y - G'K (rows 0..12; row 12 = (A' pt - K' w)') ----
+  {
+    double pn[2][2][2];
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (t == 0 && u == 1) continue;  // mirror of (1, 0)
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int s3 = 0; s3 < 3; s3++) {
+          const double b = (8 * u + lr < 12) ? Y[(4 * s3 + lc) * 12 + 8 * u + lr] : 0.0;
+          ric_dmma(c0, c1, AB[s3][t], b);
+        }
+        if constexpr (NTU > 0) {
+#pragma unroll
+          for (int s2 = 0; s2 < KS; s2++) {
+            const int cc = 4 * s2 + lc, i = 8 * t + lr;
+            const double a = i < 12 ? -G[cc * 12 + i] : (i == 12 ? -M[12 * 12 + cc] : 0.0);
+            const double b = (cc < n && 8 * u + lr < 12) ? K[cc * 12 + 8 * u + lr] : 0.0;
+            ric_dmma(c0, c1, a, b);
+          }
+        }
+        pn[t][u][0] = c0;
+        pn[t][u][1] = c1;
+      }
+    __syncwarp();  // everybody is done reading the old P (pa was loaded at the top) -- and Y, G, K of this step
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (t == 0 && u == 1) continue;
+        const int r = 8 * t + lr, c = 8 * u + 2 * lc;
+        if (r < 13 && c < 12) {
+          double v0n = pn[t][u][0], v1n = pn[t][u][1];
+          if (r == 12) {  // the identity part of A' on the padding row
+            v0n += Y[12 * 12 + c];
+            v1n += Y[12 * 12 + c + 1];
+          }
+          if (s >= 1 && r == c) v0n += k.Q[r];
+          if (s >= 1 && r == c + 1) v1n += k.Q[r];
+          *reinterpret_cast<double2*>(P + r * 12 + c) = make_double2(v0n, v1n);
+          if (t == 1 && u == 0 && r < 12) {
+            P[c * 12 + r] = v0n;
+            P[(c + 1) * 12 + r] = v1n;
+          }
+        }
+      }
+    __syncwarp();
+    // p = row 12 - Q xd_s;  pt = p + P a for the next step (a has two entries; P is symmetric)
+    if (lane < 12) {
+      double pv = P[12 * 12 + lane];
+      if (s >= 1) pv -= k.Q[lane] * (double)rec[MPC_REC_TRAJ + 12 * (s - 1) + lane];
+      P[12 * 12 + lane] = pv + k.dyn[5] * P[5 * 12 + lane] + k.dyn[6] * P[11 * 12 + lane];
+    }
+    __syncwarp();
+  }
+  return bad;
+}
+
+// requires the factorisation view of the union to hold P [13 x 12], Y [13 x 12], M [13 x 12], G [12 x 12],
+// S [12 x 12] and scol [2 x 16] (make_ric_layout)
+__device__ __forceinline__ void ric_factor_mma(const RicWork& k, const float* rec, int lane) {
+  const int h = k.h, lr = lane >> 2, lc = lane & 3;
+  // B fragments of A = I + N for X A (k = 4 s3 + lc, column 8u + lr); the A fragments of A' are the same numbers
+  double AB[3][2];
+#pragma unroll
+  for (int s3 = 0; s3 < 3; s3++)
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int l = 4 * s3 + lc, j = 8 * u + lr;
+      double v = 0.0;
+      if (j < 12) {
+        v = (l == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int t = 0; t < 3; t++) v += (k.NcI[3 * j + t] == l) ? k.NcV[3 * j + t] : 0.0;
+      }
+      AB[s3][u] = v;
+    }
+  // terminal cost: P = Q, p = -Q xd_h, pt = p + P a
+  for (int e = lane; e < 13 * 12; e += 32) {
+    const int i = e / 12, j = e - 12 * i;
+    double v = 0.0;
+    if (i < 12) v = (i == j) ? k.Q[i] : 0.0;
+    else v = -k.Q[j] * (double)rec[MPC_REC_TRAJ + 12 * (h - 1) + j] + (j == 5 ? k.dyn[5] * k.Q[5] : 0.0) +
+             (j == 11 ? k.dyn[6] * k.Q[11] : 0.0);
+    k.P[e] = v;
+  }
+  __syncwarp();
+  bool bad = false;
+#pragma unroll 1
+  for (int s = h - 1; s >= 0; s--) {
+    const int n = k.nk[s];
+    if (n == 0) bad |= ric_step_mma<0>(k, rec, s, lane, AB);
+    else if (n <= 6) bad |= ric_step_mma<1>(k, rec, s, lane, AB);
+    else bad |= ric_step_mma<2>(k, rec, s, lane, AB);
+  }
+  if (__any_sync(0xffffffffu, bad)) {
+    if (lane == 0) k.sc->status = MPC_STATUS_NOT_PD;
+    __syncwarp();
+  }
+}
+#endif  // __CUDACC__
 
 // Forward sweep: u_k = -K_k x_k - kap_k, x_{k+1} = A x_k + B_k u_k (+ a when `affine`: the tracking problem; the
 // products H^{-1} v are homogeneous), from x_0 = xstart (nullptr: 0).  kap_k counts as zero for steps > last.
@@ -819,9 +1121,14 @@ MPC_HD void ric_scatter(const Cx& cx, const RicWork& k, float* forces, double* s
 
 // One problem, start to finish (everything but the outputs).  Returns the status code (uniform).
 template <class Cx>
-MPC_HD int ric_solve_problem(const Cx& cx, const float* rec, const unsigned char* gait, const RicWork& k, int max_iter) {
+MPC_HD int ric_solve_problem(const Cx& cx, const float* rec, const unsigned char* gait, const RicWork& k, int max_iter,
+                             bool generic = false) {
   ric_setup(cx, rec, gait, k);
   if (k.sc->status != MPC_STATUS_OPTIMAL) return k.sc->status;
+#if defined(__CUDA_ARCH__)
+  if (Cx::kOneWarp && !generic) ric_factor_mma(k, rec, cx.tid);
+  else
+#endif
   ric_factor(cx, rec, k);
   if (k.sc->status != MPC_STATUS_OPTIMAL) return k.sc->status;
   ric_forward(cx, k, k.x0, true, k.h, k.x);  // x = -H^{-1} g

@@ -29,7 +29,7 @@ BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_creat
                  "mpc_batch_assemble_device", "mpc_batch_build_records_device", "mpc_batch_solve_ticks_device",
                  "mpc_batch_gait_state_device", "mpc_batch_leg_commands_device",
                  "mpc_batch_set_gather_peers", "mpc_batch_gather_alloc", "mpc_batch_gather_connect",
-                 "mpc_batch_gather_buffer", "mpc_batch_gather_buffer_slot", "mpc_batch_gather_sync", "mpc_batch_gather_sync_slot", "mpc_batch_set_max_iterations", "mpc_batch_set_warm_start", "mpc_batch_warm_stride", "mpc_batch_set_sweep_variant", "mpc_batch_sweep_variant", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
+                 "mpc_batch_gather_buffer", "mpc_batch_gather_buffer_slot", "mpc_batch_gather_sync", "mpc_batch_gather_sync_slot", "mpc_batch_set_max_iterations", "mpc_batch_set_warm_start", "mpc_batch_warm_stride", "mpc_batch_set_sweep_variant", "mpc_batch_sweep_variant", "mpc_batch_set_solver", "mpc_batch_solver", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
                  "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
                  "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_class_kernel_ms", "mpc_batch_timing_mark",
                  "mpc_batch_timing_collect", "mpc_batch_host_buffers", "mpc_batch_device_buffers",
@@ -100,6 +100,8 @@ def lib():
     L.mpc_batch_set_warm_start.argtypes = [vp, vp, vp, i32]
     L.mpc_batch_set_sweep_variant.argtypes = [vp, i32]
     L.mpc_batch_sweep_variant.argtypes = [vp]
+    L.mpc_batch_set_solver.argtypes = [vp, i32]
+    L.mpc_batch_solver.argtypes = [vp]
     L.mpc_batch_set_timing.argtypes = [vp, i32]
     L.mpc_batch_set_timed_class.argtypes = [vp, i32]
     L.mpc_batch_set_phase_clock_buffer.argtypes = [vp, vp]
@@ -202,6 +204,15 @@ class MpcBatch:
 
     def sweep_variant(self):
         return "mma" if self._L.mpc_batch_sweep_variant(self._h) == 1 else "fma"
+
+    def set_solver(self, solver):
+        """1 / "riccati" (default): Riccati sweeps, the condensed Hessian is never formed (csrc/mpc_riccati.h);
+        0 / "inverse": explicit inverse of the reduced condensed Hessian (csrc/mpc_core.h)."""
+        v = {"inverse": 0, "riccati": 1}.get(solver, solver)
+        self._check(self._L.mpc_batch_set_solver(self._h, int(v)), "set_solver")
+
+    def solver(self):
+        return "riccati" if self._L.mpc_batch_solver(self._h) == 1 else "inverse"
 
     def set_timing(self, on):
         self._check(self._L.mpc_batch_set_timing(self._h, int(bool(on))), "set_timing")
