@@ -54,10 +54,10 @@ inline RicLayout make_ric_layout(int h, int nv_cap, int m_cap) {
   int o = 0;
   L.off_sc = o;
   o += (int)((sizeof(Scalars) + 15) / 16 * 16);
-  // ints: stance, posk, amask [4h each]; nk [h]; voff, koff [h+1 each]; bcol [nv_cap]; W, Wia, Wiz [m_cap+1 each];
-  // NcI, NrI [36 each]
+  // ints: step [h][4] (n_k, voff, koff, swing mask: one 16-byte load per step); stance, posk, amask [4h each]; nk [h];
+  // voff, koff [h+1 each]; bcol [nv_cap]; W, Wia, Wiz [m_cap+1 each]; NcI, NrI [36 each]
   L.off_ints = o;
-  o += 4 * (12 * h + h + 2 * (h + 1) + nv_cap + 3 * (m_cap + 1) + 72);
+  o += 4 * (4 * h + 12 * h + h + 2 * (h + 1) + nv_cap + 3 * (m_cap + 1) + 72);
   o = (o + 15) / 16 * 16;
   L.off_dyn = o;
   o += 8 * kRicDyn;
@@ -76,9 +76,9 @@ inline RicLayout make_ric_layout(int h, int nv_cap, int m_cap) {
   L.off_red = o;
   o += 8 * kRedDoubles;
   L.off_un = o;
-  // union: factorisation scratch (P, Y, M 13 x 12 each; G, S 144; scol 2 x 16; Bc 156) | active set (Z, T, six
+  // union: factorisation scratch (P, Y, M 13 x 12 each; G, S 144; scol 2 x 18; Bc 156) | active set (Z, T, six
   // vectors, ub)
-  const int fac = 3 * 156 + 2 * 144 + 32 + 156;
+  const int fac = 3 * 156 + 2 * 144 + 36 + 156;
   const int as = nv_cap * m_cap + m_cap * L.ldT + 6 * (m_cap + 1) + 4 * h;
   o += 8 * (fac > as ? fac : as);
   L.bytes = (o + 15) / 16 * 16;
@@ -87,7 +87,7 @@ inline RicLayout make_ric_layout(int h, int nv_cap, int m_cap) {
 
 struct RicWork {
   Scalars* sc;
-  int *stance, *posk, *amask, *nk, *voff, *koff, *bcol, *W, *Wia, *Wiz, *NcI, *NrI;
+  int *step, *stance, *posk, *amask, *nk, *voff, *koff, *bcol, *W, *Wia, *Wiz, *NcI, *NrI;
   double *dyn, *Q, *NcV, *NrV, *x0, *Bd, *gain, *x, *d, *kap, *pv, *pn, *xv, *xn, *wv, *pt, *red;
   double *P, *Y, *M, *G, *S, *scol, *Bc;              // factorisation view of the union
   double *Z, *T, *w, *r, *u, *tcol, *Wca, *Wcz, *ub;  // active-set view
@@ -100,6 +100,8 @@ MPC_HD RicWork ric_carve(const RicLayout& L, char* fast) {
   RicWork k;
   k.sc = (Scalars*)(fast + L.off_sc);
   int* ip = (int*)(fast + L.off_ints);
+  k.step = ip;
+  ip += 4 * L.h;
   k.stance = ip;
   k.posk = ip + 4 * L.h;
   k.amask = ip + 8 * L.h;
@@ -136,7 +138,7 @@ MPC_HD RicWork ric_carve(const RicLayout& L, char* fast) {
   k.G = k.M + 156;
   k.S = k.G + 144;
   k.scol = k.S + 144;
-  k.Bc = k.scol + 32;
+  k.Bc = k.scol + 36;
   k.Z = un;
   k.T = k.Z + L.nv_cap * L.m_cap;
   k.w = k.T + L.m_cap * L.ldT;
@@ -198,6 +200,24 @@ MPC_HD void ric_setup(const Cx& cx, const float* rec, const unsigned char* gait,
         !(fmax >= 0.f))
       sc->status = MPC_STATUS_BAD_INPUT;
   }
+#if defined(__CUDA_ARCH__)
+  if (Cx::kOneWarp) {  // prefix count by ballots, 32 table entries per round
+    int base = 0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < 4 * h; k0 += 32) {
+      const int kk = k0 + cx.tid;
+      const int f = kk < 4 * h ? flag[kk] : 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, f != 0);
+      const int pos = base + __popc(bal & ((1u << cx.tid) - 1u));
+      if (kk < 4 * h) {
+        if (f) { k.stance[pos] = kk; k.posk[kk] = pos; }
+        else k.posk[kk] = -1;
+      }
+      base += __popc(bal);
+    }
+    MPC_ONE { sc->ns = base; sc->nv = 3 * base; }
+  } else
+#endif
   MPC_FOR(kk, 4 * h) {
     int pos = 0;
 #pragma unroll 4
@@ -218,6 +238,19 @@ MPC_HD void ric_setup(const Cx& cx, const float* rec, const unsigned char* gait,
       k.dyn[1] = cy;
       k.dyn[2] = sy;
     }
+#if defined(__CUDA_ARCH__)
+    if (Cx::kOneWarp) {
+      // the three angles through ONE atan2 call on lanes 1..3 (a warp runs divergent calls one after the other):
+      // asin(s) = atan2(s, sqrt(1 - s^2))
+      double as = -2. * (qx * qz - qw * qy);
+      if (!(as < .99999)) as = .99999;
+      const double yy = cx.tid == 1 ? 2. * (qx * qy + qw * qz) : (cx.tid == 2 ? as : 2. * (qy * qz + qw * qx));
+      const double xx = cx.tid == 1 ? qw * qw + qx * qx - qy * qy - qz * qz
+                                    : (cx.tid == 2 ? sqrt(fma(-as, as, 1.0)) : qw * qw - qx * qx - qy * qy + qz * qz);
+      if (cx.tid >= 1 && cx.tid <= 3) k.x0[3 - cx.tid] = MPC_ATAN2(yy, xx);
+    } else
+#endif
+    {
     if (cx.tid == l1) k.x0[2] = MPC_ATAN2(2. * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
     if (cx.tid == l2) {
       double as = -2. * (qx * qz - qw * qy);
@@ -225,6 +258,7 @@ MPC_HD void ric_setup(const Cx& cx, const float* rec, const unsigned char* gait,
       k.x0[1] = asin(as);
     }
     if (cx.tid == l3) k.x0[0] = MPC_ATAN2(2. * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
+    }
   }
   cx.sync();
   const double dt = (double)rec[MPC_REC_DT];
@@ -308,6 +342,10 @@ MPC_HD void ric_setup(const Cx& cx, const float* rec, const unsigned char* gait,
       k.nk[s] = n;
       k.voff[s] = v;
       k.koff[s] = g;
+      int swm = 0;  // leg columns (of B_d) whose leg is in swing at this step
+      for (int l = 0; l < 4; l++)
+        if (!flag[4 * s + l]) swm |= 7 << (3 * l);
+      k.step[4 * s] = n; k.step[4 * s + 1] = v; k.step[4 * s + 2] = g; k.step[4 * s + 3] = swm;
       v += n;
       g += (12 * n + n * (n + 1) / 2 + 1) / 2 * 2;
     }
@@ -616,34 +654,37 @@ __device__ __forceinline__ bool ric_step_mma(const RicWork& k, const float* rec,
     }
     // ---- (3) sweep: S <- -S^{-1}, pivots 0..n-1 (the padding keeps its alpha diagonal; it only ever meets the zero
     //      rows of G) ----
-    double* scol = k.scol;  // [2][16]
+    // Uniform rank-1 update (as invert_spd_tiles): the pivot column is published with slot p holding d - 1, so that
+    // a_rc -= (c_r / d) c_c gives a_rc - c_r c_c / d off the pivot, c_c / d on the pivot row / column and 2 - 1/d at
+    // (p, p) -- no per-element case distinction; every swept diagonal entry ends exactly 2 above its true value.
+    double* scol = k.scol;  // [2][18]: the pivot column (16 slots) and d (slot 16), double buffered
 #pragma unroll 1
     for (int p = 0; p < n; p++) {
-      double* cur = scol + 16 * (p & 1);
+      double* cur = scol + 18 * (p & 1);
       const int tp = p >> 3, pl = p & 7;
+      if (lc == (pl >> 1)) {
 #pragma unroll
-      for (int t = 0; t < NT; t++)
+        for (int t = 0; t < NT; t++)
 #pragma unroll
-        for (int tb = 0; tb < NT; tb++)
-          if (tb == tp && lc == (pl >> 1)) cur[8 * t + lr] = (pl & 1) ? sw[t][tb][1] : sw[t][tb][0];
+          for (int tb = 0; tb < NT; tb++)
+            if (tb == tp) {
+              const double v = (pl & 1) ? sw[t][tb][1] : sw[t][tb][0];
+              const bool diag = 8 * t + lr == p;
+              cur[8 * t + lr] = diag ? v - 1.0 : v;
+              if (diag) cur[16] = v;
+            }
+      }
       __syncwarp();
-      const double dp = cur[p];
-      const double dinv = fast_rcp(dp);
+      const double dinv = fast_rcp(cur[16]);
       bad = bad || (unsigned)(__double2hiint(dinv) - 0x00100000) >= (unsigned)(0x7E37E43C - 0x00100000);
 #pragma unroll
       for (int t = 0; t < NT; t++) {
-        const int r = 8 * t + lr;
-        const double cr = cur[r];
+        const double ur = -cur[8 * t + lr] * dinv;
 #pragma unroll
         for (int tb = 0; tb < NT; tb++) {
           const double2 cc = *reinterpret_cast<const double2*>(cur + 8 * tb + 2 * lc);
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int c = 8 * tb + 2 * lc + e;
-            const double ccv = e ? cc.y : cc.x;
-            const double upd = fma(-cr * dinv, ccv, sw[t][tb][e]);
-            sw[t][tb][e] = (r == p) ? (c == p ? -dinv : ccv * dinv) : (c == p ? cr * dinv : upd);
-          }
+          sw[t][tb][0] = fma(ur, cc.x, sw[t][tb][0]);
+          sw[t][tb][1] = fma(ur, cc.y, sw[t][tb][1]);
         }
       }
     }
@@ -655,7 +696,7 @@ __device__ __forceinline__ bool ric_step_mma(const RicWork& k, const float* rec,
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int r = 8 * t + lr, c = 8 * tb + 2 * lc + e;
-          const double v = -sw[t][tb][e];
+          const double v = (r == c) ? 2.0 - sw[t][tb][e] : -sw[t][tb][e];
           if (r < KPAD && c < KPAD) SF[r * 12 + c] = (r < n && c < n) ? v : 0.0;
           if (r < n && c <= r) Si[r * (r + 1) / 2 + c] = v;
         }
@@ -745,7 +786,7 @@ __device__ __forceinline__ bool ric_step_mma(const RicWork& k, const float* rec,
 }
 
 // requires the factorisation view of the union to hold P [13 x 12], Y [13 x 12], M [13 x 12], G [12 x 12],
-// S [12 x 12] and scol [2 x 16] (make_ric_layout)
+// S [12 x 12] and scol [2 x 18] (make_ric_layout)
 __device__ __forceinline__ void ric_factor_mma(const RicWork& k, const float* rec, int lane) {
   const int h = k.h, lr = lane >> 2, lc = lane & 3;
   // B fragments of A = I + N for X A (k = 4 s3 + lc, column 8u + lr); the A fragments of A' are the same numbers
@@ -896,14 +937,169 @@ MPC_HD void ric_hinv_row(const Cx& cx, const RicWork& k, const Row& rp, double* 
   ric_forward(cx, k, nullptr, false, kp, out);
 }
 
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------
+// The sweeps on one warp with the state / costate in registers (device only).  Lane i < 12 owns component i of the
+// 12-vector that travels along the horizon, row i of B_d and row i of the sparse part of A (or column i, for the
+// costate) in registers; a step is two phases with one __syncwarp each:
+//   forward   u = -(K x + kap)   (lanes c < n: one 12-term dot, three chains)   |   x' = A x + B_d u_full
+//   backward  w = B_k' p         (lanes c < n)                                  |   kap = S^{-1} w  and  p' = A'p - K'w
+// u_full is u scattered into the 12 leg columns (zeros for swing legs), so that the B_d product runs over
+// compile-time register indices.
+// ---------------------------------------------------------------------------
+struct RicLaneConst {
+  double brow[12];        // row `lane` of B_d
+  int ri[3], ci[3];       // sparse part N = A - I: row form / column form entries of row / column `lane`
+  double rv[3], cv[3];
+};
+__device__ __forceinline__ RicLaneConst ric_lane_const(const RicWork& k, int lane) {
+  RicLaneConst L;
+  const int i = lane < 12 ? lane : 0;
+#pragma unroll
+  for (int j = 0; j < 12; j += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(k.Bd + i * 12 + j);
+    L.brow[j] = v.x;
+    L.brow[j + 1] = v.y;
+  }
+#pragma unroll
+  for (int t = 0; t < 3; t++) {
+    L.ri[t] = k.NrI[3 * i + t]; L.rv[t] = k.NrV[3 * i + t];
+    L.ci[t] = k.NcI[3 * i + t]; L.cv[t] = k.NcV[3 * i + t];
+  }
+  return L;
+}
+
+// out[v] = u of every step, from x_0 = xstart (nullptr: 0); kap_k counts as zero for steps > last; `affine` adds a.
+__device__ __forceinline__ void ric_forward_fast(const RicWork& k, const RicLaneConst& L, const double* xstart, bool affine,
+                                                 int last, double* out, int lane) {
+  const int h = k.h;
+  double xi = (lane < 12 && xstart) ? xstart[lane] : 0.0;
+  const double ai = !affine ? 0.0 : (lane == 5 ? k.dyn[5] : (lane == 11 ? k.dyn[6] : 0.0));
+  double* uf = k.pt;  // u scattered to leg columns
+#pragma unroll 1
+  for (int s = 0; s < h; s++) {
+    const int4 si = *reinterpret_cast<const int4*>(k.step + 4 * s);  // n_k, voff, koff, swing mask
+    const int n = si.x, v0 = si.y;
+    double* xs = (s & 1) ? k.xn : k.xv;
+    if (lane < 12) xs[lane] = xi;
+    __syncwarp();
+    if ((si.w >> lane) & 1) uf[lane] = 0.0;  // swing leg: no force
+    if (lane < n) {
+      const double* Kr = k.gain + si.z + lane * 12;
+      double a0 = (s <= last) ? k.kap[v0 + lane] : 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 12; j += 6) {
+        const double2 k0 = *reinterpret_cast<const double2*>(Kr + j), k1 = *reinterpret_cast<const double2*>(Kr + j + 2),
+                      k2 = *reinterpret_cast<const double2*>(Kr + j + 4);
+        const double2 x0 = *reinterpret_cast<const double2*>(xs + j), x1 = *reinterpret_cast<const double2*>(xs + j + 2),
+                      x2 = *reinterpret_cast<const double2*>(xs + j + 4);
+        a0 = fma(k0.x, x0.x, a0); a1 = fma(k1.x, x1.x, a1); a2 = fma(k2.x, x2.x, a2);
+        a0 = fma(k0.y, x0.y, a0); a1 = fma(k1.y, x1.y, a1); a2 = fma(k2.y, x2.y, a2);
+      }
+      const double u = -((a0 + a1) + a2);
+      out[v0 + lane] = u;
+      uf[k.bcol[v0 + lane]] = u;
+    }
+    if (s == h - 1) break;  // the state after the last step is not needed
+    __syncwarp();
+    if (lane < 12) {
+      double a0 = xi + ai, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+      for (int t = 0; t < 3; t++) a1 = fma(L.rv[t], xs[L.ri[t]], a1);
+#pragma unroll
+      for (int j = 0; j < 12; j += 4) {
+        const double2 u0 = *reinterpret_cast<const double2*>(uf + j), u1 = *reinterpret_cast<const double2*>(uf + j + 2);
+        a0 = fma(L.brow[j], u0.x, a0); a2 = fma(L.brow[j + 2], u1.x, a2);
+        a0 = fma(L.brow[j + 1], u0.y, a0); a2 = fma(L.brow[j + 3], u1.y, a2);
+      }
+      xi = (a0 + a1) + a2;
+    }
+    // (the next step writes the other xs buffer; uf is rewritten only after the next __syncwarp)
+  }
+  __syncwarp();
+}
+
+// out = H^{-1} n for a catalogue row (see ric_hinv_row)
+__device__ __forceinline__ void ric_hinv_row_fast(const RicWork& k, const RicLaneConst& L, const Row& rp, double* out, int lane) {
+  const int kp = k.stance[rp.iz / 3] >> 2;
+  double pj = 0.0;  // lane j < 12: costate component j
+  double* ws = k.wv;
+#pragma unroll 1
+  for (int s = kp; s >= 0; s--) {
+    const int4 si = *reinterpret_cast<const int4*>(k.step + 4 * s);
+    const int n = si.x, v0 = si.y;
+    const double* K = k.gain + si.z;
+    const double* Si = K + 12 * n;
+    double* ps = (s & 1) ? k.pn : k.pv;
+    if (s == kp) {  // w = -n/2 on the variables of this step
+      if (lane < n) ws[lane] = -0.5 * ((v0 + lane == rp.ia ? rp.ca : 0.0) + (v0 + lane == rp.iz ? rp.cz : 0.0));
+      if (lane < 12) ps[lane] = 0.0;
+    } else {
+      if (lane < 12) ps[lane] = pj;
+      __syncwarp();
+      if (lane < n) {
+        const double* Bc = k.Bd + k.bcol[v0 + lane];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 12; i += 6) {
+          const double2 p0 = *reinterpret_cast<const double2*>(ps + i), p1 = *reinterpret_cast<const double2*>(ps + i + 2),
+                        p2 = *reinterpret_cast<const double2*>(ps + i + 4);
+          a0 = fma(Bc[12 * i], p0.x, a0); a1 = fma(Bc[12 * (i + 2)], p1.x, a1); a2 = fma(Bc[12 * (i + 4)], p2.x, a2);
+          a0 = fma(Bc[12 * (i + 1)], p0.y, a0); a1 = fma(Bc[12 * (i + 3)], p1.y, a1); a2 = fma(Bc[12 * (i + 5)], p2.y, a2);
+        }
+        ws[lane] = (a0 + a1) + a2;
+      }
+    }
+    __syncwarp();
+    if (lane < n) {  // kap = S^{-1} w (packed lower triangle, row `lane`)
+      double a0 = 0.0, a1 = 0.0;
+      const int base = lane * (lane + 1) / 2;
+#pragma unroll 1
+      for (int b = 0; b < n; b += 2) {
+        const int i0 = b <= lane ? base + b : b * (b + 1) / 2 + lane;
+        const int b1 = b + 1;
+        const int i1 = b1 <= lane ? base + b1 : b1 * (b1 + 1) / 2 + lane;
+        a0 = fma(Si[i0], ws[b], a0);
+        if (b1 < n) a1 = fma(Si[i1], ws[b1], a1);
+      }
+      k.kap[v0 + lane] = a0 + a1;
+    }
+    if (lane < 12) {  // p' = A'p - K'w
+      double a0 = pj, a1 = 0.0;
+      if (s != kp) {
+#pragma unroll
+        for (int t = 0; t < 3; t++) a1 = fma(L.cv[t], ps[L.ci[t]], a1);
+      }
+      const double* Kc = K + lane;
+#pragma unroll 1
+      for (int c = 0; c < n; c += 3) {  // n is a multiple of 3
+        a0 = fma(-Kc[12 * c], ws[c], a0);
+        a1 = fma(-Kc[12 * (c + 1)], ws[c + 1], a1);
+        a0 = fma(-Kc[12 * (c + 2)], ws[c + 2], a0);
+      }
+      pj = a0 + a1;
+    }
+    // ws is rewritten only after the next __syncwarp (the ps store of the next step comes first and goes to the
+    // other buffer)
+  }
+  __syncwarp();
+  ric_forward_fast(k, L, nullptr, false, kp, out, lane);
+}
+#endif  // __CUDACC__
+
 // ---------------------------------------------------------------------------
 // Goldfarb-Idnani dual active set with H^{-1} products from the Riccati sweeps.  Same selection rule, tolerances,
 // step rules and T updates as mpc_core.h's active_set; rows of H^{-1} are replaced by the stored columns
 // Z[:, a] = H^{-1} n_a of the working set and d = H^{-1} n_p of the entering row.
 // ---------------------------------------------------------------------------
 template <class Cx>
-MPC_HD void ric_active_set(const Cx& cx, const float* rec, const unsigned char* gait, const RicWork& k, int max_iter) {
+MPC_HD void ric_active_set(const Cx& cx, const float* rec, const unsigned char* gait, const RicWork& k, int max_iter,
+                           bool generic = false) {
   Scalars* sc = k.sc;
+#if defined(__CUDA_ARCH__)
+  const RicLaneConst LC = ric_lane_const(k, cx.tid & 31);
+#endif
+  (void)generic;
   const int nv = sc->nv, ns = sc->ns, ldT = k.ldT, ldz = k.ldz;
   const double mu_inv = k.dyn[7];
   double* T = k.T;
@@ -945,6 +1141,10 @@ MPC_HD void ric_active_set(const Cx& cx, const float* rec, const unsigned char* 
     const double bp = (p % 6 == 5) ? -k.ub[p / 6] : 0.0;
     cx.sync();
     MPC_ONE { sc->iters++; sc->up = 0.0; }
+#if defined(__CUDA_ARCH__)
+    if (Cx::kOneWarp && !generic) ric_hinv_row_fast(k, LC, rp, d, cx.tid);
+    else
+#endif
     ric_hinv_row(cx, k, rp, d);  // (ends with a sync)
     const double vnp = rp.ca * d[rp.ia] + rp.cz * d[rp.iz];
     bool fail = false;
@@ -1131,8 +1331,12 @@ MPC_HD int ric_solve_problem(const Cx& cx, const float* rec, const unsigned char
 #endif
   ric_factor(cx, rec, k);
   if (k.sc->status != MPC_STATUS_OPTIMAL) return k.sc->status;
+#if defined(__CUDA_ARCH__)
+  if (Cx::kOneWarp && !generic) ric_forward_fast(k, ric_lane_const(k, cx.tid), k.x0, true, k.h, k.x, cx.tid);
+  else
+#endif
   ric_forward(cx, k, k.x0, true, k.h, k.x);  // x = -H^{-1} g
-  ric_active_set(cx, rec, gait, k, max_iter);
+  ric_active_set(cx, rec, gait, k, max_iter, generic);
   return k.sc->status;
 }
 

@@ -28,8 +28,10 @@ def cuda_engine_factory():
     from quadruped_ctrl_b200 import engine as E
     made = []
 
-    def make(horizon, max_batch):
+    def make(horizon, max_batch, solver=None):
         e = E.MpcBatch(horizon, max_batch, 0)
+        if solver is not None:
+            e.set_solver(solver)   # "riccati" (the default) or "inverse"
         made.append(e)
         return e
 

@@ -30,12 +30,16 @@ CASES = [("config1", None), ("config2", 512), ("config4", 512), ("four_stance", 
          ("config3", 192)]
 
 
+@pytest.mark.parametrize("solver", ["riccati", "inverse"])
 @pytest.mark.parametrize("name,batch", CASES)
-def test_forces_match_oracle(name, batch, oracle, cuda_engine_factory):
+def test_forces_match_oracle(name, batch, solver, oracle, cuda_engine_factory):
+    """Both solvers: Riccati sweeps (csrc/mpc_riccati.h, the default) and the explicit inverse of the condensed Hessian
+    (csrc/mpc_core.h)."""
     h = W.HORIZONS[name]
     rec = W.CONFIGS[name]() if batch is None else W.CONFIGS[name](batch)
     B = rec.shape[0]
-    eng = cuda_engine_factory(h, B)
+    eng = cuda_engine_factory(h, B, solver)
+    assert eng.solver() == solver
     forces, sol, status = eng.solve_host(rec, want_solution=True)
     code = E.status_code(status)
     assert (code == E.STATUS_OPTIMAL).all(), np.bincount(code)
@@ -45,7 +49,7 @@ def test_forces_match_oracle(name, batch, oracle, cuda_engine_factory):
     ok64 = o64["rc"] == 0
     # whole 12h solution against the fp64 truth
     e64 = rel(sol, o64["sol"])
-    print("\n[%s] B=%d backend=%s  |gpu-o64| max %.2e  med %.2e" % (name, B, backend, e64[ok64].max(), np.median(e64)))
+    print("\n[%s/%s] B=%d backend=%s  |gpu-o64| max %.2e  med %.2e" % (name, solver, B, backend, e64[ok64].max(), np.median(e64)))
     assert e64[ok64].max() < 1e-9   # agreement with the reference solver to round-off (fp64 QP)
     # first-step forces against the reference-faithful fp32 path, on its well-conditioned set
     cloud = rel(o32["forces"], o64["forces"])
@@ -89,12 +93,13 @@ def test_device_entry_matches_host_entry(cuda_engine_factory):
     assert (st_dev.cpu().numpy() == st_host).all()
 
 
+@pytest.mark.parametrize("solver", ["riccati", "inverse"])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_golden_fixture(name, cuda_engine_factory):
+def test_golden_fixture(name, solver, cuda_engine_factory):
     """Committed fixture (reference qpOASES outputs generated in the build container): no oracle needed."""
     G = load_golden()
     rec, h = G[name + "_records"], int(G[name + "_h"])
-    eng = cuda_engine_factory(h, rec.shape[0])
+    eng = cuda_engine_factory(h, rec.shape[0], solver)
     forces, sol, status = eng.solve_host(rec, want_solution=True)
     assert (E.status_code(status) == E.STATUS_OPTIMAL).all()
     ok = G[name + "_o64_rc"] == 0
@@ -176,13 +181,14 @@ def test_cpp_caller_stub_matches_oracle(oracle):
         assert rel(got[None], ref["forces"][:1].astype(np.float64))[0] < 1e-6
 
 
+@pytest.mark.parametrize("solver", ["riccati", "inverse"])
 @pytest.mark.parametrize("h", [1, 2, 9, 36])
-def test_extreme_horizons(h, oracle, cuda_engine_factory):
+def test_extreme_horizons(h, solver, oracle, cuda_engine_factory):
     """Horizon 1 and 2 (smallest problems), 9 (the last horizon whose gait table fits update_data_t.gait without
     running on into hack_pad) and 36 (K_MAX_GAIT_SEGMENTS, the largest the reference's structs can carry: trot
     nv = 216, four-stance nv = 432 -- the catch-all class with its grouped sweep)."""
     rec = np.concatenate([W.config2(6, h, 70 + h), W.four_stance(3, h, 80 + h)])
-    eng = cuda_engine_factory(h, rec.shape[0])
+    eng = cuda_engine_factory(h, rec.shape[0], solver)
     f, s, st = eng.solve_device(torch.from_numpy(rec).cuda(), want_solution=True)
     torch.cuda.synchronize()
     o = oracle.solve_batch(rec, h, 64)
@@ -193,7 +199,8 @@ def test_extreme_horizons(h, oracle, cuda_engine_factory):
     assert ok.sum() >= 3
 
 
-def test_status_codes_and_failure_outputs(cuda_engine_factory):
+@pytest.mark.parametrize("solver", ["riccati", "inverse"])
+def test_status_codes_and_failure_outputs(solver, cuda_engine_factory):
     from quadruped_ctrl_b200 import records as R
     h = 10
     rec = W.config2(6, h, 5)
@@ -204,14 +211,14 @@ def test_status_codes_and_failure_outputs(cuda_engine_factory):
     f[2, R.REC_MU] = 0.0
     f[3, R.REC_MASS] = -1.0
     f[4, R.REC_FMAX] = 0.001
-    eng = cuda_engine_factory(h, 6)
+    eng = cuda_engine_factory(h, 6, solver)
     forces, sol, status = eng.solve_host(rec, want_solution=True)
     assert E.status_code(status).tolist() == [E.STATUS_NO_STANCE, E.STATUS_BAD_INPUT, E.STATUS_BAD_INPUT,
                                               E.STATUS_BAD_INPUT, E.STATUS_NO_STANCE, E.STATUS_OPTIMAL]
     assert (forces[:5] == 0).all() and (sol[:5] == 0).all() and np.abs(forces[5]).max() > 1.0
     eng.set_max_iterations(1)
     rec = W.four_stance(16, h, 3)
-    eng2 = cuda_engine_factory(h, 16)
+    eng2 = cuda_engine_factory(h, 16, solver)
     eng2.set_max_iterations(1)
     f2, s2, st = eng2.solve_host(rec, want_solution=True)
     capped = E.status_code(st) == E.STATUS_MAX_ITER
@@ -220,14 +227,15 @@ def test_status_codes_and_failure_outputs(cuda_engine_factory):
     assert (f2[capped] == 0).all() and (s2[capped] == 0).all()
 
 
-def test_full_size_properties(cuda_engine_factory):
+@pytest.mark.parametrize("solver", ["riccati", "inverse"])
+def test_full_size_properties(solver, cuda_engine_factory):
     """BASELINE sizes (B=4096 config 2; B=65536 config 4 shard-free) through size-independent properties:
     every problem optimal, swing legs exactly zero, friction pyramid and force limits hold, a permuted batch
     gives the permuted answer bit for bit, and repeated solves are bitwise reproducible."""
     for name, B in (("config2", 4096), ("config4", 65536)):
         h = 10
         rec = W.CONFIGS[name](B)
-        eng = cuda_engine_factory(h, B)
+        eng = cuda_engine_factory(h, B, solver)
         d = torch.from_numpy(rec).cuda()
         forces, sol, status = eng.solve_device(d, want_solution=True)
         torch.cuda.synchronize()
@@ -294,7 +302,7 @@ def _kkt_report(H, g, C, lo, x):
     return primal, res / max(1.0, np.linalg.norm(g))
 
 
-@pytest.mark.parametrize("sweep", ["fma", "mma"])
+@pytest.mark.parametrize("sweep", ["riccati", "fma", "mma"])
 def test_full_size_config3_and_config5(sweep, oracle, cuda_engine_factory):
     """BASELINE sizes of the two configs that were never solved above B=192: config 3 (B=4096, h=20, mixed gaits --
     every size class incl. the catch-all) and config 5 (B=65536, h=16 gallop), with either inversion: every problem
@@ -303,8 +311,9 @@ def test_full_size_config3_and_config5(sweep, oracle, cuda_engine_factory):
     for name, B, n_sample in (("config3", 4096, 384), ("config5", 65536, 1024)):
         h = W.HORIZONS[name]
         rec = W.CONFIGS[name](B)
-        eng = cuda_engine_factory(h, B)
-        eng.set_sweep_variant(sweep)
+        eng = cuda_engine_factory(h, B, "riccati" if sweep == "riccati" else "inverse")
+        if sweep != "riccati":
+            eng.set_sweep_variant(sweep)   # the inverse solver with either register-resident inversion
         d = torch.from_numpy(rec).cuda()
         forces, sol, status = eng.solve_device(d, want_solution=True)
         torch.cuda.synchronize()
@@ -338,7 +347,8 @@ def test_full_size_config3_and_config5(sweep, oracle, cuda_engine_factory):
         eng.set_sweep_variant("fma")
 
 
-def test_kkt_where_the_reference_gives_up(oracle, cuda_engine_factory):
+@pytest.mark.parametrize("solver", ["riccati", "inverse"])
+def test_kkt_where_the_reference_gives_up(solver, oracle, cuda_engine_factory):
     """Problems on which reference qpOASES hits nWSR = 100 and returns an error (SolverMPC.cpp:435, 537-557) are
     masked out of every oracle comparison -- so they are judged here on their own: the GPU answer must satisfy the
     KKT conditions of the fp64-assembled QP (primal feasibility, stationarity with non-negative multipliers on the
@@ -349,7 +359,7 @@ def test_kkt_where_the_reference_gives_up(oracle, cuda_engine_factory):
     rec = W.four_stance(48, h, 21)
     rec.view(np.float32)[:, R.REC_FMAX] = 7.0
     rec = np.concatenate([rec, W.config3(64, h, 22)])
-    eng = cuda_engine_factory(h, rec.shape[0])
+    eng = cuda_engine_factory(h, rec.shape[0], solver)
     forces, sol, status = eng.solve_host(rec, want_solution=True)
     assert (E.status_code(status) == E.STATUS_OPTIMAL).all()
     backend = oracle.default_backend()
@@ -376,14 +386,15 @@ def test_kkt_where_the_reference_gives_up(oracle, cuda_engine_factory):
     assert rel(sol, port["sol"]).max() < 1e-7
 
 
-def test_working_set_overflow_is_requeued_not_dropped(oracle, cuda_engine_factory):
+@pytest.mark.parametrize("solver", ["riccati", "inverse"])
+def test_working_set_overflow_is_requeued_not_dropped(solver, oracle, cuda_engine_factory):
     """Problems whose active set outgrows the shared-memory tile of their size class are re-solved by the
     catch-all class inside the same call.  Forced here with f_max so low that most fz rows saturate."""
     from quadruped_ctrl_b200 import records as R
     h = 10
     rec = W.four_stance(64, h, 9)
     rec.view(np.float32)[:, R.REC_FMAX] = 6.0
-    eng = cuda_engine_factory(h, 64)
+    eng = cuda_engine_factory(h, 64, solver)
     m_cap = eng.classes()[-2]["m_cap"]
     forces, sol, status = eng.solve_host(rec, want_solution=True)
     assert (E.status_code(status) == E.STATUS_OPTIMAL).all()
