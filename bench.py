@@ -646,8 +646,10 @@ def run_ours(args):
         alg_bytes = R.algorithmic_bytes(h) * max(n_dom, 1)
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         nv_dom = min(classes[dominant]["nv_cap"], 12 * h)
-        on_chip.update(algorithmic_fp64_flops_per_solve=R.algorithmic_flops(h, nv_dom),
-                       fp64_tflops_achieved=R.algorithmic_flops(h, nv_dom) * n_dom / (k_ms * 1e-3) / 1e12)
+        ric_dom = classes[dominant]["threads"] == 32   # the dominant class runs the Riccati kernel (one warp per problem)
+        flops = R.algorithmic_flops_riccati(h, nv_dom) if ric_dom else R.algorithmic_flops(h, nv_dom)
+        on_chip.update(algorithmic_fp64_flops_per_solve=flops, flop_model="riccati" if ric_dom else "inverse",
+                       fp64_tflops_achieved=flops * n_dom / (k_ms * 1e-3) / 1e12)
         parity = parity_block(eng, host_sets[0], h)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

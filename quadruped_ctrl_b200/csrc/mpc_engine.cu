@@ -58,6 +58,7 @@ struct SolveParams {
   char* slab;
   mpc::Layout L;
   mpc::RicLayout RL;  // workspace of the Riccati solver (mpc_solve_riccati_kernel)
+  char* ric_slab;     // [grid][RL.slab_bytes] global scratch for working sets that outgrow the Riccati tile
   int ric_generic;    // development switch (env MPC_RIC_GENERIC): the scalar generic factorisation instead of the DMMA one
   int max_iter;
   int warp_mode;
@@ -552,42 +553,35 @@ __global__ void __launch_bounds__(256, MINB) mpc_solve_wrench_kernel(const __gri
 // H^{-1} product the dual active-set method asks for is a backward + forward sweep over the horizon.  A CTA is one
 // warp (__syncwarp only); the persistent grid keeps as many warps per SM as the per-problem workspace allows.  Records
 // are staged by TMA bulk copies, double buffered, exactly as in mpc_solve_kernel.
-__global__ void __launch_bounds__(32) mpc_solve_riccati_kernel(const __grid_constant__ SolveParams P) {
+template <bool GENERIC>
+__global__ void __launch_bounds__(32, 12) mpc_solve_riccati_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) char smem[];
   const int count = P.count ? *P.count : P.batch;
   if ((int)blockIdx.x >= count) return;
   uint64_t* bar = (uint64_t*)smem;
   char* recbuf = smem + 16;
-  char* fast = recbuf + 2 * P.stride;
+  char* fast = recbuf + P.stride;  // ONE record buffer: the co-resident warps hide the copy, shared memory buys residency
   const int lane = (int)threadIdx.x;
   const mpc::WarpT<false> cx{lane, 32};
-  const mpc::RicWork k = mpc::ric_carve(P.RL, fast);
+  mpc::RicWork k = mpc::ric_carve(P.RL, fast);
+  k.slab = P.ric_slab ? P.ric_slab + (size_t)blockIdx.x * P.RL.slab_bytes : nullptr;
   if (lane == 0) {
     mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
   const uint32_t rec_bytes = (uint32_t)P.stride;
-  int item = blockIdx.x;
-  if (lane == 0) {
-    const int b0 = P.list ? P.list[item] : item;
-    mbar_expect_tx(&bar[0], rec_bytes);
-    tma_bulk_g2s(recbuf, P.records + P.stride * b0, rec_bytes, &bar[0]);
-  }
-  for (int it = 0; item < count; item += gridDim.x, it++) {
-    const int cur = it & 1;
-    const int next = item + gridDim.x;
-    if (lane == 0 && next < count) {  // buffer cur^1 was released by the __syncwarp that ended the last pass
-      const int bn = P.list ? P.list[next] : next;
-      mbar_expect_tx(&bar[cur ^ 1], rec_bytes);
-      tma_bulk_g2s(recbuf + (size_t)(cur ^ 1) * P.stride, P.records + P.stride * bn, rec_bytes, &bar[cur ^ 1]);
-    }
-    mbar_wait(&bar[cur], (uint32_t)((it >> 1) & 1));
+  const float* rec = (const float*)recbuf;
+  const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
+  int it = 0;
+  for (int item = blockIdx.x; item < count; item += gridDim.x, it++) {
     const int b = P.list ? P.list[item] : item;
-    const float* rec = (const float*)(recbuf + (size_t)cur * P.stride);
-    const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
-    const int code = mpc::ric_solve_problem(cx, rec, gait, k, P.max_iter, P.ric_generic != 0);
+    if (lane == 0) {  // the buffer was released by the __syncwarp that ended the last pass
+      mbar_expect_tx(&bar[0], rec_bytes);
+      tma_bulk_g2s(recbuf, P.records + P.stride * b, rec_bytes, &bar[0]);
+    }
+    mbar_wait(&bar[0], (uint32_t)(it & 1));
+    const int code = mpc::ric_solve_problem<GENERIC>(cx, rec, gait, k, P.max_iter);
     __syncwarp();
     if (code == mpc::STATUS_RETRY_BIG && P.retry_list) {
       if (lane == 0) {
@@ -652,6 +646,7 @@ struct mpc_batch {
     int* counts = nullptr;  // [2][classes], double-buffered by solve parity
     int parity = 0;
     char* slab = nullptr;   // per-CTA global workspace of the catch-all class
+    char* ric_slab = nullptr;  // per-warp global workspace of the Riccati classes (working sets beyond the tile)
     int pending_batch = 0;
     bool pending_solution = false;
     int pending_single_class = -1;  // >= 0: the pending solve was host-classified (every problem in that class)
@@ -690,6 +685,7 @@ struct mpc_batch {
   const int* warm_ids = nullptr;
   int warm_shift = 1;
   int sweep = MPC_SWEEP_DEFAULT;  // inversion of the register-resident classes: 0 FMA tiles, 1 DMMA grouped sweep
+  char* cur_ric_slab = nullptr;  // the Riccati slab of the slot whose solve is being queued (set by solve_on_stream)
   int solver = MPC_SOLVER_DEFAULT;  // 0: explicit inverse of the condensed Hessian; 1: Riccati sweeps (mpc_riccati.h)
   int debug_stop = 0;
   int ric_generic = 0;
@@ -894,18 +890,28 @@ int build_classes(mpc_batch* eng) {
         break;
       }
     }
-    // Riccati variant of the class: working-set tile of MPC_RIC_MCAP columns (default 16 / 24 / 32 by class; a larger
-    // working set is re-queued to the last class like every tile overflow)
-    if (!getenv("MPC_NO_RICCATI")) {
-      int m = c.variant == V_64 ? 16 : c.variant == V_96 ? 24 : 32;
+    // Riccati variant of the class: working-set tile of MPC_RIC_MCAP columns (default 8 at nv <= 60 -- what keeps 11
+    // warps per SM -- and 10 above: measured best or equal on every class; 7 warps per SM at nv <= 96, 6 at nv <= 128)
+    // Which classes: measured on the BASELINE workloads (tools/ab_solver.py, same box) the Riccati kernel wins wherever
+    // a sweep over the horizon is cheap next to the inversion it replaces -- nv <= 60 (trot h = 10: x1.35), nv <= 96
+    // (gallop h = 16: x1.79), nv <= 128 at short horizons (four-stance h = 10: x1.42) -- and loses for the nv <= 128
+    // class at long horizons (config 3, h = 20, 12.5 working-set changes of 40 step-phases each: x0.6..0.86), which
+    // therefore keeps the inverse-based kernel (MPC_RIC_128=1 / 0 overrides).
+    bool ric_ok = c.variant != V_128 || h <= 12;
+    if (const char* e = getenv("MPC_RIC_128")) if (c.variant == V_128) ric_ok = atoi(e) != 0;
+    if (!getenv("MPC_NO_RICCATI") && ric_ok) {
+      // (the tile holds the working sets of all but a fraction of a percent of the BASELINE problems; the rest move
+      // into the per-warp global slab and carry on there)
+      int m = c.variant == V_64 ? 8 : 10;
       if (const char* e = getenv("MPC_RIC_MCAP")) m = std::max(4, atoi(e));
       m = std::min(m, c.nv_cap);
       const mpc::RicLayout Lr = mpc::make_ric_layout(h, c.nv_cap, m);
-      const size_t need = 16 + 2 * eng->stride + Lr.bytes;
+      const size_t need = 16 + eng->stride + Lr.bytes;
       if ((int)need <= max_smem) {
         int o = 0;
-        CK(cudaFuncSetAttribute(mpc_solve_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, mpc_solve_riccati_kernel, 32, need));
+        CK(cudaFuncSetAttribute(mpc_solve_riccati_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CK(cudaFuncSetAttribute(mpc_solve_riccati_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, mpc_solve_riccati_kernel<false>, 32, need));
         if (o >= 1) {
           c.ric = true;
           c.ric_m_cap = m;
@@ -941,11 +947,36 @@ int build_classes(mpc_batch* eng) {
     if (c.m_cap > 0) {
       int rc = configure_kernel(eng, c);
       if (rc) return rc;
+      // Riccati variant, OFF unless MPC_RIC_BIG=1: gains of 12h variables and a working-set tile of MPC_RIC_MCAP_BIG
+      // columns (default 16) in shared memory, larger working sets in the per-warp slab.  Measured on config 3 (h = 20,
+      // nv = 168 / 240, 12.5 working-set changes on average, up to 70): 0.57 M solves/s against 0.80 with the
+      // wrench-space kernel -- two warps per SM and 40 step-phases per working-set change lose against one 6h x 6h
+      // inversion.  The Riccati solver pays where the working set stays small next to the horizon.
+      if (!getenv("MPC_NO_RICCATI") && getenv("MPC_RIC_BIG") && atoi(getenv("MPC_RIC_BIG")) == 1) {
+        int m = 16;
+        if (const char* e = getenv("MPC_RIC_MCAP_BIG")) m = std::max(4, atoi(e));
+        const mpc::RicLayout Lr = mpc::make_ric_layout(h, nv_max, m);
+        const size_t need = 16 + eng->stride + Lr.bytes;
+        if ((int)need <= max_smem) {
+          int o = 0;
+          CK(cudaFuncSetAttribute(mpc_solve_riccati_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+          CK(cudaFuncSetAttribute(mpc_solve_riccati_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, mpc_solve_riccati_kernel<false>, 32, need));
+          if (o >= 1) {
+            c.ric = true;
+            c.ric_m_cap = m;
+            c.ric_L = Lr;
+            c.ric_smem = need;
+            c.ric_grid = o * eng->sms;
+          }
+        }
+      }
       eng->classes.push_back(c);
       // ... and its own catch-all: the same kernel with a working set of any size, the working-set matrix T in a
       // per-CTA global slab (L2 resident).  With it the dense catch-all below (a 12h x 12h inversion in L2) is
       // not needed at this horizon at all.
       ClassCfg o = c;
+      o.ric = false;
       o.m_cap = nv_max;
       o.in_fast = 0;
       o.L = mpc::make_layout(h, nv_max, nv_max, 1, kVariantPad[V_WRENCH], 1, 0, 2);
@@ -1003,16 +1034,23 @@ void fill_params(const mpc_batch* eng, int slot, SolveParams& P, const void* rec
 }
 
 // does this launch of class c go through the Riccati kernel?
-bool use_riccati(const mpc_batch* eng, const ClassCfg& c, bool assemble_only) {
-  return c.ric && eng->solver == 1 && !eng->phase_clk && !eng->debug_stop && !assemble_only && !eng->warm_cache;
+// batch: problems of the call (-1: not known / do not care).  One warp per problem pays when the warps fill the SMs; a
+// batch that does not even fill the inverse-based kernel's grid (the legacy single-robot tick: a batch of ONE) is a
+// latency problem, and there 128 threads on one problem finish sooner than 32 (27 us against 37 us per trot tick).
+bool use_riccati(const mpc_batch* eng, const ClassCfg& c, bool assemble_only, int batch = -1) {
+  if (!(c.ric && eng->solver == 1 && !eng->phase_clk && !eng->debug_stop && !assemble_only && !eng->warm_cache)) return false;
+  if (batch >= 0 && c.variant != V_WRENCH && batch <= (c.pipe ? c.pipe_grid : c.grid)) return false;
+  return true;
 }
 
 int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int grid, cudaStream_t st) {
   const bool prof = P.phase_clk != nullptr || P.H_out != nullptr || P.debug_stop != 0;
-  if (use_riccati(eng, c, P.H_out != nullptr)) {
+  if (use_riccati(eng, c, P.H_out != nullptr, P.batch)) {
     SolveParams Pr = P;
     Pr.RL = c.ric_L;
-    mpc_solve_riccati_kernel<<<grid, 32, c.ric_smem, st>>>(Pr);
+    Pr.ric_slab = eng->cur_ric_slab;
+    if (eng->ric_generic) mpc_solve_riccati_kernel<true><<<grid, 32, c.ric_smem, st>>>(Pr);
+    else mpc_solve_riccati_kernel<false><<<grid, 32, c.ric_smem, st>>>(Pr);
     eng->launches++;
     CK(cudaGetLastError());
     return MPC_OK;
@@ -1140,6 +1178,7 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
   if (int rc = ensure_slot(eng, slot)) return rc;
   const int nc = (int)eng->classes.size();
   mpc_batch::Slot& S = eng->s[slot];
+  eng->cur_ric_slab = S.ric_slab;
   if (single_class >= 0) {
     const ClassCfg& c = eng->classes[single_class];
     SolveParams P;
@@ -1148,7 +1187,7 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
     P.warp_mode = c.variant == V_64 ? 1 : 0;
     P.slab = c.in_fast ? nullptr : S.slab;
     const bool piped = c.pipe && !eng->phase_clk && !eng->debug_stop;
-    int grid = std::min(use_riccati(eng, c, false) ? c.ric_grid : piped ? c.pipe_grid : c.grid, batch);
+    int grid = std::min(use_riccati(eng, c, false, batch) ? c.ric_grid : piped ? c.pipe_grid : c.grid, batch);
     if (eng->ctas_per_sm_limit > 0) grid = std::min(grid, eng->ctas_per_sm_limit * eng->sms);
     return launch_solve(eng, c, P, grid, st);  // a working-set tile overflow comes back as MAX_ITER (see wait_host)
   }
@@ -1187,7 +1226,7 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
     const bool time_this = eng->timed && (eng->timed_class < 0 || eng->timed_class == ci);
     if (time_this) CK(cudaEventRecord(eng->ring0[ring], st));
     const bool piped = c.pipe && !eng->phase_clk && !H_out && !eng->debug_stop;
-    int grid = std::min(use_riccati(eng, c, H_out != nullptr) ? c.ric_grid : piped ? c.pipe_grid : c.grid, batch);
+    int grid = std::min(use_riccati(eng, c, H_out != nullptr, batch) ? c.ric_grid : piped ? c.pipe_grid : c.grid, batch);
     if (eng->ctas_per_sm_limit > 0) grid = std::min(grid, eng->ctas_per_sm_limit * eng->sms);
     int rc = launch_solve(eng, c, P, grid, st);
     if (rc) return rc;
@@ -1236,6 +1275,10 @@ int ensure_slot(mpc_batch* eng, int q) {
   CKS(cudaMalloc(&S.counts, sizeof(int) * 2 * kMaxClasses));
   CKS(cudaMemset(S.counts, 0, sizeof(int) * 2 * kMaxClasses));
   CKS(cudaMalloc(&S.slab, slab_bytes));
+  size_t ric_bytes = 0;
+  for (const ClassCfg& c : eng->classes)
+    if (c.ric) ric_bytes = std::max(ric_bytes, c.ric_L.slab_bytes * (size_t)std::min<long long>(c.ric_grid, eng->max_batch));
+  if (ric_bytes) CKS(cudaMalloc(&S.ric_slab, ric_bytes));
   S.stream = st;  // last: marks the slot as complete
 #undef CKS
   return MPC_OK;
@@ -1342,6 +1385,7 @@ void mpc_batch_destroy(mpc_batch_t* eng) {
     cudaFree(S.lists);
     cudaFree(S.counts);
     cudaFree(S.slab);
+    cudaFree(S.ric_slab);
     if (S.stream) cudaStreamDestroy(S.stream);
   }
   cudaFree(eng->caps_dev);

@@ -35,6 +35,7 @@ struct RicLayout {
   int h, nv_cap, m_cap, ldT, ldz, gain_cap;
   int off_sc, off_ints, off_dyn, off_Bd, off_gain, off_x, off_d, off_kap, off_vec, off_red, off_un;
   int bytes;
+  size_t slab_bytes;  // per-warp global slab: Z [nv_cap x nv_cap], T [nv_cap x (nv_cap|1)], six vectors, three index lists
 };
 
 // doubles a problem's gains can take: per step 12 n_k (K_k) + n_k (n_k + 1) / 2 (S_k^{-1}, packed), n_k <= 12
@@ -67,21 +68,21 @@ inline RicLayout make_ric_layout(int h, int nv_cap, int m_cap) {
   o += 8 * L.gain_cap;
   L.off_x = o;
   o += 8 * nv_cap;
-  L.off_d = o;
-  o += 8 * nv_cap;
-  L.off_kap = o;
+  L.off_d = o;    // d = H^{-1} n_p shares its place with kap: the forward sweep reads kap[v] and writes d[v] in the
+  L.off_kap = o;  // same lane, and kap is dead once the sweep has passed
   o += 8 * nv_cap;
   L.off_vec = o;
   o += 8 * kRicVec;
-  L.off_red = o;
-  o += 8 * kRedDoubles;
+  L.off_red = o;  // (no reduction scratch: one warp reduces by shuffles, the host emulation has one thread)
   L.off_un = o;
-  // union: factorisation scratch (P, Y, M 13 x 12 each; G, S 144; scol 2 x 18; Bc 156) | active set (Z, T, six
+  // union: factorisation scratch (P, M, S | Y 13 x 12 each; G 144; scol 2 x 18) | active set (Z, T, six
   // vectors, ub)
-  const int fac = 3 * 156 + 2 * 144 + 36 + 156;
+  const int fac = 3 * 156 + 144 + 36;  // (Y takes S^{-1}'s place; the continuous-time B of the set-up overlays P and M)
   const int as = nv_cap * m_cap + m_cap * L.ldT + 6 * (m_cap + 1) + 4 * h;
   o += 8 * (fac > as ? fac : as);
   L.bytes = (o + 15) / 16 * 16;
+  L.slab_bytes = ((size_t)8 * ((size_t)nv_cap * nv_cap + (size_t)nv_cap * (nv_cap | 1) + 6 * (nv_cap + 1)) +
+                  (size_t)4 * 3 * (nv_cap + 1) + 255) / 256 * 256;
   return L;
 }
 
@@ -92,6 +93,7 @@ struct RicWork {
   double *P, *Y, *M, *G, *S, *scol, *Bc;              // factorisation view of the union
   double *Z, *T, *w, *r, *u, *tcol, *Wca, *Wcz, *ub;  // active-set view
   int h, nv_cap, m_cap, ldT, ldz;
+  char* slab;  // per-warp global scratch for working sets that outgrow the fast-memory tile (nullptr: none)
 };
 // dyn[]: 0 dt, 1 cos(yaw), 2 sin(yaw), 3 x_drag, 4 alpha, 5 a[5], 6 a[11] (gravity's column of A_d times x0[12]),
 // 7 1/mu (float, as the reference forms it)
@@ -130,15 +132,15 @@ MPC_HD RicWork ric_carve(const RicLayout& L, char* fast) {
   k.xn = k.xv + 12;
   k.wv = k.xn + 12;
   k.pt = k.wv + 12;
-  k.red = (double*)(fast + L.off_red);
+  k.red = nullptr;
   double* un = (double*)(fast + L.off_un);
   k.P = un;
-  k.Y = k.P + 156;
-  k.M = k.Y + 156;
-  k.G = k.M + 156;
-  k.S = k.G + 144;
-  k.scol = k.S + 144;
-  k.Bc = k.scol + 36;
+  k.M = k.P + 156;
+  k.S = k.M + 156;  // S^{-1} [12 x 12] until K is formed, then Y = P A [13 x 12]
+  k.Y = k.S;
+  k.G = k.S + 156;
+  k.scol = k.G + 144;
+  k.Bc = un;  // 13 x 12, dead before the factorisation initialises P
   k.Z = un;
   k.T = k.Z + L.nv_cap * L.m_cap;
   k.w = k.T + L.m_cap * L.ldT;
@@ -153,6 +155,7 @@ MPC_HD RicWork ric_carve(const RicLayout& L, char* fast) {
   k.m_cap = L.m_cap;
   k.ldT = L.ldT;
   k.ldz = L.ldz;
+  k.slab = nullptr;
   return k;
 }
 
@@ -452,6 +455,7 @@ MPC_HD void ric_factor(const Cx& cx, const float* rec, const RicWork& k) {
     }
     // (4) G = M' A = M' + M' N  (n x 12);  S^{-1} into the gains
     MPC_FOR(e, ntri) Si[e] = -S[e];
+    cx.sync();  // (Y below takes S's place)
     MPC_FOR(e, 12 * n) {
       const int c = e / 12, j = e - 12 * c;
       double acc = M[j * 12 + c];
@@ -574,26 +578,16 @@ __device__ __forceinline__ bool ric_step_mma(const RicWork& k, const float* rec,
   for (int t = 0; t < 2; t++)
 #pragma unroll
     for (int s3 = 0; s3 < 3; s3++) pa[t][s3] = (8 * t + lr < 13) ? P[(8 * t + lr) * 12 + 4 * s3 + lc] : 0.0;
-  // ---- Y = P A (rows 0..12) ----
-  {
-    double y[2][2][2];
+  // ---- Y = P A (rows 0..12): the products now, off the critical path; stored once S^{-1} has left its place ----
+  double y[2][2][2];
 #pragma unroll
-    for (int t = 0; t < 2; t++)
+  for (int t = 0; t < 2; t++)
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        y[t][u][0] = y[t][u][1] = 0.0;
+    for (int u = 0; u < 2; u++) {
+      y[t][u][0] = y[t][u][1] = 0.0;
 #pragma unroll
-        for (int s3 = 0; s3 < 3; s3++) ric_dmma(y[t][u][0], y[t][u][1], pa[t][s3], AB[s3][u]);
-      }
-#pragma unroll
-    for (int t = 0; t < 2; t++)
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const int r = 8 * t + lr, c = 8 * u + 2 * lc;
-        if (r < 13 && c < 12) *reinterpret_cast<double2*>(Y + r * 12 + c) = make_double2(y[t][u][0], y[t][u][1]);
-      }
-    __syncwarp();
-  }
+      for (int s3 = 0; s3 < 3; s3++) ric_dmma(y[t][u][0], y[t][u][1], pa[t][s3], AB[s3][u]);
+    }
   if constexpr (NTU > 0) {
     // ---- (1) M = P B_k (rows 0..12: row 12 is w') ----
     double m[2][NT][2];
@@ -725,6 +719,15 @@ __device__ __forceinline__ bool ric_step_mma(const RicWork& k, const float* rec,
     }
     __syncwarp();
   }
+  // ---- Y goes into the place S^{-1} has just left (everybody is past the K product) ----
+#pragma unroll
+  for (int t = 0; t < 2; t++)
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int r = 8 * t + lr, c = 8 * u + 2 * lc;
+      if (r < 13 && c < 12) *reinterpret_cast<double2*>(Y + r * 12 + c) = make_double2(y[t][u][0], y[t][u][1]);
+    }
+  __syncwarp();
   // ---- (6) P <- Q + A'Y - G'K (rows 0..12; row 12 = (A' pt - K' w)') ----
   {
     double pn[2][2][2];
@@ -1087,20 +1090,44 @@ __device__ __forceinline__ void ric_hinv_row_fast(const RicWork& k, const RicLan
 }
 #endif  // __CUDACC__
 
+// Warp-wide argmin of (val, idx) pairs, ties to the smaller idx (as block_argmin).  One warp on the device: three
+// REDUX instructions on an order-preserving 64-bit integer image of the doubles (high word, low word among the lanes
+// that hold the minimal high word, index among the winners) instead of five rounds of 64-bit shuffles and compares.
+template <class Cx>
+MPC_HD void ric_argmin(const Cx& cx, double& val, int& idx) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (Cx::kOneWarp) {
+    const long long bits = __double_as_longlong(val);
+    const unsigned long long key = (unsigned long long)bits ^ (unsigned long long)((bits >> 63) | (long long)0x8000000000000000ull);
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    const bool win = hi == mhi && lo == mlo;
+    idx = (int)__reduce_min_sync(0xffffffffu, win ? (unsigned)idx : 0x7fffffffu);
+    const unsigned long long mk = ((unsigned long long)mhi << 32) | mlo;
+    val = __longlong_as_double((long long)((mk >> 63) ? (mk ^ 0x8000000000000000ull) : ~mk));
+    return;
+  }
+#endif
+  block_argmin(cx, (double*)nullptr, val, idx);
+}
+
 // ---------------------------------------------------------------------------
 // Goldfarb-Idnani dual active set with H^{-1} products from the Riccati sweeps.  Same selection rule, tolerances,
 // step rules and T updates as mpc_core.h's active_set; rows of H^{-1} are replaced by the stored columns
 // Z[:, a] = H^{-1} n_a of the working set and d = H^{-1} n_p of the entering row.
 // ---------------------------------------------------------------------------
-template <class Cx>
-MPC_HD void ric_active_set(const Cx& cx, const float* rec, const unsigned char* gait, const RicWork& k, int max_iter,
-                           bool generic = false) {
+template <bool GENERIC, class Cx>
+MPC_HD void ric_active_set(const Cx& cx, const float* rec, const unsigned char* gait, const RicWork& kin, int max_iter) {
+  constexpr bool generic = GENERIC;
+  RicWork k = kin;  // (the working-set pointers move to the slab when the fast-memory tile overflows)
   Scalars* sc = k.sc;
 #if defined(__CUDA_ARCH__)
   const RicLaneConst LC = ric_lane_const(k, cx.tid & 31);
 #endif
   (void)generic;
-  const int nv = sc->nv, ns = sc->ns, ldT = k.ldT, ldz = k.ldz;
+  const int nv = sc->nv, ns = sc->ns, ldz = k.ldz;
+  int ldT = k.ldT;
   const double mu_inv = k.dyn[7];
   double* T = k.T;
   double* Z = k.Z;
@@ -1122,7 +1149,7 @@ MPC_HD void ric_active_set(const Cx& cx, const float* rec, const unsigned char* 
       for (int t = 0; t < 6; t++)
         if (!((mask >> t) & 1) && sl[t] < best) { best = sl[t]; bidx = 6 * j + t; }
     }
-    block_argmin(cx, k.red, best, bidx);
+    ric_argmin(cx, best, bidx);
     if (bidx == 0x7fffffff) break;  // uniform
     if (sc->iters >= max_iter) {
       cx.sync();
@@ -1130,11 +1157,47 @@ MPC_HD void ric_active_set(const Cx& cx, const float* rec, const unsigned char* 
       cx.sync();
       break;
     }
-    if (sc->m >= k.m_cap) {  // no room for another column of Z: the problem goes to a class with a larger tile
+    if (sc->m >= k.m_cap) {  // no room for another column of Z in the fast-memory tile
+      if (k.slab == nullptr || k.m_cap >= k.nv_cap) {  // no slab: the problem goes to a class with a larger tile
+        cx.sync();
+        MPC_ONE sc->status = STATUS_RETRY_BIG;
+        cx.sync();
+        return;
+      }
+      // Move the working set into this warp's global slab (L2 resident) and carry on with room for nv_cap rows: Z keeps
+      // its leading dimension, T is re-strided, the per-row vectors and index lists follow.  Rare by construction
+      // (the tile holds the working sets of all but a fraction of a percent of the BASELINE problems).
+      const int m = sc->m, nb = k.nv_cap + 1, ldTb = k.nv_cap | 1;
+      double* Zb = (double*)k.slab;
+      double* Tb = Zb + (size_t)k.nv_cap * ldz;
+      double* vb = Tb + (size_t)k.nv_cap * ldTb;   // w, r, u, tcol, Wca, Wcz
+      int* ib = (int*)(vb + 6 * nb);               // W, Wia, Wiz
       cx.sync();
-      MPC_ONE sc->status = STATUS_RETRY_BIG;
+#pragma unroll 1
+      for (int e = cx.tid; e < m * nv; e += cx.nt) {
+        const int a = e / nv, i = e - a * nv;
+        Zb[a * ldz + i] = Z[a * ldz + i];
+      }
+#pragma unroll 1
+      for (int e = cx.tid; e < m * m; e += cx.nt) {
+        const int a = e / m, b = e - a * m;
+        Tb[a * ldTb + b] = T[a * ldT + b];
+      }
+      MPC_FOR(a, m) {
+        vb[2 * nb + a] = k.u[a];
+        vb[4 * nb + a] = k.Wca[a];
+        vb[5 * nb + a] = k.Wcz[a];
+        ib[a] = k.W[a];
+        ib[nb + a] = k.Wia[a];
+        ib[2 * nb + a] = k.Wiz[a];
+      }
       cx.sync();
-      return;
+      Z = k.Z = Zb;
+      T = k.T = Tb;
+      ldT = k.ldT = ldTb;
+      k.w = vb; k.r = vb + nb; k.u = vb + 2 * nb; k.tcol = vb + 3 * nb; k.Wca = vb + 4 * nb; k.Wcz = vb + 5 * nb;
+      k.W = ib; k.Wia = ib + nb; k.Wiz = ib + 2 * nb;
+      k.m_cap = k.nv_cap;
     }
     const int p = bidx;
     const Row rp = make_row(p, mu_inv);
@@ -1142,7 +1205,7 @@ MPC_HD void ric_active_set(const Cx& cx, const float* rec, const unsigned char* 
     cx.sync();
     MPC_ONE { sc->iters++; sc->up = 0.0; }
 #if defined(__CUDA_ARCH__)
-    if (Cx::kOneWarp && !generic) ric_hinv_row_fast(k, LC, rp, d, cx.tid);
+    if constexpr (Cx::kOneWarp && !GENERIC) ric_hinv_row_fast(k, LC, rp, d, cx.tid);
     else
 #endif
     ric_hinv_row(cx, k, rp, d);  // (ends with a sync)
@@ -1171,7 +1234,7 @@ MPC_HD void ric_active_set(const Cx& cx, const float* rec, const unsigned char* 
       double wr = 0.0;
       if (m > 0) {  // uniform
         wr = block_sum(cx, k.red, part);
-        block_argmin(cx, k.red, tbest, tidx);
+        ric_argmin(cx, tbest, tidx);
       }
       const double znp = vnp - wr;
       const bool dependent = !(znp > 1e-11 * vnp);
@@ -1275,7 +1338,7 @@ MPC_HD void ric_active_set(const Cx& cx, const float* rec, const unsigned char* 
       {
         double neg = -worst;
         int who = cx.tid;
-        block_argmin(cx, k.red, neg, who);
+        ric_argmin(cx, neg, who);
         if (!(-neg > 1e-12)) break;  // uniform
       }
       cx.sync();
@@ -1320,23 +1383,24 @@ MPC_HD void ric_scatter(const Cx& cx, const RicWork& k, float* forces, double* s
 }
 
 // One problem, start to finish (everything but the outputs).  Returns the status code (uniform).
-template <class Cx>
-MPC_HD int ric_solve_problem(const Cx& cx, const float* rec, const unsigned char* gait, const RicWork& k, int max_iter,
-                             bool generic = false) {
+// GENERIC: the scalar factorisation and sweeps (the host emulation; on the device a development switch) instead of the
+// tensor-pipe factorisation and the register-resident sweeps.
+template <bool GENERIC = true, class Cx>
+MPC_HD int ric_solve_problem(const Cx& cx, const float* rec, const unsigned char* gait, const RicWork& k, int max_iter) {
   ric_setup(cx, rec, gait, k);
   if (k.sc->status != MPC_STATUS_OPTIMAL) return k.sc->status;
 #if defined(__CUDA_ARCH__)
-  if (Cx::kOneWarp && !generic) ric_factor_mma(k, rec, cx.tid);
+  if constexpr (Cx::kOneWarp && !GENERIC) ric_factor_mma(k, rec, cx.tid);
   else
 #endif
   ric_factor(cx, rec, k);
   if (k.sc->status != MPC_STATUS_OPTIMAL) return k.sc->status;
 #if defined(__CUDA_ARCH__)
-  if (Cx::kOneWarp && !generic) ric_forward_fast(k, ric_lane_const(k, cx.tid), k.x0, true, k.h, k.x, cx.tid);
+  if constexpr (Cx::kOneWarp && !GENERIC) ric_forward_fast(k, ric_lane_const(k, cx.tid), k.x0, true, k.h, k.x, cx.tid);
   else
 #endif
   ric_forward(cx, k, k.x0, true, k.h, k.x);  // x = -H^{-1} g
-  ric_active_set(cx, rec, gait, k, max_iter, generic);
+  ric_active_set<GENERIC>(cx, rec, gait, k, max_iter);
   return k.sc->status;
 }
 

@@ -99,3 +99,15 @@ def algorithmic_flops(horizon, nv):
     assembly = 18 * (nv * (nv + 1) // 2) + 6 * 2 * 12 * 12 * 12 + 2 * 3 * 12 * horizon * horizon
     return sweep + assembly
 
+
+
+def algorithmic_flops_riccati(horizon, nv):
+    """fp64 operations per solve of the Riccati solver (csrc/mpc_riccati.h), counted on the algorithm (not on the padded
+    8x8 tiles the tensor pipe executes), for n = nv / horizon controls per step: the factorisation
+    (M = PB 288n, S = B'M 24n^2, sweep n^3, G = M'A and the sparse products with A ~ 72n + 1728, K = S^-1 G 24n^2,
+    G'K 288n per step) plus ONE backward / forward sweep pair (x = -H^-1 g: 96n + 2n^2 + 100 per step).  The sweeps of the
+    active-set iterations are data dependent and left out, like the iterations of the inverse-based solver."""
+    n = nv / float(horizon)
+    factor = n ** 3 + 48 * n * n + 648 * n + 1728
+    sweep = 96 * n + 2 * n * n + 100
+    return int(horizon * (factor + sweep))

@@ -131,7 +131,7 @@ def emu_solve_wrench(rec, h, m_cap=0, max_iter=100000):
     return dict(forces=f, sol=sol, nv=info[:, 0], m=info[:, 1], iters=info[:, 2], status=info[:, 3])
 
 
-def emu_solve_riccati(rec, h, nv_cap=0, m_cap=0, max_iter=100000):
+def emu_solve_riccati(rec, h, nv_cap=0, m_cap=0, max_iter=100000, with_slab=False):
     """Host build of the Riccati solver (csrc/mpc_riccati.h): no condensed Hessian, H^{-1} products by sweeps."""
     L = emu_lib()
     rec = np.ascontiguousarray(rec, np.uint8)
@@ -141,6 +141,6 @@ def emu_solve_riccati(rec, h, nv_cap=0, m_cap=0, max_iter=100000):
     info = np.zeros((B, 4), np.int32)
     vp = ctypes.c_void_p
     rc = L.emu_solve_batch_riccati(vp(rec.ctypes.data), B, h, nv_cap, m_cap, max_iter, vp(f.ctypes.data),
-                                   vp(sol.ctypes.data), vp(info.ctypes.data))
+                                   vp(sol.ctypes.data), vp(info.ctypes.data), int(bool(with_slab)))
     assert rc == 0, rc
     return dict(forces=f, sol=sol, nv=info[:, 0], m=info[:, 1], iters=info[:, 2], status=info[:, 3])

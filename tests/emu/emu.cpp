@@ -158,7 +158,7 @@ int emu_solve_batch_wrench(const void* records, int batch, int h, int m_cap, int
 // Riccati solver (csrc/mpc_riccati.h): the same problems without the condensed Hessian, one emulated thread.
 // info [batch*4]: nv, active-set size at exit, iterations, status code (STATUS_RETRY_BIG = 0x40 when m_cap is hit).
 int emu_solve_batch_riccati(const void* records, int batch, int h, int nv_cap, int m_cap, int max_iter, float* forces,
-                            double* solution, int* info) {
+                            double* solution, int* info, int with_slab) {
   using namespace mpc;
   if (nv_cap <= 0) nv_cap = 12 * h;
   if (m_cap <= 0) m_cap = nv_cap;
@@ -169,7 +169,9 @@ int emu_solve_batch_riccati(const void* records, int batch, int h, int nv_cap, i
   const int NU = 12 * h;
   for (int b = 0; b < batch; b++) {
     memset(fast.data(), 0xCD, fast.size());  // poison: nothing may rely on zeroed workspace
-    const RicWork k = ric_carve(L, fast.data());
+    RicWork k = ric_carve(L, fast.data());
+    std::vector<char> slab(with_slab ? L.slab_bytes : 0, (char)0xCD);
+    if (with_slab) k.slab = slab.data();  // a working set that outgrows the tile moves here instead of being re-queued
     const float* rec = (const float*)((const char*)records + stride * b);
     const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * h);
     ric_solve_problem(cx, rec, gait, k, max_iter);

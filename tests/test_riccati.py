@@ -109,6 +109,11 @@ def test_iteration_cap_and_column_tile_overflow():
     assert (small["status"][over] == ST_RETRY).all()
     same = ~over
     assert (small["sol"][same] == full["sol"][same]).all()
+    # with a global slab behind the tile the working set moves there and the solve carries on: same bits as with a
+    # tile that was large enough from the start
+    moved = emu_solve_riccati(rec, 10, nv_cap=120, m_cap=4, with_slab=True)
+    assert (moved["status"] == ST_OPT).all()
+    assert (moved["sol"] == full["sol"]).all() and (moved["iters"] == full["iters"]).all()
 
 
 def test_flight_phases_and_mixed_stance_counts(oracle):

@@ -19,9 +19,13 @@ from collections import defaultdict
 def sass_rows(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hi = next(i for i, r in enumerate(rows) if "Source" in r and "Address" in r)
+    # one section (header row + SASS rows) per captured launch; NCU_LINES_KERNEL picks the section (default: the first)
+    his = [i for i, r in enumerate(rows) if "Source" in r and "Address" in r]
+    which = int(os.environ.get("NCU_LINES_KERNEL", "0"))
+    hi = his[which]
+    end = his[which + 1] if which + 1 < len(his) else len(rows)
     hdr = rows[hi]
-    return hdr, [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    return hdr, [r for r in rows[hi + 1:end] if len(r) == len(hdr)]
 
 
 def line_table(lib, kernel_sub):
