@@ -72,7 +72,7 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_static_profile(cfg_id):
+def load_static_profile(cfg_id, solver="riccati"):
     """Figures that come from committed ncu captures / microbenchmarks, NOT from this run (labelled static):
     DRAM bytes per launch of the dominant kernel, its pipe utilisation, the measured fp64 peaks."""
     out = {"static": True}
@@ -81,7 +81,7 @@ def load_static_profile(cfg_id):
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        e = d.get("config%d" % cfg_id) or (d if cfg_id == 2 and "dram_bytes_per_launch" in d else None)
+        e = (d.get("inverse_solver_config%d" % cfg_id) if solver == "inverse" else None) or d.get("config%d" % cfg_id)
         if e:
             traffic = e.get("dram_bytes_per_launch")
             out.update({k: e.get(k) for k in ("fp64_pipe_pct_of_peak", "issue_slots_pct_of_peak",
@@ -367,7 +367,7 @@ def run_config1(args):
     torch.cuda.synchronize()
     k_ms = max(eng.last_class_kernel_ms(c) for c in range(len(eng.classes())))
     peak, peak_src = load_peaks()
-    traffic, on_chip = load_static_profile(1)
+    traffic, on_chip = load_static_profile(1, args.solver)
     achieved = R.algorithmic_bytes(h) / (k_ms * 1e-3) / 1e9
     exe_o, extra_o = build_legacy_stub(True)
     cmed, cp95, cmean, _, _ = run_legacy_stub(exe_o, extra_o, 400)
@@ -641,7 +641,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        traffic, on_chip = load_static_profile(args.config)
+        traffic, on_chip = load_static_profile(args.config, args.solver)
         n_dom = int(per_class[dominant])
         alg_bytes = R.algorithmic_bytes(h) * max(n_dom, 1)
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9

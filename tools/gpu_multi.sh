@@ -12,4 +12,4 @@ $RUN bench.py --gpus $N --steps 100 --warmup 5 2> gpurun_out/m_c2.err | tail -1 
 $RUN bench.py --gpus $N --steps 100 --warmup 5 --gather peer 2> gpurun_out/m_c2p.err | tail -1 | tee -a gpurun_out/bench_multi_$N.json | cut -c1-300
 $RUN bench.py --gpus $N --config 4 --steps 30 --warmup 5 2> gpurun_out/m_c4.err | tail -1 | tee -a gpurun_out/bench_multi_$N.json | cut -c1-300
 python tools/show_bench.py gpurun_out/bench_multi_$N.json
-tail -2 gpurun_out/m_c2.err gpurun_out/m_c2p.err gpurun_out/m_c4.err
+tail -q -n 2 gpurun_out/m_c2.err gpurun_out/m_c2p.err gpurun_out/m_c4.err

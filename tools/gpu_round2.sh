@@ -11,7 +11,7 @@ STEPS=${STEPS:-50}
 : > gpurun_out/bench_configs.json
 for c in 1 2 3 4 5; do
   timeout 900 python bench.py --config $c --steps $STEPS --warmup 5 2> gpurun_out/bench_c$c.err | tail -1 | tee -a gpurun_out/bench_configs.json
-  tail -3 gpurun_out/bench_c$c.err
+  tail -n 3 gpurun_out/bench_c$c.err
 done
 if [ "${1:-}" != "quick" ]; then
   python bench.py --impl reference --steps 2 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_reference.json

@@ -17,7 +17,7 @@ for c in 2 5; do
   # the class kernels of a solve are launched back to back; three consecutive Riccati launches contain the non-empty one
   $NCU --set full --import-source on --kernel-name-base demangled -k regex:riccati -s 9 -c 3 -f -o gpurun_out/r2_ric_c$c $B --config $c > gpurun_out/r2_ric_c$c.log 2>&1
   python tools/ncu_summary.py gpurun_out/r2_ric_c$c.ncu-rep smsp__average_warps_issue_stalled sm__pipe_tensor sm__inst_executed_pipe > gpurun_out/r2_ric_c${c}_summary.txt 2>&1
-  python tools/ncu_lines.py gpurun_out/r2_ric_c$c.ncu-rep $LIB riccati 700 > gpurun_out/r2_ric_c${c}_lines.txt 2>&1
+  python tools/ncu_lines.py gpurun_out/r2_ric_c$c.ncu-rep $LIB riccati_kernelILb0 700 > gpurun_out/r2_ric_c${c}_lines.txt 2>&1
   rm -f gpurun_out/r2_ric_c$c.ncu-rep
 done
 ls -la gpurun_out | head -50
