@@ -6,8 +6,11 @@
 
 One "step" = one pass of the hot path (record -> assembled QP -> 12 contact forces) over one batch of synthetic
 problems.  `--config` picks the BASELINE.json workload; the default, and what the driver runs, is
-config 2: B=4096 independent robots per GPU, trot, horizon 10 (weak scaling; at N>1 the step ends with the gather of
-the [N*4096, 12] forces -- north_star: "a single NCCL all-gather of solved forces only when the batch is split").
+config 2: B=4096 independent robots per GPU, trot, horizon 10 (weak scaling; at N>1 the step ends with ONE gather of
+the [N*4096, 12] forces -- north_star: "a single ... all-gather of solved forces only when the batch is split".  The
+default gather is the engine's own: the copy engines push every rank's forces into all ranks' gather buffers over NVLink
+peer mappings and a device-side flag barrier closes the step, on a communication stream of its own; `--gather nccl` is
+all_gather_into_tensor, `--gather peer` the solve kernel's fused peer-store epilogue).
 Configs 4 and 5 are one 65536-problem batch cut into N contiguous shards (sharding.shard_bounds, strong scaling);
 config 1 is one robot through the reference's own C interface, one MPC tick at a time.
 
@@ -451,32 +454,50 @@ def run_ours(args):
     # of step i (a few CTAs still solving) shares the GPU with the head of step i+1.
     nq = max(1, min(args.inflight, E.SLOTS))
     streams = [torch.cuda.Stream(dev) for _ in range(nq)]
-    forces2 = [torch.empty((B, 12), dtype=torch.float32, device=dev) for _ in range(nq)]
-    status2 = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(nq)]
-    gathered2 = [torch.empty((world * B, 12), dtype=torch.float32, device=dev) for _ in range(nq)] if world > 1 else None
     peer = world > 1 and args.gather == "peer"
-    if peer:  # fused: the solve kernel stores every force straight into all ranks' gather buffers over NVLink
+    # Output buffers rotate over MORE sets than there are scratch slots when the batch is gathered over NCCL: a solve
+    # then waits for the gather that read its output set 2*nq steps ago instead of nq -- the ranks are separate
+    # processes whose launch jitter otherwise stalls every slot on the slowest rank's previous gather.
+    push = world > 1 and args.gather == "push"
+    nbuf = nq * (args.outbufs if (world > 1 and not peer and not push) else 1)
+    forces2 = [torch.empty((B, 12), dtype=torch.float32, device=dev) for _ in range(nbuf)]
+    status2 = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(nbuf)]
+    gathered2 = [torch.empty((world * B, 12), dtype=torch.float32, device=dev) for _ in range(nbuf)] if world > 1 else None
+    if peer or push:
+        # peer: the solve kernel stores every force straight into all ranks' gather buffers over NVLink (fused epilogue);
+        # push: the copy engines do it after the solve (no SM takes part) -- both end with a device-side flag barrier
         eng.setup_peer_gather(world * B, rank * B)
+        eng.set_gather_fused(peer)
         gathered2 = eng.gather_views   # one region per scratch slot
     # NCCL gather on a stream of its own: the next batch's kernels never queue behind the collective
-    comm = torch.cuda.Stream(dev) if world > 1 and not peer else None
-    gather_done = [torch.cuda.Event() for _ in range(nq)]
+    nogather = world > 1 and args.gather == "none"   # diagnosis only: what the step costs without its gather
+    comm = torch.cuda.Stream(dev, priority=-1 if args.comm_priority else 0) if world > 1 and not peer and not nogather else None
+    gather_done = [torch.cuda.Event() for _ in range(nbuf)]
+    tiny_gather = bool(os.environ.get("MPC_DIAG_TINY_GATHER"))
+    if os.environ.get("MPC_DIAG_CTAS_PER_SM"):
+        eng.set_ctas_per_sm_limit(int(os.environ["MPC_DIAG_CTAS_PER_SM"]))
 
     def step(i, overlap=True):
         q = (i % nq) if overlap else 0
+        j = (i % nbuf) if overlap else 0
         st = streams[q]
         with torch.cuda.stream(st):
             if comm is not None:
-                st.wait_event(gather_done[q])   # the previous gather out of this slot's forces has finished
-            eng.solve_device(dev_sets[i % n_sets], forces=forces2[q], status=status2[q], stream=st, slot=q)
-            if world > 1:
+                st.wait_event(gather_done[j])   # the previous gather out of this output set has finished
+            eng.solve_device(dev_sets[i % n_sets], forces=forces2[j], status=status2[j], stream=st, slot=q)
+            if world > 1 and not nogather:
                 if peer:
                     eng.gather_sync(stream=st, slot=q)  # device-side flag exchange over NVLink
                 else:
                     comm.wait_stream(st)
                     with torch.cuda.stream(comm):
-                        dist.all_gather_into_tensor(gathered2[q], forces2[q])
-                        gather_done[q].record(comm)
+                        if push:
+                            eng.gather_push(forces2[j], slot=j, stream=comm)
+                        elif tiny_gather:   # diagnosis only (MPC_DIAG_TINY_GATHER): the rendezvous without the payload
+                            dist.all_gather_into_tensor(gathered2[j].view(-1)[:2 * world], forces2[j].view(-1)[:2])
+                        else:
+                            dist.all_gather_into_tensor(gathered2[j], forces2[j])
+                        gather_done[j].record(comm)
                     if not overlap:
                         st.wait_stream(comm)
 
@@ -495,14 +516,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(n, first, overlap):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         eng.timing_mark()
         ev0.record()
         fork()
+        h0 = time.perf_counter()
         for i in range(n):
             step(first + i, overlap)
+        host_ms[0] = (time.perf_counter() - h0) * 1e3 / n   # host time to QUEUE one step (no synchronisation inside)
         join()
         ev1.record()
         barrier()
@@ -540,6 +565,7 @@ def run_ours(args):
         time.sleep(0.3)
     launches0 = eng.kernel_launches()
     total_ms = timed(args.steps, args.warmup, True)
+    host_queue_ms = host_ms[0]
     launches = eng.kernel_launches() - launches0
     k_timed = eng.timing_collect(dominant)
     frac_ok = optimal_fraction()   # statuses of the LAST batch on every slot, i.e. of timed steps
@@ -556,7 +582,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     results_ok = bool(torch.equal(ref_f, forces2[0])) and frac_ok == 1.0
     gather_ok = None
-    if world > 1:
+    if world > 1 and not nogather:
         mine = forces2[0].view(torch.int32).to(torch.int64).sum()
         tot = mine.clone()
         dist.all_reduce(tot)
@@ -580,15 +606,27 @@ def run_ours(args):
     checksum = [0.0]
     e2e_bad = [0]
 
+    e2e_gathered = [None] * nslots   # event: the gather out of the slot's device forces has finished
+    e2e_comm = comm if comm is not None else (torch.cuda.Stream(dev) if world > 1 else None)
+
     def collect(slot):
         eng.wait_host(slot)                       # results stay in the slot's pinned buffers
         checksum[0] += float(out_f[slot][0, 2])
         e2e_bad[0] += int((out_s[slot][:B] & 0xff != 0).sum())
-        if world > 1:
-            dist.all_gather_into_tensor(gathered2[0], dev_f[slot][:B])
+        if world > 1 and not nogather:            # the forces are complete on the device (wait_host synchronised)
+            with torch.cuda.stream(e2e_comm):
+                if push:
+                    eng.gather_push(dev_f[slot][:B], slot=slot, stream=e2e_comm)
+                else:
+                    dist.all_gather_into_tensor(gathered2[0], dev_f[slot][:B])
+                ev = torch.cuda.Event()
+                ev.record(e2e_comm)
+            e2e_gathered[slot] = ev
 
     def e2e_run(n):
         for i in range(n):
+            if e2e_gathered[i % nslots] is not None:
+                e2e_gathered[i % nslots].synchronize()   # (long done) before the slot's device forces are overwritten
             eng.submit_host(i % nslots, pinned_sets[i % len(pinned_sets)].numpy(), zero_copy=True)
             if i >= depth:
                 collect((i - depth) % nslots)
@@ -664,6 +702,8 @@ def run_ours(args):
                                      "one-batch-at-a-time figure" % nq,
                        "collective": ("none (N=1)" if world == 1 else
                                       "peer stores from the solve kernel + device-side flag barrier (no NCCL on the path)" if peer else
+                                      "copy-engine gather: one DMA per peer of this rank's [B,12] forces over NVLink into every rank's gather "
+                                      "buffer + device-side flag barrier, on a communication stream of its own (no SM takes part)" if push else
                                       "all_gather_into_tensor of [N*B,12] fp32 forces on a communication stream of its own"),
                        "solver": eng.solver(), "sweep": eng.sweep_variant(), "classes": classes,
                        "problems_per_class": [int(x) for x in per_class]},
@@ -673,7 +713,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * 48 + B * 4,
                     "api": "mpc_batch_submit_host / mpc_batch_wait_host (%d slots, %d batches submitted ahead; "
                            "page-locked caller buffers handed over zero-copy with mpc_batch_submit_host_pinned)" % (nslots, depth)},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "host_queue_ms_per_step": host_queue_ms,
             "results_ok": results_ok, "optimal_fraction": frac_ok,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "on_chip": on_chip,
@@ -712,15 +752,18 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json workload (1..5)")
     ap.add_argument("--batch", type=int, default=0, help="override the config's batch size")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--inflight", type=int, default=3, help="batches in flight on the device-resident path (<= 3)")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("MPC_INFLIGHT", "3")), help="batches in flight on the device-resident path (<= 3)")
     ap.add_argument("--e2e-slots", type=int, default=6, help="scratch slots the end-to-end leg rotates over (<= 6)")
     ap.add_argument("--sweep", default=os.environ.get("MPC_SWEEP", "fma"), choices=["fma", "mma"],
                     help="inversion of the register-resident classes: FP64 FMA pipe or FP64 tensor pipe (DMMA)")
     ap.add_argument("--solver", default=os.environ.get("MPC_SOLVER", "riccati"), choices=["riccati", "inverse"],
                     help="riccati: sweeps over the horizon, no condensed Hessian (default); inverse: explicit inverse of "
                          "the reduced condensed Hessian")
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
-                    help="N>1: NCCL all-gather of the forces (default) or the kernel's fused peer-store epilogue")
+    ap.add_argument("--outbufs", type=int, default=1, help="N>1, NCCL gather: output sets per scratch slot")
+    ap.add_argument("--comm-priority", type=int, default=1, help="N>1: 1 = the NCCL gather runs on a high-priority stream")
+    ap.add_argument("--gather", default="push", choices=["push", "nccl", "peer", "none"],
+                    help="N>1: push = copy-engine gather over NVLink peer mappings + device-side flag barrier (default); "
+                         "nccl = all_gather_into_tensor; peer = the solve kernel's fused peer-store epilogue; none = diagnosis")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -286,6 +286,14 @@ void* mpc_batch_gather_buffer_slot(mpc_batch_t* eng, int slot);
  * the solve after next is queued. */
 int mpc_batch_gather_sync(mpc_batch_t* eng, void* cuda_stream);
 int mpc_batch_gather_sync_slot(mpc_batch_t* eng, int slot, void* cuda_stream);
+/* The same gather by the COPY ENGINES instead of the solve kernel's epilogue: after gather_connect, turn the epilogue
+ * off (set_gather_fused 0) and call gather_push_slot once per solve, on any stream ordered after the solve (a
+ * communication stream of its own, so that the next batch's kernels never wait for it): this rank's [batch, 12] forces
+ * at forces_dev are DMA-copied over NVLink into region `slot` of every rank's gather buffer at this rank's row offset
+ * -- no SM takes part, nothing competes with the solve kernels in flight -- and the flag barrier of gather_sync_slot
+ * follows.  Work queued behind it on the stream sees the whole batch in mpc_batch_gather_buffer_slot(slot). */
+int mpc_batch_set_gather_fused(mpc_batch_t* eng, int on);
+int mpc_batch_gather_push_slot(mpc_batch_t* eng, int slot, const float* forces_dev, int batch, void* cuda_stream);
 
 /* Inversion of the reduced Hessian in the register-resident size classes (selectable per engine, any time):
  *   0  symmetric sweep with one rank-1 update per pivot on the FP64 FMA pipe (invert_spd_tiles)

@@ -677,6 +677,7 @@ struct mpc_batch {
   size_t gather_slot_bytes = 0;
   int gather_rows = 0;
   int gather_world = 0, gather_rank = 0;
+  bool gather_fused = true;  // the solve kernels' peer-store epilogue is armed (false: gather by mpc_batch_gather_push_slot)
   unsigned gather_epoch[kSlots] = {0};
   unsigned** peer_flags_dev = nullptr;  // [kSlots][kMaxPeers]
   long long* phase_clk = nullptr;
@@ -1027,7 +1028,7 @@ void fill_params(const mpc_batch* eng, int slot, SolveParams& P, const void* rec
   P.warm_cache = eng->warm_cache;
   P.warm_ids = eng->warm_ids;
   P.warm_shift = eng->warm_shift;
-  P.n_peers = eng->n_peers;
+  P.n_peers = eng->gather_fused ? eng->n_peers : 0;
   P.rank_offset = eng->rank_offset;
   for (int q = 0; q < kMaxPeers; q++)
     P.peers[q] = eng->peers[q] ? (float*)((char*)eng->peers[q] + eng->gather_slot_bytes * (size_t)slot) : nullptr;
@@ -1772,6 +1773,28 @@ int mpc_batch_gather_sync_slot(mpc_batch_t* eng, int slot, void* cuda_stream) {
 }
 
 int mpc_batch_gather_sync(mpc_batch_t* eng, void* cuda_stream) { return mpc_batch_gather_sync_slot(eng, 0, cuda_stream); }
+
+int mpc_batch_set_gather_fused(mpc_batch_t* eng, int on) {
+  if (!eng) return MPC_E_ARG;
+  eng->gather_fused = on != 0;
+  return MPC_OK;
+}
+
+// Copy-engine gather: this rank's [batch, 12] forces go into every rank's gather region `slot` by DMA over NVLink (no
+// SM takes part, so nothing competes with the solve kernels of the batches in flight), then the device-side flag
+// barrier of mpc_batch_gather_sync_slot tells the peers and waits for them.
+int mpc_batch_gather_push_slot(mpc_batch_t* eng, int slot, const float* forces_dev, int batch, void* cuda_stream) {
+  if (!eng || slot < 0 || slot >= kSlots || !forces_dev || batch < 0 || !eng->peer_flags_dev || eng->gather_world < 1 ||
+      eng->rank_offset + batch > eng->gather_rows)
+    return MPC_E_ARG;
+  ON_DEVICE(eng);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const size_t bytes = (size_t)batch * 12 * sizeof(float);
+  const size_t off = eng->gather_slot_bytes * (size_t)slot + (size_t)eng->rank_offset * 12 * sizeof(float);
+  for (int q = 0; q < eng->gather_world; q++)
+    if (eng->peers[q]) CK(cudaMemcpyAsync((char*)eng->peers[q] + off, forces_dev, bytes, cudaMemcpyDeviceToDevice, st));
+  return mpc_batch_gather_sync_slot(eng, slot, st);
+}
 
 void* mpc_batch_gather_buffer(mpc_batch_t* eng) { return eng ? eng->gather_buf : nullptr; }
 void* mpc_batch_gather_buffer_slot(mpc_batch_t* eng, int slot) {

@@ -29,7 +29,7 @@ BATCH_SYMBOLS = ["mpc_record_stride", "mpc_record_gait_offset", "mpc_batch_creat
                  "mpc_batch_assemble_device", "mpc_batch_build_records_device", "mpc_batch_solve_ticks_device",
                  "mpc_batch_gait_state_device", "mpc_batch_leg_commands_device",
                  "mpc_batch_set_gather_peers", "mpc_batch_gather_alloc", "mpc_batch_gather_connect",
-                 "mpc_batch_gather_buffer", "mpc_batch_gather_buffer_slot", "mpc_batch_gather_sync", "mpc_batch_gather_sync_slot", "mpc_batch_set_max_iterations", "mpc_batch_set_warm_start", "mpc_batch_warm_stride", "mpc_batch_set_sweep_variant", "mpc_batch_sweep_variant", "mpc_batch_set_solver", "mpc_batch_solver", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
+                 "mpc_batch_gather_buffer", "mpc_batch_gather_buffer_slot", "mpc_batch_gather_sync", "mpc_batch_gather_sync_slot", "mpc_batch_set_gather_fused", "mpc_batch_gather_push_slot", "mpc_batch_set_max_iterations", "mpc_batch_set_warm_start", "mpc_batch_warm_stride", "mpc_batch_set_sweep_variant", "mpc_batch_sweep_variant", "mpc_batch_set_solver", "mpc_batch_solver", "mpc_batch_set_timing", "mpc_batch_set_timed_class", "mpc_batch_set_phase_clock_buffer", "mpc_batch_set_ctas_per_sm_limit",
                  "mpc_batch_num_classes", "mpc_batch_class_info", "mpc_batch_kernel_launches",
                  "mpc_batch_last_solve_kernel_ms", "mpc_batch_last_class_kernel_ms", "mpc_batch_timing_mark",
                  "mpc_batch_timing_collect", "mpc_batch_host_buffers", "mpc_batch_device_buffers",
@@ -94,6 +94,8 @@ def lib():
     L.mpc_batch_gather_alloc.argtypes = [vp, i32, vp]
     L.mpc_batch_gather_connect.argtypes = [vp, vp, i32, i32, i32]
     L.mpc_batch_gather_sync.argtypes = [vp, vp]
+    L.mpc_batch_set_gather_fused.argtypes = [vp, i32]
+    L.mpc_batch_gather_push_slot.argtypes = [vp, i32, vp, i32, vp]
     L.mpc_batch_gather_buffer.argtypes = [vp]
     L.mpc_batch_gather_buffer.restype = vp
     L.mpc_batch_set_max_iterations.argtypes = [vp, i32]
@@ -324,6 +326,19 @@ class MpcBatch:
             views.append(torch.as_tensor(self._gather_keepalive[-1], device=torch.device("cuda", self.device)))
         self.gather_views = views   # one [world_batch, 12] view per scratch slot
         return views[0]
+
+    def set_gather_fused(self, on):
+        """True (default after setup_peer_gather): the solve kernels store the forces into every rank's gather buffer
+        themselves; False: the gather is made by gather_push (copy engines)."""
+        self._check(self._L.mpc_batch_set_gather_fused(self._h, int(bool(on))), "set_gather_fused")
+
+    def gather_push(self, forces, slot=0, stream=None):
+        """Copy-engine gather of this rank's forces [B, 12] (cuda float32) into region `slot` of every rank's gather
+        buffer + the device-side cross-rank barrier, queued on `stream` (default: current)."""
+        torch = _torch()
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self._check(self._L.mpc_batch_gather_push_slot(self._h, int(slot), forces.data_ptr(), int(forces.shape[0]),
+                                                       st.cuda_stream), "mpc_batch_gather_push_slot")
 
     def gather_sync(self, stream=None, slot=0):
         """Device-side cross-rank barrier of the fused gather for scratch slot `slot`, queued on `stream`

@@ -1,4 +1,5 @@
-"""Run under torchrun with 2+ GPUs: checks the fused peer-store gather against the NCCL all-gather."""
+"""Run under torchrun with 2+ GPUs: checks the fused peer-store gather and the copy-engine gather against the NCCL
+all-gather."""
 import os
 import sys
 
@@ -51,8 +52,30 @@ for pair in range(3):
         torch.cuda.synchronize()
         ok = ok and bool(torch.equal(snaps[q], ref_r))
     dist.barrier()
-print("rank %d: peer-store gather %s NCCL all-gather (%d rows, both slots)" % (rank, "==" if ok else "!=", world * B),
-      flush=True)
+# the copy-engine gather: epilogue off, this rank's forces pushed into every rank's region by DMA on a stream of its
+# own, then the same flag barrier -- several epochs on two regions, against NCCL
+eng.set_gather_fused(False)
+comm = torch.cuda.Stream()
+ok_push = True
+for rep in range(4):
+    q = rep & 1
+    rec_r = torch.from_numpy(W.config2(B, h, 1300 + rank + 10 * rep)).to(dev)
+    torch.cuda.current_stream().synchronize()
+    with torch.cuda.stream(streams[q]):
+        f_r, _, _ = eng.solve_device(rec_r, stream=streams[q], slot=q)
+    comm.wait_stream(streams[q])
+    with torch.cuda.stream(comm):
+        eng.gather_push(f_r, slot=q, stream=comm)
+        snap = eng.gather_views[q].clone()   # stream-ordered behind the barrier
+    torch.cuda.synchronize()
+    ref_r = torch.empty_like(ref)
+    dist.all_gather_into_tensor(ref_r, f_r)
+    torch.cuda.synchronize()
+    ok_push = ok_push and bool(torch.equal(snap, ref_r))
+    dist.barrier()
+print("rank %d: peer-store gather %s NCCL all-gather, copy-engine gather %s NCCL all-gather (%d rows, both slots)" %
+      (rank, "==" if ok else "!=", "==" if ok_push else "!=", world * B), flush=True)
+ok = ok and ok_push
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 eng.close()
