@@ -690,6 +690,7 @@ struct mpc_batch {
   int solver = MPC_SOLVER_DEFAULT;  // 0: explicit inverse of the condensed Hessian; 1: Riccati sweeps (mpc_riccati.h)
   int debug_stop = 0;
   int ric_generic = 0;
+  bool ric_always = false;  // env MPC_RIC_ALWAYS: small batches too (tests of the kernel under compute-sanitizer)
   bool no_host_classify = false;  // env MPC_NO_HOST_CLASSIFY: batches of one take the general path too
   void* peer_open[kMaxPeers] = {nullptr};
   std::string err;
@@ -1040,7 +1041,7 @@ void fill_params(const mpc_batch* eng, int slot, SolveParams& P, const void* rec
 // latency problem, and there 128 threads on one problem finish sooner than 32 (27 us against 37 us per trot tick).
 bool use_riccati(const mpc_batch* eng, const ClassCfg& c, bool assemble_only, int batch = -1) {
   if (!(c.ric && eng->solver == 1 && !eng->phase_clk && !eng->debug_stop && !assemble_only && !eng->warm_cache)) return false;
-  if (batch >= 0 && c.variant != V_WRENCH && batch <= (c.pipe ? c.pipe_grid : c.grid)) return false;
+  if (batch >= 0 && c.variant != V_WRENCH && batch <= (c.pipe ? c.pipe_grid : c.grid) && !eng->ric_always) return false;
   return true;
 }
 
@@ -1338,6 +1339,7 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
   } while (0)
   if (const char* ds = getenv("MPC_DEBUG_STOP")) eng->debug_stop = atoi(ds);
   if (const char* rg = getenv("MPC_RIC_GENERIC")) eng->ric_generic = atoi(rg);
+  if (const char* ra = getenv("MPC_RIC_ALWAYS")) eng->ric_always = atoi(ra) != 0;
   eng->no_host_classify = getenv("MPC_NO_HOST_CLASSIFY") != nullptr;
   if (const char* sw = getenv("MPC_SWEEP")) eng->sweep = (sw[0] == 'm' || sw[0] == '1') ? 1 : 0;  // "mma" / "fma"
   if (const char* sv = getenv("MPC_SOLVER")) eng->solver = (sv[0] == 'r' || sv[0] == '1') ? 1 : 0;  // "riccati" / "inverse"
