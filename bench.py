@@ -460,6 +460,9 @@ def run_ours(args):
     # processes whose launch jitter otherwise stalls every slot on the slowest rank's previous gather.
     push = world > 1 and args.gather == "push"
     nbuf = nq * (args.outbufs if (world > 1 and not peer and not push) else 1)
+    if push:   # the engine has one gather region per scratch slot (six): a rank may run that many batches ahead of the
+        nbuf = max(nq, min(E.SLOTS, nq * args.pushbufs))   # slowest rank's gather instead of nq
+
     forces2 = [torch.empty((B, 12), dtype=torch.float32, device=dev) for _ in range(nbuf)]
     status2 = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(nbuf)]
     gathered2 = [torch.empty((world * B, 12), dtype=torch.float32, device=dev) for _ in range(nbuf)] if world > 1 else None
@@ -759,6 +762,7 @@ def main():
     ap.add_argument("--solver", default=os.environ.get("MPC_SOLVER", "riccati"), choices=["riccati", "inverse"],
                     help="riccati: sweeps over the horizon, no condensed Hessian (default); inverse: explicit inverse of "
                          "the reduced condensed Hessian")
+    ap.add_argument("--pushbufs", type=int, default=2, help="N>1, push gather: output sets / gather regions per scratch slot")
     ap.add_argument("--outbufs", type=int, default=1, help="N>1, NCCL gather: output sets per scratch slot")
     ap.add_argument("--comm-priority", type=int, default=1, help="N>1: 1 = the NCCL gather runs on a high-priority stream")
     ap.add_argument("--gather", default="push", choices=["push", "nccl", "peer", "none"],
