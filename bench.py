@@ -469,9 +469,24 @@ def run_ours(args):
     if peer or push:
         # peer: the solve kernel stores every force straight into all ranks' gather buffers over NVLink (fused epilogue);
         # push: the copy engines do it after the solve (no SM takes part) -- both end with a device-side flag barrier
-        eng.setup_peer_gather(world * B, rank * B)
-        eng.set_gather_fused(peer)
-        gathered2 = eng.gather_views   # one region per scratch slot
+        try:
+            eng.setup_peer_gather(world * B, rank * B)
+            ipc_ok = 1
+        except E.MpcError as exc:      # no CUDA IPC between the ranks (container restrictions): NCCL gather instead
+            print("bench.py: peer mappings unavailable (%s) -- falling back to --gather nccl" % exc, file=sys.stderr)
+            ipc_ok = 0
+        flag = torch.tensor([ipc_ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)   # every rank takes the same path
+        if int(flag.item()) == 1:
+            eng.set_gather_fused(peer)
+            gathered2 = eng.gather_views   # one region per scratch slot
+        else:
+            peer = push = False
+            args.gather = "nccl"
+            nbuf = nq * args.outbufs
+            forces2 = [torch.empty((B, 12), dtype=torch.float32, device=dev) for _ in range(nbuf)]
+            status2 = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(nbuf)]
+            gathered2 = [torch.empty((world * B, 12), dtype=torch.float32, device=dev) for _ in range(nbuf)]
     # NCCL gather on a stream of its own: the next batch's kernels never queue behind the collective
     nogather = world > 1 and args.gather == "none"   # diagnosis only: what the step costs without its gather
     comm = torch.cuda.Stream(dev, priority=-1 if args.comm_priority else 0) if world > 1 and not peer and not nogather else None
