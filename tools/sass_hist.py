@@ -3,7 +3,7 @@
   python tools/sass_hist.py quadruped_ctrl_b200/libquadruped_mpc_b200.so > profiles/r2_sass_opcodes.txt
 Per kernel: instruction count, SASS bytes, and the counts of the opcodes that identify which units the kernel uses
 (DFMA/DMUL/DADD: FP64 FMA pipe; DMMA: FP64 tensor pipe; UBLKCP / SYNCS: TMA bulk copy + mbarrier; LDS/STS: shared memory;
-SHFL; BAR / WARPSYNC; MUFU.RCP64H)."""
+SHFL; CREDUX: warp-wide integer reductions; BAR / WARPSYNC; MUFU.RCP64H)."""
 import re
 import subprocess
 import sys
@@ -24,7 +24,7 @@ for ln in out.splitlines():
         kern[cur][m.group(1)] += 1
 dem = subprocess.run(["cu++filt"] + list(kern), capture_output=True, text=True).stdout.splitlines()
 KEYS = ["DFMA", "DMUL", "DADD", "DMMA", "UBLKCP", "SYNCS", "LDS", "STS", "LDG", "STG", "SHFL", "BAR", "WARPSYNC", "MUFU",
-        "REDUX", "ATOMG", "HMMA", "UTCHMMA", "UTMALDG"]
+        "CREDUX", "REDUX", "ATOMG", "HMMA", "UTCHMMA", "UTMALDG"]
 for (name, c), d in zip(kern.items(), dem if len(dem) == len(kern) else list(kern)):
     n = sum(c.values())
     fam = Counter()
