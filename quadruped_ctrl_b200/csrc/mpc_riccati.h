@@ -19,11 +19,19 @@
 // z = d - Z r.  On the BASELINE workloads a problem changes its working set 2 (trot, horizon 10) to 14 times
 // (horizon 20, mixed gaits), so a solve is one factorisation and a handful of sweeps.
 //
-// Execution model: ONE WARP PER PROBLEM (no CTA barrier anywhere; __syncwarp only), written against the same tiny
-// execution context as mpc_core.h, so the single-thread host build of tests/emu/ runs the very same source.
+// Execution model: ONE WARP PER PROBLEM (no CTA barrier anywhere; __syncwarp only).  The algorithm is written once
+// against the same tiny execution context as mpc_core.h (ric_setup, ric_factor, ric_forward, ric_hinv_row,
+// ric_active_set: strided loops, one barrier per phase), and that generic form is what the single-thread host build of
+// tests/emu/ runs and what MPC_RIC_GENERIC=1 runs on the device.  The production kernel replaces the two hot parts by
+// device-only forms that compute the same quantities:
+//   ric_factor_mma      the factorisation on the FP64 tensor pipe (DMMA.8x8x4 on 8x8 tiles, the tracking sweep riding
+//                       along in the tile padding, S swept in registers),
+//   ric_forward_fast /  the sweeps with the travelling 12-vector in registers (lane i owns component i), two phases
+//   ric_hinv_row_fast   of one __syncwarp per horizon step.
+// Working sets that outgrow the fast-memory tile of Z move into a per-warp global slab and carry on (ric_active_set).
 // Exactness: A_d = I + dt A + dt^2/2 A^2 and B_d = dt B + dt^2/2 AB + dt^3/6 A^2 B are exact (A^3 = 0, see
 // mpc_core.h); results agree with the reference's qpOASES on the fp64-assembled dense QP to ~1e-13 relative
-// (tests/test_riccati.py, tests/test_gpu_parity.py).
+// (tests/test_riccati.py on the host build, tests/test_gpu_parity.py on the kernel, both solvers).
 #ifndef QUADRUPED_MPC_RICCATI_H
 #define QUADRUPED_MPC_RICCATI_H
 
