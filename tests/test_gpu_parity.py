@@ -228,6 +228,41 @@ def test_status_codes_and_failure_outputs(solver, cuda_engine_factory):
 
 
 @pytest.mark.parametrize("solver", ["riccati", "inverse"])
+def test_mixed_stance_counts_flight_phases_x_drag_and_singular_hessian(solver, oracle, cuda_engine_factory):
+    """Random contact tables (0 to 4 stance legs per step: 0, 3, 6, 9 or 12 controls -- every tile shape of the Riccati
+    factorisation, flight phases included), x_drag != 0 (the sparse part of A_d, SolverMPC.cpp:241) and a singular
+    Hessian (alpha = 0 with zero weights -> NOT_PD), in batches large enough to run the production kernel of each
+    solver."""
+    from quadruped_ctrl_b200 import records as R
+    h, B = 10, 1536
+    rec = W.config2(B, h, 31)
+    go = R.gait_offset(h)
+    rng = np.random.default_rng(7)
+    gait = (rng.random((B, h, 4)) < 0.4).astype(np.uint8)
+    gait[:, 2] = 0                      # a flight phase in every problem
+    gait[: B // 2, 6] = 1               # a four-stance step in half of them
+    rec[:, go:go + 4 * h] = gait.reshape(B, -1)
+    f = rec.view(np.float32)
+    f[:, R.REC_XDRAG] = rng.uniform(-0.8, 0.9, B).astype(np.float32)
+    eng = cuda_engine_factory(h, B, solver)
+    forces, sol, status = eng.solve_host(rec, want_solution=True)
+    assert (E.status_code(status) == E.STATUS_OPTIMAL).all(), np.bincount(E.status_code(status))
+    idx = np.sort(rng.choice(B, 256, replace=False))
+    o = oracle.solve_batch(rec[idx], h, 64)
+    ok = o["rc"] == 0
+    assert ok.sum() > 200 and rel(sol[idx], o["sol"])[ok].max() < 1e-9
+    bad = W.config2(1024, h, 5)
+    fb = bad.view(np.float32)
+    fb[:7, R.REC_ALPHA] = 0.0
+    fb[:7, R.REC_WEIGHTS:R.REC_WEIGHTS + 12] = 0.0
+    eng2 = cuda_engine_factory(h, 1024, solver)
+    f2, s2, st2 = eng2.solve_host(bad, want_solution=True)
+    code = E.status_code(st2)
+    assert (code[:7] == E.STATUS_NOT_PD).all() and (code[7:] == E.STATUS_OPTIMAL).all()
+    assert (f2[:7] == 0).all() and (s2[:7] == 0).all()
+
+
+@pytest.mark.parametrize("solver", ["riccati", "inverse"])
 def test_full_size_properties(solver, cuda_engine_factory):
     """BASELINE sizes (B=4096 config 2; B=65536 config 4 shard-free) through size-independent properties:
     every problem optimal, swing legs exactly zero, friction pyramid and force limits hold, a permuted batch
