@@ -59,6 +59,7 @@ struct SolveParams {
   mpc::Layout L;
   mpc::RicLayout RL;  // workspace of the Riccati solver (mpc_solve_riccati_kernel)
   char* ric_slab;     // [grid][RL.slab_bytes] global scratch for working sets that outgrow the Riccati tile
+  int* ric_queue;     // {next, done}: dynamic problem queue of the Riccati kernel (nullptr: static stride)
   int ric_generic;    // development switch (env MPC_RIC_GENERIC): the scalar generic factorisation instead of the DMMA one
   int max_iter;
   int warp_mode;
@@ -573,8 +574,12 @@ __global__ void __launch_bounds__(32, 12) mpc_solve_riccati_kernel(const __grid_
   const uint32_t rec_bytes = (uint32_t)P.stride;
   const float* rec = (const float*)recbuf;
   const unsigned char* gait = (const unsigned char*)rec + 4 * (MPC_REC_TRAJ + 12 * P.h);
+  // Problems differ by a factor of five in work (0 ... 11 working-set changes on a trot batch), and a 4096-batch is
+  // only 2.5 problems per resident warp: after its first problem (its block index, no atomic) a warp takes the next
+  // one from a queue instead of a fixed stride.  The last warp to leave resets the queue for the next launch on this
+  // slot (launches of one slot and class are stream-ordered).
   int it = 0;
-  for (int item = blockIdx.x; item < count; item += gridDim.x, it++) {
+  for (int item = blockIdx.x; item < count; it++) {
     const int b = P.list ? P.list[item] : item;
     if (lane == 0) {  // the buffer was released by the __syncwarp that ended the last pass
       mbar_expect_tx(&bar[0], rec_bytes);
@@ -599,6 +604,22 @@ __global__ void __launch_bounds__(32, 12) mpc_solve_riccati_kernel(const __grid_
       }
     }
     __syncwarp();
+    if (P.ric_queue) {
+      int nxt = 0;
+      if (lane == 0) nxt = (int)gridDim.x + atomicAdd(P.ric_queue, 1);
+      item = __shfl_sync(0xffffffffu, nxt, 0);
+    } else {
+      item += gridDim.x;
+    }
+  }
+  if (P.ric_queue && lane == 0) {
+    const int target = min((int)gridDim.x, count);  // the warps that took part (the others left at the top)
+    __threadfence();
+    if (atomicAdd(P.ric_queue + 1, 1) == target - 1) {
+      P.ric_queue[0] = 0;
+      P.ric_queue[1] = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -647,6 +668,7 @@ struct mpc_batch {
     int parity = 0;
     char* slab = nullptr;   // per-CTA global workspace of the catch-all class
     char* ric_slab = nullptr;  // per-warp global workspace of the Riccati classes (working sets beyond the tile)
+    int* ric_queue = nullptr;  // [kMaxClasses][2] {next, done} of the Riccati kernel's dynamic problem queue
     int pending_batch = 0;
     bool pending_solution = false;
     int pending_single_class = -1;  // >= 0: the pending solve was host-classified (every problem in that class)
@@ -687,6 +709,9 @@ struct mpc_batch {
   int warm_shift = 1;
   int sweep = MPC_SWEEP_DEFAULT;  // inversion of the register-resident classes: 0 FMA tiles, 1 DMMA grouped sweep
   char* cur_ric_slab = nullptr;  // the Riccati slab of the slot whose solve is being queued (set by solve_on_stream)
+  int* cur_ric_queue = nullptr;  // ... and its queue counters; cur_class: the class being launched
+  int cur_class = 0;
+  bool ric_dynamic = true;       // env MPC_RIC_STATIC=1: static stride instead of the queue
   int solver = MPC_SOLVER_DEFAULT;  // 0: explicit inverse of the condensed Hessian; 1: Riccati sweeps (mpc_riccati.h)
   int debug_stop = 0;
   int ric_generic = 0;
@@ -1051,6 +1076,7 @@ int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int gr
     SolveParams Pr = P;
     Pr.RL = c.ric_L;
     Pr.ric_slab = eng->cur_ric_slab;
+    Pr.ric_queue = (eng->ric_dynamic && eng->cur_ric_queue) ? eng->cur_ric_queue + 2 * eng->cur_class : nullptr;
     if (eng->ric_generic) mpc_solve_riccati_kernel<true><<<grid, 32, c.ric_smem, st>>>(Pr);
     else mpc_solve_riccati_kernel<false><<<grid, 32, c.ric_smem, st>>>(Pr);
     eng->launches++;
@@ -1181,7 +1207,9 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
   const int nc = (int)eng->classes.size();
   mpc_batch::Slot& S = eng->s[slot];
   eng->cur_ric_slab = S.ric_slab;
+  eng->cur_ric_queue = S.ric_queue;
   if (single_class >= 0) {
+    eng->cur_class = single_class;
     const ClassCfg& c = eng->classes[single_class];
     SolveParams P;
     fill_params(eng, slot, P, records, batch, forces, solution, status);
@@ -1227,6 +1255,7 @@ int solve_on_stream(mpc_batch* eng, int slot, const void* records, int batch, fl
     const size_t ring = (size_t)(eng->ring_pos % kRing) * kMaxClasses + ci;
     const bool time_this = eng->timed && (eng->timed_class < 0 || eng->timed_class == ci);
     if (time_this) CK(cudaEventRecord(eng->ring0[ring], st));
+    eng->cur_class = ci;
     const bool piped = c.pipe && !eng->phase_clk && !H_out && !eng->debug_stop;
     int grid = std::min(use_riccati(eng, c, H_out != nullptr, batch) ? c.ric_grid : piped ? c.pipe_grid : c.grid, batch);
     if (eng->ctas_per_sm_limit > 0) grid = std::min(grid, eng->ctas_per_sm_limit * eng->sms);
@@ -1281,6 +1310,8 @@ int ensure_slot(mpc_batch* eng, int q) {
   for (const ClassCfg& c : eng->classes)
     if (c.ric) ric_bytes = std::max(ric_bytes, c.ric_L.slab_bytes * (size_t)std::min<long long>(c.ric_grid, eng->max_batch));
   if (ric_bytes) CKS(cudaMalloc(&S.ric_slab, ric_bytes));
+  CKS(cudaMalloc(&S.ric_queue, sizeof(int) * 2 * kMaxClasses));
+  CKS(cudaMemset(S.ric_queue, 0, sizeof(int) * 2 * kMaxClasses));
   S.stream = st;  // last: marks the slot as complete
 #undef CKS
   return MPC_OK;
@@ -1340,6 +1371,7 @@ int mpc_batch_create(mpc_batch_t** out, int device, int horizon, int max_batch) 
   if (const char* ds = getenv("MPC_DEBUG_STOP")) eng->debug_stop = atoi(ds);
   if (const char* rg = getenv("MPC_RIC_GENERIC")) eng->ric_generic = atoi(rg);
   if (const char* ra = getenv("MPC_RIC_ALWAYS")) eng->ric_always = atoi(ra) != 0;
+  if (const char* rs = getenv("MPC_RIC_STATIC")) eng->ric_dynamic = atoi(rs) == 0;
   eng->no_host_classify = getenv("MPC_NO_HOST_CLASSIFY") != nullptr;
   if (const char* sw = getenv("MPC_SWEEP")) eng->sweep = (sw[0] == 'm' || sw[0] == '1') ? 1 : 0;  // "mma" / "fma"
   if (const char* sv = getenv("MPC_SOLVER")) eng->solver = (sv[0] == 'r' || sv[0] == '1') ? 1 : 0;  // "riccati" / "inverse"
@@ -1389,6 +1421,7 @@ void mpc_batch_destroy(mpc_batch_t* eng) {
     cudaFree(S.counts);
     cudaFree(S.slab);
     cudaFree(S.ric_slab);
+    cudaFree(S.ric_queue);
     if (S.stream) cudaStreamDestroy(S.stream);
   }
   cudaFree(eng->caps_dev);
