@@ -568,7 +568,9 @@ def run_ours(args):
     join()
     barrier()
     k_alone = [eng.timing_collect(c) for c in range(len(classes))]
-    dominant = int(np.argmax([ms for ms, _ in k_alone]))
+    # (among the classes the host counts problems in: the overflow class only receives re-queued problems, a handful
+    # of CTAs whose latency says nothing about the batch)
+    dominant = int(np.argmax([ms if per_class[c] > 0 else -1.0 for c, (ms, _) in enumerate(k_alone)]))
     eng.set_timed_class(dominant)
 
     def optimal_fraction():

@@ -77,6 +77,7 @@ struct Layout {
 
 struct Scalars {
   int nv, ns, m, status, iters, p, kdrop, full, done;
+  int next_item;  // hand-over slot of the kernels' dynamic problem queue (thread 0 -> CTA); not part of the algorithm
   double sp, t1, t2, t, up, vnp, znp, dreg;
 };
 

@@ -59,7 +59,7 @@ struct SolveParams {
   mpc::Layout L;
   mpc::RicLayout RL;  // workspace of the Riccati solver (mpc_solve_riccati_kernel)
   char* ric_slab;     // [grid][RL.slab_bytes] global scratch for working sets that outgrow the Riccati tile
-  int* ric_queue;     // {next, done}: dynamic problem queue of the Riccati kernel (nullptr: static stride)
+  int* queue;         // {next, done}: dynamic problem queue of the persistent solve kernels (nullptr: static stride)
   int ric_generic;    // development switch (env MPC_RIC_GENERIC): the scalar generic factorisation instead of the DMMA one
   int max_iter;
   int warp_mode;
@@ -217,6 +217,25 @@ __device__ __forceinline__ void peer_store_forces(const SolveParams& P, int b, i
   }
 }
 
+// Dynamic problem queue of the persistent solve kernels.  Problems of one class differ widely in work (0 ... 70
+// working-set changes), so after its first problem (its block index, no atomic) a CTA takes the next one from an atomic
+// counter instead of a fixed stride; the ticket is taken by thread 0 when it prefetches the next record and handed to
+// the CTA through shared memory.  The last CTA to leave resets the counters for the next launch on this slot and class
+// (those launches are stream-ordered).
+__device__ __forceinline__ int queue_take(const SolveParams& P, int item) {
+  return P.queue ? (int)gridDim.x + atomicAdd(P.queue, 1) : item + (int)gridDim.x;
+}
+__device__ __forceinline__ void queue_leave(const SolveParams& P, int count) {
+  if (!P.queue) return;
+  const int target = min((int)gridDim.x, count);  // the CTAs that took part (the others left at the top)
+  __threadfence();
+  if (atomicAdd(P.queue + 1, 1) == target - 1) {
+    P.queue[0] = 0;
+    P.queue[1] = 0;
+    __threadfence();
+  }
+}
+
 // NT threads per CTA.  R > 0: register-resident inversion with R x C tiles on a GR x GC thread grid (NT == GR*GC,
 // padded size GR*R == GC*C).  R == 0: the generic shared/global-memory sweep, used by the catch-all class whose
 // matrix does not fit in the register file of one SM.
@@ -247,13 +266,19 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
     mbar_expect_tx(&bar[0], rec_bytes);
     tma_bulk_g2s(recbuf, P.records + P.stride * b0, rec_bytes, &bar[0]);
   }
-  for (int it = 0; item < count; item += gridDim.x, it++) {
+  int& s_next = k.sc->next_item;  // (dynamic shared memory: a static __shared__ variable would lower the opt-in limit)
+  int nxt = 0;
+  for (int it = 0; item < count; item = nxt, it++) {
     const int cur = it & 1;
-    const int next = item + gridDim.x;
-    if (threadIdx.x == 0 && next < count) {  // buffer cur^1 was released by the barrier that ended the last pass
-      const int bn = P.list ? P.list[next] : next;
-      mbar_expect_tx(&bar[cur ^ 1], rec_bytes);
-      tma_bulk_g2s(recbuf + (size_t)(cur ^ 1) * P.stride, P.records + P.stride * bn, rec_bytes, &bar[cur ^ 1]);
+    nxt = item + gridDim.x;  // static stride (the profiling entries, whose early `continue`s skip the hand-over below)
+    if (threadIdx.x == 0) {  // buffer cur^1 was released by the barrier that ended the last pass
+      const int next = PROF ? nxt : queue_take(P, item);
+      s_next = next;
+      if (next < count) {
+        const int bn = P.list ? P.list[next] : next;
+        mbar_expect_tx(&bar[cur ^ 1], rec_bytes);
+        tma_bulk_g2s(recbuf + (size_t)(cur ^ 1) * P.stride, P.records + P.stride * bn, rec_bytes, &bar[cur ^ 1]);
+      }
     }
     mbar_wait(&bar[cur], (uint32_t)((it >> 1) & 1));
     const int b = P.list ? P.list[item] : item;
@@ -342,7 +367,8 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
         peer_store_forces(P, b, (int)threadIdx.x);
       }
     }
-    __syncthreads();
+    if constexpr (!PROF) nxt = s_next;  // (written at the top of this pass, CTA barriers in between; read before the
+    __syncthreads();                    //  barrier that lets thread 0 overwrite it)
     if (clk && threadIdx.x == 0) {
       unsigned wid, sid;
       asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
@@ -350,6 +376,7 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_kernel(const __grid_consta
       clk[4] = clock64(); clk[5] = blockIdx.x; clk[6] = it; clk[7] = (long long)(sid << 8 | wid);
     }
   }
+  if constexpr (!PROF) if (threadIdx.x == 0) queue_leave(P, count);
 }
 
 // ---- two problems in flight per CTA (the smallest class, production instantiation) --------------------------------
@@ -390,6 +417,7 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
     mbar_expect_tx(&bar[0], rec_bytes);
     tma_bulk_g2s(recbuf, P.records + P.stride * b0, rec_bytes, &bar[0]);
   }
+  int& s_next = mpc::carve(P.L, fast, nullptr, 0).sc->next_item;
   int prev_b = -1;  // problem whose active set is still to run (its state sits in set (it-1)&1, its record in buffer (it-1)&1)
   for (int it = 0;; it++) {
     const int cur = it & 1;
@@ -434,11 +462,14 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
     __syncthreads();
     if (!have) break;
     const int b = P.list ? P.list[item] : item;
-    const int next = item + gridDim.x;
-    if (tid == 0 && next < count) {  // buffer cur^1 is free now: the previous problem's active set is done with it
-      const int bn = P.list ? P.list[next] : next;
-      mbar_expect_tx(&bar[cur ^ 1], rec_bytes);
-      tma_bulk_g2s(recbuf + (size_t)(cur ^ 1) * P.stride, P.records + P.stride * bn, rec_bytes, &bar[cur ^ 1]);
+    if (tid == 0) {  // buffer cur^1 is free now: the previous problem's active set is done with it
+      const int next = queue_take(P, item);
+      s_next = next;
+      if (next < count) {
+        const int bn = P.list ? P.list[next] : next;
+        mbar_expect_tx(&bar[cur ^ 1], rec_bytes);
+        tma_bulk_g2s(recbuf + (size_t)(cur ^ 1) * P.stride, P.records + P.stride * bn, rec_bytes, &bar[cur ^ 1]);
+      }
     }
     // ---- phase Y: H blocks, inversion, active-set set-up (all warps) ----
     const mpc::Work k = mpc::carve(P.L, fast, nullptr, cur);
@@ -461,8 +492,9 @@ __global__ void __launch_bounds__(NT, MINB) mpc_solve_pipe_kernel(const __grid_c
       prev_b = -1;
       __syncthreads();
     }
-    item = next;
+    item = s_next;  // (handed over through the CTA barriers of phase Y; overwritten only after the next phase-X barrier)
   }
+  if (tid == 0) queue_leave(P, count);
 }
 
 // ---- wrench-space class: problems with more reduced variables than the register-resident classes hold (nv > 128)
@@ -496,13 +528,19 @@ __global__ void __launch_bounds__(256, MINB) mpc_solve_wrench_kernel(const __gri
     tma_bulk_g2s(recbuf, P.records + P.stride * b0, rec_bytes, &bar[0]);
   }
   const int n = 6 * P.h;
-  for (int it = 0; item < count; item += gridDim.x, it++) {
+  int& s_next = k.sc->next_item;
+  int nxt = 0;
+  for (int it = 0; item < count; item = nxt, it++) {
     const int cur = it & 1;
-    const int next = item + gridDim.x;
-    if (tid == 0 && next < count) {
-      const int bn = P.list ? P.list[next] : next;
-      mbar_expect_tx(&bar[cur ^ 1], rec_bytes);
-      tma_bulk_g2s(recbuf + (size_t)(cur ^ 1) * P.stride, P.records + P.stride * bn, rec_bytes, &bar[cur ^ 1]);
+    nxt = item + gridDim.x;  // static stride (the profiling instantiation)
+    if (tid == 0) {
+      const int next = PROF ? nxt : queue_take(P, item);
+      s_next = next;
+      if (next < count) {
+        const int bn = P.list ? P.list[next] : next;
+        mbar_expect_tx(&bar[cur ^ 1], rec_bytes);
+        tma_bulk_g2s(recbuf + (size_t)(cur ^ 1) * P.stride, P.records + P.stride * bn, rec_bytes, &bar[cur ^ 1]);
+      }
     }
     mbar_wait(&bar[cur], (uint32_t)((it >> 1) & 1));
     const int b = P.list ? P.list[item] : item;
@@ -545,8 +583,10 @@ __global__ void __launch_bounds__(256, MINB) mpc_solve_wrench_kernel(const __gri
         peer_store_forces(P, b, tid);
       }
     }
+    if constexpr (!PROF) nxt = s_next;
     __syncthreads();
   }
+  if constexpr (!PROF) if (tid == 0) queue_leave(P, count);
 }
 
 // ---- Riccati solver (csrc/mpc_riccati.h): ONE WARP PER PROBLEM ------------------------------------------------
@@ -604,23 +644,11 @@ __global__ void __launch_bounds__(32, 12) mpc_solve_riccati_kernel(const __grid_
       }
     }
     __syncwarp();
-    if (P.ric_queue) {
-      int nxt = 0;
-      if (lane == 0) nxt = (int)gridDim.x + atomicAdd(P.ric_queue, 1);
-      item = __shfl_sync(0xffffffffu, nxt, 0);
-    } else {
-      item += gridDim.x;
-    }
+    int nxt = 0;
+    if (lane == 0) nxt = queue_take(P, item);
+    item = __shfl_sync(0xffffffffu, nxt, 0);
   }
-  if (P.ric_queue && lane == 0) {
-    const int target = min((int)gridDim.x, count);  // the warps that took part (the others left at the top)
-    __threadfence();
-    if (atomicAdd(P.ric_queue + 1, 1) == target - 1) {
-      P.ric_queue[0] = 0;
-      P.ric_queue[1] = 0;
-      __threadfence();
-    }
-  }
+  if (lane == 0) queue_leave(P, count);
 }
 
 struct ClassCfg {
@@ -1076,25 +1104,29 @@ int launch_solve(mpc_batch* eng, const ClassCfg& c, const SolveParams& P, int gr
     SolveParams Pr = P;
     Pr.RL = c.ric_L;
     Pr.ric_slab = eng->cur_ric_slab;
-    Pr.ric_queue = (eng->ric_dynamic && eng->cur_ric_queue) ? eng->cur_ric_queue + 2 * eng->cur_class : nullptr;
+    Pr.queue = (eng->ric_dynamic && eng->cur_ric_queue) ? eng->cur_ric_queue + 2 * eng->cur_class : nullptr;
     if (eng->ric_generic) mpc_solve_riccati_kernel<true><<<grid, 32, c.ric_smem, st>>>(Pr);
     else mpc_solve_riccati_kernel<false><<<grid, 32, c.ric_smem, st>>>(Pr);
     eng->launches++;
     CK(cudaGetLastError());
     return MPC_OK;
   }
+  int* const queue = (eng->ric_dynamic && eng->cur_ric_queue && !prof) ? eng->cur_ric_queue + 2 * eng->cur_class : nullptr;
   if (c.pipe && !prof) {
     SolveParams Pp = P;
     Pp.L = c.pipe_L;
+    Pp.queue = queue;
     MPC_PIPE_CALL(c.variant, eng->sweep, (kern<<<grid, c.threads, c.pipe_smem, st>>>(Pp)));
     eng->launches++;
     CK(cudaGetLastError());
     return MPC_OK;
   }
+  SolveParams Pq = P;
+  Pq.queue = queue;
   if (c.variant == V_WRENCH) {
-    MPC_WRENCH_CALL(prof, eng->sweep, !c.in_fast, (kern<<<grid, c.threads, c.smem, st>>>(P)));
+    MPC_WRENCH_CALL(prof, eng->sweep, !c.in_fast, (kern<<<grid, c.threads, c.smem, st>>>(Pq)));
   } else {
-    MPC_VARIANT_CALL(c.variant, prof, eng->sweep, (kern<<<grid, c.threads, c.smem, st>>>(P)));
+    MPC_VARIANT_CALL(c.variant, prof, eng->sweep, (kern<<<grid, c.threads, c.smem, st>>>(Pq)));
   }
   eng->launches++;
   CK(cudaGetLastError());
