@@ -627,6 +627,7 @@ def run_ours(args):
     e2e_bad = [0]
 
     e2e_gathered = [None] * nslots   # event: the gather out of the slot's device forces has finished
+    dev_f_B = [t[:B] for t in dev_f] if dev_f is not None else None
     e2e_comm = comm if comm is not None else (torch.cuda.Stream(dev) if world > 1 else None)
 
     def collect(slot):
@@ -634,14 +635,14 @@ def run_ours(args):
         checksum[0] += float(out_f[slot][0, 2])
         e2e_bad[0] += int((out_s[slot][:B] & 0xff != 0).sum())
         if world > 1 and not nogather:            # the forces are complete on the device (wait_host synchronised)
-            with torch.cuda.stream(e2e_comm):
-                if push:
-                    eng.gather_push(dev_f[slot][:B], slot=slot, stream=e2e_comm)
-                else:
-                    dist.all_gather_into_tensor(gathered2[0], dev_f[slot][:B])
-                ev = torch.cuda.Event()
-                ev.record(e2e_comm)
-            e2e_gathered[slot] = ev
+            if e2e_gathered[slot] is None:
+                e2e_gathered[slot] = torch.cuda.Event()
+            if push:
+                eng.gather_push(dev_f_B[slot], slot=slot, stream=e2e_comm)
+            else:
+                with torch.cuda.stream(e2e_comm):
+                    dist.all_gather_into_tensor(gathered2[0], dev_f_B[slot])
+            e2e_gathered[slot].record(e2e_comm)
 
     def e2e_run(n):
         for i in range(n):
