@@ -1,18 +1,21 @@
 // Batched convex-MPC engine for sm_100a: kernels + the C ABI of include/mpc_batch.h.
 //
 // Kernels
-//   mpc_classify_kernel  one thread per problem: counts stance (step,leg) pairs in the
-//                        gait table and appends the problem to the size class whose
-//                        shared-memory tile fits its reduced QP (nv = 3 * stance).
-//   mpc_solve_kernel<NT> persistent CTAs, one problem per CTA at a time.  Records are
-//                        staged global -> shared by TMA bulk copies (cp.async.bulk +
-//                        mbarrier, double buffered: the next record lands while the
-//                        current one is solved).  Assembly, inversion and the active-set
-//                        iterations (csrc/mpc_core.h) run entirely in shared memory; H
-//                        and g never touch HBM.  Only the record (4*(48+12h)+4h bytes)
-//                        is read and 12 fp32 forces (+ optional 12h fp64, status) written.
-// There is no CPU solver in this library: every entry point either runs these kernels or
-// fails with an error code.
+//   mpc_solve_riccati_kernel  the production kernel of the classes nv <= 60 / 96 (and <= 128 at horizons <= 12): ONE
+//                        WARP per problem, the QP solved without its condensed Hessian (csrc/mpc_riccati.h: Riccati
+//                        factorisation on the FP64 tensor pipe, H^{-1} products as sweeps over the horizon).
+//   mpc_solve_pipe_kernel / mpc_solve_kernel<NT>  the explicit-inverse solver (csrc/mpc_core.h), one problem per CTA
+//                        (two in flight in the piped form): long horizons, the single-robot tick, the warm start.
+//   mpc_solve_wrench_kernel   nv > 128 through the rank-6h structure of the Hessian.
+//   mpc_classify_kernel  one thread per problem: counts stance (step,leg) pairs in the gait table and appends the
+//                        problem to its size class (nv = 3 * stance); the host entries classify while they stage a
+//                        batch and launch ONE kernel when it is uniform.
+//   mpc_build_records_kernel / mpc_gait_state_kernel / mpc_leg_commands_kernel  the callers either side of the solve
+//                        (SURVEY 8f N1, N2, N4), one robot per thread.
+// All solve kernels are persistent: records are staged global -> shared by TMA bulk copies (cp.async.bulk + mbarrier),
+// problems are handed out by a dynamic queue, everything between the record (4*(48+12h)+4h bytes read) and the 12 fp32
+// forces (+ optional 12h fp64, status) written lives in shared memory / registers; H and g never touch HBM.
+// There is no CPU solver in this library: every entry point either runs these kernels or fails with an error code.
 #include <cuda_runtime.h>
 
 #include <algorithm>
