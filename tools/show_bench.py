@@ -14,6 +14,9 @@ for path in sys.argv[1:]:
             continue
         r = d.get("roofline", {})
         print("%s | %s" % (path, d["config"]["workload"][:60]))
+        print("   solver %s  collective: %s  host queue %s ms/step" % (
+            d["config"].get("solver"), str(d["config"].get("collective"))[:60],
+            "%.4f" % d["host_queue_ms_per_step"] if "host_queue_ms_per_step" in d else "-"))
         print("   value %.3f M/s  serial %s  e2e %.3f M/s  ms/step %.3f  n_gpus %d  launches %s  ok %s gather %s" % (
             d["value"] / 1e6, "%.3f" % (d["serial"]["value"] / 1e6) if "serial" in d else "-", d["e2e"]["value"] / 1e6,
             d["ms_per_step"], d["n_gpus"], d.get("gpu_launches"), d.get("results_ok"), d.get("gather_ok")))
