@@ -143,3 +143,37 @@ def test_x_drag_couples_through_the_sparse_part_of_A(oracle):
     o = oracle.solve_batch(rec, h, 64)
     ok = o["rc"] == 0
     assert (r["status"] == ST_OPT).all() and rel(r["sol"], o["sol"])[ok].max() < 1e-9
+
+
+def test_randomised_parameters_far_from_the_reference_defaults(oracle):
+    """Horizons 3 ... 14, random contact tables, alpha over 3.5 decades (down to 3e-7), weights over four decades with
+    a fifth of them zero, random dt / mu / f_max / mass / inertia / x_drag: both solvers stay optimal and agree with the
+    independent dense active-set port (the conditioning of these QPs reaches 1e9+: 1e-7 is what is asserted, ~1e-9 is
+    what is measured, the Riccati route usually the closer of the two)."""
+    rng = np.random.default_rng(123)
+    for trial in range(8):
+        h, B = int(rng.integers(3, 15)), 16
+        rec = W.config2(B, h, 1000 + trial)
+        f = rec.view(np.float32)
+        go = R.gait_offset(h)
+        gait = (rng.random((B, h, 4)) < rng.uniform(0.3, 0.9)).astype(np.uint8)
+        rec[:, go:go + 4 * h] = gait.reshape(B, -1)
+        f[:, R.REC_ALPHA] = 10 ** rng.uniform(-6.5, -3, B).astype(np.float32)
+        w = (10 ** rng.uniform(-2, 2.3, (B, 12))).astype(np.float32)
+        w[rng.random((B, 12)) < 0.2] = 0
+        f[:, R.REC_WEIGHTS:R.REC_WEIGHTS + 12] = w
+        f[:, R.REC_DT] = rng.uniform(0.01, 0.05, B).astype(np.float32)
+        f[:, R.REC_MU] = rng.uniform(0.2, 1.0, B).astype(np.float32)
+        f[:, R.REC_FMAX] = rng.uniform(40, 300, B).astype(np.float32)
+        f[:, R.REC_MASS] = rng.uniform(5, 40, B).astype(np.float32)
+        f[:, R.REC_IBODY:R.REC_IBODY + 3] = rng.uniform(0.03, 1.5, (B, 3)).astype(np.float32)
+        f[:, R.REC_XDRAG] = rng.uniform(-0.5, 0.5, B).astype(np.float32)
+        r = emu_solve_riccati(rec, h)
+        e = emu_solve(rec, h)
+        o = oracle.solve_batch(rec, h, 64, "port")
+        ok = o["rc"] == 0
+        some = ((r["status"] == ST_OPT) | (r["status"] == ST_NOSTANCE))
+        assert some.all() and (r["status"] == e["status"]).all()
+        assert ok.any()
+        assert rel(r["sol"], o["sol"])[ok].max() < 1e-7
+        assert rel(e["sol"], o["sol"])[ok].max() < 1e-7
